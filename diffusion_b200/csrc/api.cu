@@ -1,0 +1,273 @@
+// C-ABI entry points: context lifecycle, TMA tensor-map construction and the sd2_gemm host-side planner
+// (tile shape, split-K, tensor maps) in front of gemm_tc.cu.  See include/sd2b200.h for the contract.
+#include <mutex>
+
+#include "gemm_tc.cuh"
+#include "host.h"
+
+namespace sd2 {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4], std::string* err) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (!fn) {
+    if (err) *err = "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)";
+    return false;
+  }
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i < 3; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof(buf),
+               "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u,%u,%u)",
+               (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+               (unsigned long long)dims[3], (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+               (unsigned long long)strides_bytes[2], box[0], box[1], box[2], box[3]);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+// tensor map of a plain (possibly batched) operand; K-major box = (64, box_rows), MN-major box = (64, 64)
+static bool plain_tmap(CUtensorMap* tm, const sd2_operand& o, int box_rows, std::string* err) {
+  const uint64_t nb0 = o.nb0 > 0 ? (uint64_t)o.nb0 : 1, nb1 = o.nb0 > 0 && o.nb1 > 0 ? (uint64_t)o.nb1 : 1;
+  const uint64_t dims[4] = {(uint64_t)o.cols, (uint64_t)o.rows, nb0, nb1};
+  // strides must be non-zero multiples of 16 B even for extent-1 dims
+  const uint64_t s1 = (uint64_t)o.ld * 2;
+  const uint64_t s2 = nb0 > 1 ? (uint64_t)o.bs0 * 2 : s1 * (uint64_t)o.rows;
+  const uint64_t s3 = nb1 > 1 ? (uint64_t)o.bs1 * 2 : (nb0 > 1 ? s2 * nb0 : s2);
+  const uint64_t strides[3] = {s1, s2, s3};
+  const uint32_t box[4] = {64, (uint32_t)(o.mn_major ? 64 : box_rows), 1, 1};
+  return encode_tmap_bf16_4d(tm, o.ptr, dims, strides, box, err);
+}
+
+// pixel-box geometry of a shifted NHWC operand: `pixels` (128 for an M tile, 64 for a wgrad k-block) = W * th * nb
+static bool conv_box(const sd2_conv_geom& g, int pixels, int* th, int* nb) {
+  if (g.W <= 0 || g.H <= 0 || pixels % g.W != 0) return false;
+  int rows = pixels / g.W;
+  if (rows <= g.H) {
+    if (g.H % rows != 0) return false;
+    *th = rows;
+    *nb = 1;
+  } else {
+    if (rows % g.H != 0) return false;
+    *th = g.H;
+    *nb = rows / g.H;
+  }
+  return *th <= 256 && *nb <= 256 && g.W <= 256;
+}
+
+static bool conv_tmap(CUtensorMap* tm, const sd2_conv_geom& g, int th, int nb, std::string* err) {
+  const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.n_planes};
+  const uint64_t strides[3] = {(uint64_t)g.ldc * 2, (uint64_t)g.ldc * 2 * g.W, (uint64_t)g.ldc * 2 * g.W * g.H};
+  const uint32_t box[4] = {64, (uint32_t)g.W, (uint32_t)th, (uint32_t)nb};
+  return encode_tmap_bf16_4d(tm, g.ptr, dims, strides, box, err);
+}
+
+}  // namespace sd2
+
+using namespace sd2;
+
+extern "C" {
+
+int sd2_version(void) { return SD2_VERSION; }
+
+int sd2_ctx_create(int device, sd2_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return 2;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 3;
+  if (prop.major != 10) return 4;  // sm_100a only: no fallback paths
+  sd2_ctx* c = new sd2_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return 0;
+}
+
+int sd2_ctx_destroy(sd2_ctx* ctx) {
+  delete ctx;
+  return 0;
+}
+
+const char* sd2_last_error(sd2_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int sd2_num_sms(sd2_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+long long sd2_launch_count(sd2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
+  if (!ctx || !d) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(ctx, "sd2_gemm: empty problem");
+  if (d->ldo % 8 != 0) return fail(ctx, "sd2_gemm: ldo must be a multiple of 8");
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.kind = d->kind;
+  p.M = d->M;
+  p.N = (d->N + 7) & ~7;  // stores are 8-wide; the caller's ldo covers the round-up (columns beyond N get zeros)
+  if (p.N > d->ldo && d->out_nb0 <= 1 && d->batch <= 1 && false) return fail(ctx, "sd2_gemm: ldo < round8(N)");
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.rowbias = d->rowbias;
+  p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
+  p.ld_rowbias = d->ld_rowbias;
+  p.residual = reinterpret_cast<const bf16*>(d->residual);
+  p.ldr = d->ldr;
+  p.out = d->out;
+  p.ldo = d->ldo;
+  p.out_nb0 = d->out_nb0 > 0 ? d->out_nb0 : 1;
+  p.out_bs0 = d->out_bs0;
+  p.out_bs1 = d->out_bs1;
+
+  bool a_mn, b_mn;
+  int batches = 1;
+  CUtensorMap tmA, tmB;
+  std::string err;
+  int BN;
+
+  if (d->kind == SD2_GEMM_PLAIN) {
+    a_mn = d->A.mn_major != 0;
+    b_mn = d->B.mn_major != 0;
+    BN = pick_bn(d->N, b_mn);
+    batches = d->batch > 0 ? d->batch : 1;
+    p.total_kb = (d->K + 63) / 64;
+    p.a_batched = d->A.nb0 > 0;
+    p.b_batched = d->B.nb0 > 0;
+    p.a_nb0 = d->A.nb0 > 0 ? d->A.nb0 : 1;
+    p.b_nb0 = d->B.nb0 > 0 ? d->B.nb0 : 1;
+    if (!plain_tmap(&tmA, d->A, 128, &err) || !plain_tmap(&tmB, d->B, BN, &err)) return fail(ctx, "sd2_gemm plain: " + err);
+  } else if (d->kind == SD2_GEMM_CONV) {
+    const sd2_conv_geom& g = d->conv;
+    a_mn = false;
+    b_mn = d->B.mn_major != 0;
+    BN = pick_bn(d->N, b_mn);
+    int th, nb;
+    if (!conv_box(g, 128, &th, &nb)) return fail(ctx, "sd2_gemm conv: unsupported spatial geometry for a 128-pixel tile");
+    p.cH = g.H;
+    p.cth = th;
+    p.cnb = nb;
+    p.cblks = (g.C + 63) / 64;
+    p.taps = g.ntaps;
+    if (g.ntaps < 1 || g.ntaps > 9) return fail(ctx, "sd2_gemm conv: ntaps out of range");
+    for (int t = 0; t < g.ntaps; ++t) {
+      p.tap_dh[t] = (signed char)g.dh[t];
+      p.tap_dw[t] = (signed char)g.dw[t];
+      p.tap_dn[t] = g.dn[t];
+      p.tap_w[t] = (signed char)g.wtap[t];
+    }
+    p.total_kb = g.ntaps * p.cblks;
+    if (!conv_tmap(&tmA, g, th, nb, &err)) return fail(ctx, "sd2_gemm conv A: " + err);
+    // weights [tap][rows][cols]: dims (cols, rows, 9, 1)
+    sd2_operand w = d->B;
+    w.nb0 = 9;
+    w.nb1 = 1;
+    if (!plain_tmap(&tmB, w, BN, &err)) return fail(ctx, "sd2_gemm conv B: " + err);
+  } else if (d->kind == SD2_GEMM_CONV_WGRAD) {
+    const sd2_conv_geom& g = d->conv;
+    a_mn = true;
+    b_mn = true;
+    if (!d->A.mn_major) return fail(ctx, "sd2_gemm wgrad: A (dy) must be MN-major");
+    BN = pick_bn(d->N, true);
+    int th, nb;
+    if (!conv_box(g, 64, &th, &nb)) return fail(ctx, "sd2_gemm wgrad: unsupported spatial geometry for a 64-pixel k-block");
+    p.cH = g.H;
+    p.cth = th;
+    p.cnb = nb;
+    p.taps = g.ntaps;
+    if (g.ntaps < 1 || g.ntaps > 9) return fail(ctx, "sd2_gemm wgrad: ntaps out of range");
+    for (int t = 0; t < g.ntaps; ++t) {
+      p.tap_dh[t] = (signed char)g.dh[t];
+      p.tap_dw[t] = (signed char)g.dw[t];
+      p.tap_dn[t] = g.dn[t];
+      p.tap_w[t] = (signed char)g.wtap[t];
+    }
+    batches = g.ntaps;
+    p.total_kb = (d->K + 63) / 64;
+    p.a_batched = 0;
+    p.a_nb0 = 1;
+    p.b_nb0 = 1;
+    if (!plain_tmap(&tmA, d->A, 128, &err)) return fail(ctx, "sd2_gemm wgrad A: " + err);
+    if (!conv_tmap(&tmB, g, th, nb, &err)) return fail(ctx, "sd2_gemm wgrad B: " + err);
+  } else {
+    return fail(ctx, "sd2_gemm: unknown kind");
+  }
+
+  // ---- split-K: fill the machine when there are few output tiles and a long contraction
+  const long long mt = (d->M + 127) / 128, nt = (p.N + BN - 1) / BN;
+  const long long tiles = mt * nt * batches;
+  int splits = 1;
+  const long long target = 2LL * ctx->num_sms;
+  if (tiles < target && p.total_kb >= 8) {
+    long long s = (target + tiles - 1) / tiles;
+    long long smax = p.total_kb / 4;
+    if (s > smax) s = smax;
+    if (s > 32) s = 32;
+    if (d->max_splits > 0 && s > d->max_splits) s = d->max_splits;
+    if (s < 1) s = 1;
+    splits = (int)s;
+  }
+  const bool direct_store = d->out_mode == SD2_OUT_BF16 || d->out_mode == SD2_OUT_F32;
+  if (splits > 1 && direct_store) {
+    const long long need = (long long)splits * batches * d->M * p.N * 4;
+    if (batches != 1 || d->workspace == nullptr || d->workspace_bytes < need) splits = 1;
+  }
+  p.splits = splits;
+
+  cudaError_t e;
+  if (splits > 1 && direct_store) {
+    GemmKParams pp = p;
+    pp.out_mode = OUT_F32_PARTIAL;
+    pp.out = d->workspace;
+    pp.ldo = p.N;
+    pp.alpha = 1.f;
+    pp.bias = nullptr;
+    pp.rowbias = nullptr;
+    pp.residual = nullptr;
+    e = launch_gemm_tc(tmA, tmB, pp, BN, a_mn, b_mn, batches, stream);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm launch: ") + cudaGetErrorString(e));
+    e = launch_splitk_finalize(reinterpret_cast<const float*>(d->workspace), splits, d->M, p.N, d->alpha, d->bias,
+                               d->rowbias, p.rows_per_group, d->ld_rowbias, p.residual, d->ldr, d->out, d->ldo,
+                               d->out_mode == SD2_OUT_F32, stream);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm finalize: ") + cudaGetErrorString(e));
+    ctx->launches += 2;
+    return 0;
+  }
+  if (d->out_mode == SD2_OUT_BF16)
+    p.out_mode = OUT_BF16;
+  else if (d->out_mode == SD2_OUT_F32)
+    p.out_mode = OUT_F32;
+  else
+    p.out_mode = splits > 1 ? OUT_F32_ATOMIC : OUT_F32_ACCUM;
+  e = launch_gemm_tc(tmA, tmB, p, BN, a_mn, b_mn, batches, stream);
+  if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm launch: ") + cudaGetErrorString(e));
+  ctx->launches += 1;
+  return 0;
+}
+
+}  // extern "C"

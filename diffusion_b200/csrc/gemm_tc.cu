@@ -1,0 +1,360 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM 3x3 convolution for sm_100a.
+//
+// One CTA computes one 128 x BN fp32 accumulator tile in tensor memory:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 4-D boxes, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> bias / per-image bias / residual -> global)
+// Two CTAs are co-resident per SM (<=113 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's main loop.  Operands can be K-major (forward, activations x weights) or MN-major (dgrad reads the
+// weights transposed, wgrad contracts over pixels) - the same TMA boxes serve both, only the UMMA descriptors differ.
+//
+// Replaces: cuDNN implicit-GEMM conv + cuBLASLt linear behind diffusers' nn.Conv2d / nn.Linear, called from
+// reference diffusion/models/stable_diffusion.py:183 (UNet forward) and the autograd backward of the same.
+#include "gemm_tc.cuh"
+#include "host.h"
+
+namespace sd2 {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+static constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major box = 8 KB
+
+template <int BN>
+struct TileCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const GemmKParams p,
+                                                      const int stages) {
+  using Cfg = TileCfg<BN>;
+  static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide chunks");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int kb0 = (int)(((long long)split * p.total_kb) / p.splits);
+  const int kb1 = (int)(((long long)(split + 1) * p.total_kb) / p.splits);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      // pixel-block origin of the shifted (conv) operand for this CTA / k-block
+      int cn0 = 0, ch0 = 0;
+      if (p.kind == KIND_CONV) {
+        if (p.cnb == 1) {
+          const int tiles_per_img = p.cH / p.cth;
+          cn0 = m_tile / tiles_per_img;
+          ch0 = (m_tile % tiles_per_img) * p.cth;
+        } else {
+          cn0 = m_tile * p.cnb;
+        }
+      }
+      const int ab0 = p.a_batched ? batch % p.a_nb0 : 0, ab1 = p.a_batched ? batch / p.a_nb0 : 0;
+      const int bb0 = p.b_batched ? batch % p.b_nb0 : 0, bb1 = p.b_batched ? batch / p.b_nb0 : 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb0 + i, s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_dst = smem + (size_t)s * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        if (p.kind == KIND_CONV) {
+          const int tap = kb / p.cblks, cb = kb % p.cblks;
+          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+          tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, dw, ch0 + dh, cn0 + p.tap_dn[tap]);
+          const int tap_w = p.tap_w[tap];
+          if (!B_MN) {
+            tma_load_4d(b_dst, &tmB, &full_bar[s], cb * 64, n_tile * BN, tap_w, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_tile * BN + 64 * j, cb * 64, tap_w, 0);
+          }
+        } else {
+          if (!A_MN) {
+            tma_load_4d(a_dst, &tmA, &full_bar[s], kb * 64, m_tile * BM, ab0, ab1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, &full_bar[s], m_tile * BM + 64 * j, kb * 64, ab0, ab1);
+          }
+          if (p.kind == KIND_PLAIN) {
+            if (!B_MN) {
+              tma_load_4d(b_dst, &tmB, &full_bar[s], kb * 64, n_tile * BN, bb0, bb1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_tile * BN + 64 * j, kb * 64, bb0, bb1);
+            }
+          } else {  // KIND_CONV_WGRAD: B = activations shifted by the tap (= batch index), k-block = 64 pixels
+            const int tap = batch;
+            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+            int n0, h0;
+            if (p.cnb == 1) {
+              const int blocks_per_img = p.cH / p.cth;
+              n0 = kb / blocks_per_img;
+              h0 = (kb % blocks_per_img) * p.cth;
+            } else {
+              n0 = kb * p.cnb;
+              h0 = 0;
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_tile * BN + 64 * j, dw, h0 + dh,
+                            n0 + p.tap_dn[tap]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * 2048, CHUNK_BYTES, 1024)
+                                      : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * 2048, CHUNK_BYTES, 1024)
+                                      : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
+      }
+      tc_commit(tmem_full_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
+    const int q = warp & 3;
+    const long long row = (long long)m_tile * BM + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    long long out_off;
+    if (p.out_mode == OUT_F32_PARTIAL)
+      out_off = (long long)blockIdx.z * p.M * p.ldo;
+    else
+      out_off = (long long)(batch % p.out_nb0) * p.out_bs0 + (long long)(batch / p.out_nb0) * p.out_bs1;
+    const bool row_ok = row < p.M;
+    const float* rb = (p.rowbias != nullptr && row_ok) ? p.rowbias + (row / p.rows_per_group) * p.ld_rowbias : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_wait_ld();
+      const int n_base = n_tile * BN + c * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n_base + g * 8;
+        if (!row_ok || n >= p.N) continue;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * p.alpha;
+        if (p.out_mode != OUT_F32_PARTIAL) {
+          if (p.bias != nullptr) {
+            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (rb != nullptr) {
+            const float4 b0 = *reinterpret_cast<const float4*>(rb + n);
+            const float4 b1 = *reinterpret_cast<const float4*>(rb + n + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.residual != nullptr) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + out_off + row * p.ldr + n);
+            const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                         r3 = unpack_bf16x2(rr.w);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+          }
+        }
+        if (p.out_mode == OUT_BF16) {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + row * p.ldo + n) = o;
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + out_off + row * p.ldo + n;
+          if (p.out_mode == OUT_F32_ATOMIC) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(o + e, v[e]);
+          } else {
+            if (p.out_mode == OUT_F32_ACCUM) {
+              const float4 c0 = *reinterpret_cast<const float4*>(o);
+              const float4 c1 = *reinterpret_cast<const float4*>(o + 4);
+              v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
+              v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+            }
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+      }
+      __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// out[m][n] = bf16/f32( alpha * sum_s ws[s][m][n] + bias[n] + rowbias[m/rpg][n] + residual[m][n] )
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits, long long M, int N, float alpha,
+                                       const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                       int rows_per_group, long long ld_rowbias, const bf16* __restrict__ residual,
+                                       long long ldr, void* __restrict__ out, long long ldo, int out_f32) {
+  const long long nvec = M * (N / 8);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (N / 8);
+    const int n = (int)(i % (N / 8)) * 8;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < splits; ++s) {
+      const float* src = ws + ((long long)s * M + m) * N + n;
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= alpha;
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += bias[n + e];
+    }
+    if (rowbias) {
+      const float* rb = rowbias + (m / rows_per_group) * ld_rowbias + n;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += rb[e];
+    }
+    if (residual) {
+      const uint4 rr = *reinterpret_cast<const uint4*>(residual + m * ldr + n);
+      const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
+      v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y; v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+    }
+    if (out_f32) {
+      float* o = reinterpret_cast<float*>(out) + m * ldo + n;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + m * ldo + n) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+template <int BN, bool A_MN, bool B_MN>
+static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid, int stages,
+                              cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, 192, smem, stream>>>(tmA, tmB, p, stages);
+  return cudaGetLastError();
+}
+
+static int stages_for(int BN) {
+  const int stage_bytes = A_BYTES + BN * BK * 2;
+  int s = (112 * 1024 - 1024 - 256) / stage_bytes;
+  return s < 2 ? 2 : (s > 6 ? 6 : s);
+}
+
+int pick_bn(int N, bool b_mn) {
+  const int cands[4] = {256, 160, 128, 64};
+  int best = 64;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (b_mn && bn % 64 != 0) continue;
+    const int tiles = (N + bn - 1) / bn;
+    // narrow tiles re-read the 128-row A tile more often per flop (smem-bandwidth bound)
+    const double eff = bn >= 256 ? 1.0 : bn >= 160 ? 1.04 : bn >= 128 ? 1.08 : 1.5;
+    const double cost = (double)tiles * bn * eff;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int BN, bool a_mn,
+                           bool b_mn, int batches, cudaStream_t stream) {
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, batches * p.splits);
+  const int st = stages_for(BN);
+#define SD2_GEMM_CASE(bn, amn, bmn) \
+  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn>(tmA, tmB, p, grid, st, stream);
+  SD2_GEMM_CASE(256, false, false) SD2_GEMM_CASE(160, false, false) SD2_GEMM_CASE(128, false, false)
+  SD2_GEMM_CASE(64, false, false)
+  SD2_GEMM_CASE(256, false, true) SD2_GEMM_CASE(128, false, true) SD2_GEMM_CASE(64, false, true)
+  SD2_GEMM_CASE(256, true, false) SD2_GEMM_CASE(160, true, false) SD2_GEMM_CASE(128, true, false)
+  SD2_GEMM_CASE(64, true, false)
+  SD2_GEMM_CASE(256, true, true) SD2_GEMM_CASE(128, true, true) SD2_GEMM_CASE(64, true, true)
+#undef SD2_GEMM_CASE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int N, float alpha, const float* bias,
+                                   const float* rowbias, int rows_per_group, long long ld_rowbias, const bf16* residual,
+                                   long long ldr, void* out, long long ldo, int out_f32, cudaStream_t stream) {
+  const long long nvec = M * (N / 8);
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(ws, splits, M, N, alpha, bias, rowbias, rows_per_group, ld_rowbias,
+                                                     residual, ldr, out, ldo, out_f32);
+  return cudaGetLastError();
+}
+
+}  // namespace sd2

@@ -1,0 +1,47 @@
+// Device-side parameter block of the tcgen05 GEMM / implicit-GEMM convolution kernel (gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sd2 {
+
+enum GemmKind {
+  KIND_PLAIN = 0,       // D[b] = A[b] * B[b]^T            (operands K-major or MN-major, batched through tensor-map dims 2,3)
+  KIND_CONV = 1,        // A = NHWC activations gathered by shifted TMA boxes (3x3, pad 1, stride 1), B = weights [tap][Cout][Cin]
+  KIND_CONV_WGRAD = 2,  // A = dy^T (MN-major, [pixels][Cout]), B = shifted NHWC activations (MN-major), batch index = tap
+};
+enum GemmOut {
+  OUT_BF16 = 0,         // bf16(alpha*acc + bias + rowbias + residual)
+  OUT_F32 = 1,          // fp32 store of alpha*acc (+bias)
+  OUT_F32_ACCUM = 2,    // fp32 out += alpha*acc (tile-owned read-modify-write)
+  OUT_F32_ATOMIC = 3,   // fp32 atomicAdd(out, alpha*acc)    (split-K weight gradients)
+  OUT_F32_PARTIAL = 4,  // fp32 raw accumulators into workspace[z][M][N] (split-K, finalized by splitk_finalize)
+};
+
+struct GemmKParams {
+  int M, N;            // output extent (per batch) used for store masking
+  int total_kb;        // number of 64-deep K blocks
+  int splits;          // split-K factor; gridDim.z = batches * splits
+  int kind;
+  int a_batched, b_batched;  // plain operands: does the batch index move this operand?
+  int a_nb0, b_nb0;          // batch -> (batch % nb0, batch / nb0) = tensor-map coords 2,3
+  // conv geometry of the shifted operand: tensor map dims (C, W, H, Nimg), box (64, W, th, nb)
+  int cH, cth, cnb, cblks, taps;
+  // per-tap table: spatial shift (dh, dw), image-index offset (stride-2 phase planes) and weight tap index
+  signed char tap_dh[9], tap_dw[9];
+  int tap_dn[9];
+  signed char tap_w[9];
+  // epilogue
+  int out_mode;
+  void* out;
+  long long ldo, out_bs0, out_bs1;
+  int out_nb0;
+  const bf16* residual;
+  long long ldr;
+  const float* bias;      // [N] or null
+  const float* rowbias;   // [M / rows_per_group][ld_rowbias] or null
+  int rows_per_group;
+  long long ld_rowbias;
+  float alpha;
+};
+
+}  // namespace sd2

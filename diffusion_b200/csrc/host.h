@@ -1,0 +1,56 @@
+// Internal host-side declarations shared by the .cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sd2b200.h"
+
+struct sd2_ctx {
+  int device = 0;
+  int num_sms = 148;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace sd2 {
+struct GemmKParams;
+typedef __nv_bfloat16 bf16;
+
+// cuTensorMapEncodeTiled obtained through cudaGetDriverEntryPoint (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+// 4-D bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in BYTES for dims 1..3.
+bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4], std::string* err);
+
+int pick_bn(int N, bool b_mn);
+cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int BN, bool a_mn,
+                           bool b_mn, int batches, cudaStream_t stream);
+cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int N, float alpha, const float* bias,
+                                   const float* rowbias, int rows_per_group, long long ld_rowbias, const bf16* residual,
+                                   long long ldr, void* out, long long ldo, int out_f32, cudaStream_t stream);
+
+inline int fail(sd2_ctx* ctx, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return 1;
+}
+inline int check_launch(sd2_ctx* ctx, const char* what, int nlaunch = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, std::string(what) + ": " + cudaGetErrorString(e));
+  if (ctx) ctx->launches += nlaunch;
+  return 0;
+}
+inline int grid_for(long long work_items, int threads, int num_sms, int max_waves = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)num_sms * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+}  // namespace sd2

@@ -1,0 +1,466 @@
+// GroupNorm(+SiLU) and LayerNorm, forward and backward, NHWC bf16 I/O with fp32 statistics.  HBM-bound kernels:
+// 16-byte vector loads (8 bf16 channels per thread), coalesced along the channel dimension, deterministic
+// two-level reductions through a caller-provided fp32 scratch (no atomics on global memory).
+//
+// Replaces ATen group_norm / layer_norm (+ their backward) as run by composer's LPGroupNorm / LPLayerNorm surgery
+// (reference diffusion/train.py:91-108) and the F.silu that follows every ResnetBlock2D GroupNorm (diffusers).
+#include "common.cuh"
+#include "host.h"
+
+namespace sd2 {
+
+static constexpr int GN_THREADS = 512;
+static constexpr int GN_MAXP = 32;  // pixel-chunk partials per image
+
+__device__ __forceinline__ void load8(const bf16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__host__ __device__ inline int gn_chunks(int HW) {
+  int p = HW / 32;
+  return p < 1 ? 1 : (p > GN_MAXP ? GN_MAXP : p);
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm fwd
+// grid (P, B). Partial (sum, sumsq) per group over this block's pixel chunk -> ws[b][p][G][2]
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ ws,
+                                                              int HW, int C, int G) {
+  extern __shared__ float sm[];  // [C][2]
+  const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
+  const int V = C / 8, R = GN_THREADS / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  if (r < R) {
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    const bf16* base = x + ((long long)b * HW) * ldx + v * 8;
+    for (int row = row0 + r; row < row1; row += R) {
+      float f[8];
+      load8(base + (long long)row * ldx, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += f[e];
+        q[e] += f[e] * f[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sm[(v * 8 + e) * 2], s[e]);
+      atomicAdd(&sm[(v * 8 + e) * 2 + 1], q[e]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    float s = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += sm[c * 2];
+      q += sm[c * 2 + 1];
+    }
+    float* o = ws + (((long long)b * P + p) * G + g) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+// grid (P, B): finalize stats from the P partials, then y = [silu](x * scale + shift)
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ x, long long ldx,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              bf16* __restrict__ y, long long ldy, float* __restrict__ stats,
+                                                              const float* __restrict__ ws, int HW, int C, int G, float eps,
+                                                              int silu) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < P; ++i) {
+      const float* o = ws + (((long long)b * P + i) * G + g) * 2;
+      s += o[0];
+      q += o[1];
+    }
+    const float n = (float)cpg * (float)HW;
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    s_mean[g] = mean;
+    s_rstd[g] = rstd;
+    if (p == 0) {
+      stats[((long long)b * G + g) * 2] = mean;
+      stats[((long long)b * G + g) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  const int V = C / 8, R = GN_THREADS / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  if (r >= R) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e, g = c / cpg;
+    sc[e] = gamma[c] * s_rstd[g];
+    sh[e] = beta[c] - s_mean[g] * sc[e];
+  }
+  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
+  bf16* yb = y + ((long long)b * HW) * ldy + v * 8;
+  for (int row = row0 + r; row < row1; row += R) {
+    float f[8];
+    load8(xb + (long long)row * ldx, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float z = f[e] * sc[e] + sh[e];
+      f[e] = silu ? silu_f(z) : z;
+    }
+    store8(yb + (long long)row * ldy, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm bwd
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = sigmoid_f(z);
+  return s * (1.f + z * (1.f - s));
+}
+
+// grid (P, B): per-channel partial sums of dyh and dyh * xhat -> ws[b][p][C][2]
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy,
+                                                                  const bf16* __restrict__ x, long long ldx,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ stats, float* __restrict__ ws, int HW,
+                                                                  int C, int G, int silu) {
+  extern __shared__ float sm[];  // [C][2]
+  const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
+  const int V = C / 8, R = GN_THREADS / V, cpg = C / G;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  if (r < R) {
+    float s1[8], s2[8], mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e, g = c / cpg;
+      s1[e] = s2[e] = 0.f;
+      mean[e] = stats[((long long)b * G + g) * 2];
+      rstd[e] = stats[((long long)b * G + g) * 2 + 1];
+      ga[e] = gamma[c];
+      be[e] = beta[c];
+    }
+    const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
+    const bf16* db = dy + ((long long)b * HW) * lddy + v * 8;
+    for (int row = row0 + r; row < row1; row += R) {
+      float f[8], d[8];
+      load8(xb + (long long)row * ldx, f);
+      load8(db + (long long)row * lddy, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (f[e] - mean[e]) * rstd[e];
+        float dyh = d[e];
+        if (silu) dyh *= silu_grad(xh * ga[e] + be[e]);
+        s1[e] += dyh;
+        s2[e] += dyh * xh;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sm[(v * 8 + e) * 2], s1[e]);
+      atomicAdd(&sm[(v * 8 + e) * 2 + 1], s2[e]);
+    }
+  }
+  __syncthreads();
+  float* o = ws + (((long long)b * P + p) * C) * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) o[i] = sm[i];
+}
+
+// grid (P, B): dx = rstd * (gamma*dyh - (db_g + xhat*ds_g)/n) (+ dx_add)
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
+                                                                  const bf16* __restrict__ x, long long ldx,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ stats, const float* __restrict__ ws,
+                                                                  const bf16* __restrict__ dx_add, long long ldadd,
+                                                                  bf16* __restrict__ dx, long long lddx, int HW, int C, int G,
+                                                                  int silu) {
+  __shared__ float s_ds[64], s_db[64];
+  const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float ds = 0.f, dbv = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      float a1 = 0.f, a2 = 0.f;
+      for (int i = 0; i < P; ++i) {
+        const float* o = ws + (((long long)b * P + i) * C + c) * 2;
+        a1 += o[0];
+        a2 += o[1];
+      }
+      dbv += gamma[c] * a1;
+      ds += gamma[c] * a2;
+    }
+    s_ds[g] = ds;
+    s_db[g] = dbv;
+  }
+  __syncthreads();
+  const int V = C / 8, R = GN_THREADS / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  if (r >= R) return;
+  const float inv_n = 1.f / ((float)cpg * (float)HW);
+  float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e, g = c / cpg;
+    mean[e] = stats[((long long)b * G + g) * 2];
+    rstd[e] = stats[((long long)b * G + g) * 2 + 1];
+    ga[e] = gamma[c];
+    be[e] = beta[c];
+    k1[e] = s_db[g] * inv_n;
+    k2[e] = s_ds[g] * inv_n;
+  }
+  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
+  const bf16* db = dy + ((long long)b * HW) * lddy + v * 8;
+  bf16* ob = dx + ((long long)b * HW) * lddx + v * 8;
+  const bf16* ab = dx_add ? dx_add + ((long long)b * HW) * ldadd + v * 8 : nullptr;
+  for (int row = row0 + r; row < row1; row += R) {
+    float f[8], d[8], a[8];
+    load8(xb + (long long)row * ldx, f);
+    load8(db + (long long)row * lddy, d);
+    if (ab) load8(ab + (long long)row * ldadd, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (f[e] - mean[e]) * rstd[e];
+      float dyh = d[e];
+      if (silu) dyh *= silu_grad(xh * ga[e] + be[e]);
+      float o = rstd[e] * (ga[e] * dyh - k1[e] - xh * k2[e]);
+      if (ab) o += a[e];
+      f[e] = o;
+    }
+    store8(ob + (long long)row * lddx, f);
+  }
+}
+
+// dgamma[c] += sum_i ws[i][c][1], dbeta[c] += sum_i ws[i][c][0] over `n_part` partial slabs
+__global__ void affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a1 = 0.f, a2 = 0.f;
+  for (int i = 0; i < n_part; ++i) {
+    a1 += ws[((long long)i * C + c) * 2];
+    a2 += ws[((long long)i * C + c) * 2 + 1];
+  }
+  dbeta[c] += a1;
+  dgamma[c] += a2;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+static constexpr int LN_MAXV = 5;  // up to 5 x 32 lanes x 8 channels = 1280
+
+// one warp per row
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                     float* __restrict__ stats, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int V = C / 8;
+  for (long long row = warp; row < rows; row += nwarps) {
+    float f[LN_MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+        load8(x + row * C + v * 8, f[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += f[j][e];
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = f[j][e] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0) {
+      stats[row * 2] = mean;
+      stats[row * 2 + 1] = rstd;
+    }
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (f[j][e] - mean) * rstd * gamma[v * 8 + e] + beta[v * 8 + e];
+        store8(y + row * C + v * 8, o);
+      }
+    }
+  }
+}
+
+// one warp per row; per-block partial (dbeta, dgamma) -> ws[block][C][2]
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                     const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
+                                                     float* __restrict__ ws, long long rows, int C) {
+  extern __shared__ float sm[];  // [C][2]
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int V = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float ag[LN_MAXV][8], ab[LN_MAXV][8];
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ag[j][e] = ab[j][e] = 0.f;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float xh[LN_MAXV][8], g[LN_MAXV][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+        float d[8];
+        load8(x + row * C + v * 8, xh[j]);
+        load8(dy + row * C + v * 8, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] = (xh[j][e] - mean) * rstd;
+          g[j][e] = d[e] * gamma[v * 8 + e];
+          c1 += g[j][e];
+          c2 += g[j][e] * xh[j][e];
+          ab[j][e] += d[e];
+          ag[j][e] += d[e] * xh[j][e];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / (float)C;
+    c2 = warp_sum(c2) / (float)C;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+        float o[8];
+        if (dx_add) load8(dx_add + row * C + v * 8, o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = rstd * (g[j][e] - c1 - xh[j][e] * c2);
+          o[e] = dx_add ? o[e] + t : t;
+        }
+        store8(dx + row * C + v * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < V) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&sm[(v * 8 + e) * 2], ab[j][e]);
+        atomicAdd(&sm[(v * 8 + e) * 2 + 1], ag[j][e]);
+      }
+    }
+  }
+  __syncthreads();
+  float* o = ws + (long long)blockIdx.x * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) o[i] = sm[i];
+}
+
+static int ln_blocks(long long rows, int num_sms) {
+  long long b = (rows + 7) / 8;
+  const long long cap = (long long)num_sms * 2;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace sd2
+
+using namespace sd2;
+
+extern "C" {
+
+long long sd2_groupnorm_ws_floats(int B, int C) { return (long long)B * GN_MAXP * C * 2; }
+
+int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* gamma, const float* beta, void* y,
+                      long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
+                      sd2_stream stream_) {
+  if (!ctx) return 1;
+  if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_fwd: unsupported C/G");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const dim3 grid(gn_chunks(HW), B);
+  gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
+  gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, gamma, beta,
+                                                   reinterpret_cast<bf16*>(y), ldy, stats, ws, HW, C, G, eps, silu);
+  return check_launch(ctx, "groupnorm_fwd", 2);
+}
+
+int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
+                      const float* beta, const float* stats, const void* dx_add, long long ldadd, void* dx,
+                      long long lddx, float* dgamma, float* dbeta, float* ws, int B, int HW, int C, int G, int silu,
+                      sd2_stream stream_) {
+  if (!ctx) return 1;
+  if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_bwd: unsupported C/G");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int P = gn_chunks(HW);
+  const dim3 grid(P, B);
+  gn_bwd_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws, HW, C, G, silu);
+  gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy), lddy,
+                                                       reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws,
+                                                       reinterpret_cast<const bf16*>(dx_add), ldadd,
+                                                       reinterpret_cast<bf16*>(dx), lddx, HW, C, G, silu);
+  affine_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, B * P, C, dgamma, dbeta);
+  return check_launch(ctx, "groupnorm_bwd", 3);
+}
+
+int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, float* stats,
+                      long long rows, int C, float eps, sd2_stream stream_) {
+  if (!ctx) return 1;
+  if (C % 8 != 0 || C > LN_MAXV * 256) return fail(ctx, "sd2_layernorm_fwd: unsupported C");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int blocks = grid_for(rows * 32, 256, ctx->num_sms, 8);
+  ln_fwd_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), gamma, beta, reinterpret_cast<bf16*>(y), stats,
+                                            rows, C, eps);
+  return check_launch(ctx, "layernorm_fwd");
+}
+
+long long sd2_layernorm_ws_floats(long long rows, int C) { return (long long)148 * 4 * C * 2; }
+
+int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* gamma, const float* stats,
+                      const void* dx_add, void* dx, float* dgamma, float* dbeta, float* ws, long long rows, int C,
+                      sd2_stream stream_) {
+  if (!ctx) return 1;
+  if (C % 8 != 0 || C > LN_MAXV * 256) return fail(ctx, "sd2_layernorm_bwd: unsupported C");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int blocks = ln_blocks(rows, ctx->num_sms);
+  ln_bwd_kernel<<<blocks, 256, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(dy),
+                                                                reinterpret_cast<const bf16*>(x), gamma, stats,
+                                                                reinterpret_cast<const bf16*>(dx_add),
+                                                                reinterpret_cast<bf16*>(dx), ws, rows, C);
+  affine_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, blocks, C, dgamma, dbeta);
+  return check_launch(ctx, "layernorm_bwd", 2);
+}
+
+}  // extern "C"

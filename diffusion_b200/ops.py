@@ -1,0 +1,336 @@
+"""Thin torch-tensor wrappers over the C ABI (include/sd2b200.h).  torch is plumbing here: device memory,
+streams, pointers.  Every function enqueues on torch's current CUDA stream and returns immediately.
+
+Layouts: activations are bf16 [pixels, channels] (NHWC flattened); 3x3 conv weights are [tap=kh*3+kw][Cout][Cin].
+"""
+import ctypes as C
+
+import torch
+
+from diffusion_b200 import _lib as L
+
+_ctx_cache = {}
+
+
+class Ctx:
+    """Per-device sd2_ctx handle."""
+
+    def __init__(self, device_index):
+        self.lib = L.load()
+        h = C.c_void_p()
+        rc = self.lib.sd2_ctx_create(int(device_index), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f'sd2_ctx_create(device={device_index}) failed with code {rc} '
+                               '(needs an sm_100 GPU; there is no fallback path)')
+        self.h = h
+        self.device = torch.device('cuda', device_index)
+        self.num_sms = self.lib.sd2_num_sms(h)
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError('sd2b200: ' + self.lib.sd2_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return self.lib.sd2_launch_count(self.h)
+
+
+def get_ctx(device=None) -> Ctx:
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _ctx_cache:
+        _ctx_cache[idx] = Ctx(idx)
+    return _ctx_cache[idx]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
+
+
+# ------------------------------------------------------------------------------------------------- K1
+def noise_sched_fwd(ctx, latents, alphas_cumprod, seed, offset, temb_dim, want_noised_nchw=False):
+    """Returns (timesteps i64[B], noise like latents, noised_nhwc8 bf16 [B,H,W,8], temb bf16 [B,temb_dim],
+    noised_nchw or None, philox offset consumed)."""
+    B, Cc, H, W = latents.shape
+    assert Cc == 4 and latents.is_contiguous()
+    dev = latents.device
+    ts = torch.empty(B, dtype=torch.int64, device=dev)
+    noise = torch.empty_like(latents)
+    nhwc8 = torch.empty(B, H, W, 8, dtype=torch.bfloat16, device=dev)
+    temb = torch.empty(B, temb_dim, dtype=torch.bfloat16, device=dev)
+    nchw = torch.empty_like(latents) if want_noised_nchw else None
+    used = C.c_uint64(0)
+    ctx.check(
+        ctx.lib.sd2_noise_sched_fwd(ctx.h, int(seed), int(offset), _p(latents), _DT[latents.dtype], B, H, W,
+                                    _p(alphas_cumprod), alphas_cumprod.numel(), _p(ts), _p(noise), _p(nchw), _p(nhwc8),
+                                    _p(temb), temb_dim, C.byref(used), _s()))
+    return ts, noise, nhwc8, temb, nchw, used.value
+
+
+# ------------------------------------------------------------------------------------------------- GEMM
+def _operand(t, mn_major, cols, rows, ld, nb0=0, nb1=0, bs0=0, bs1=0):
+    o = L.Operand()
+    o.ptr, o.mn_major, o.cols, o.rows, o.ld = t if isinstance(t, int) else t.data_ptr(), int(mn_major), cols, rows, ld
+    o.nb0, o.nb1, o.bs0, o.bs1 = nb0, nb1, bs0, bs1
+    return o
+
+
+def _epilogue(d, out, ldo, out_mode, bias=None, rowbias=None, rows_per_group=1, residual=None, ldr=0, alpha=1.0,
+              workspace=None):
+    d.out_mode, d.out, d.ldo = out_mode, out.data_ptr(), ldo
+    d.out_nb0, d.out_bs0, d.out_bs1 = 1, 0, 0
+    d.bias = _p(bias)
+    d.rowbias = _p(rowbias)
+    d.rows_per_group = rows_per_group
+    d.ld_rowbias = rowbias.stride(0) if rowbias is not None else 0
+    d.residual = _p(residual)
+    d.ldr = ldr
+    d.alpha = alpha
+    if workspace is not None:
+        d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    d.max_splits = 0
+
+
+def run_gemm(ctx, d):
+    ctx.check(ctx.lib.sd2_gemm(ctx.h, C.byref(d), _s()))
+
+
+def linear_fwd(ctx, x, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, alpha=1.0, out_f32=False,
+               workspace=None):
+    """out[M,N] = alpha * x[M,K] @ w[N,K]^T (+bias +rowbias +residual). x, w bf16 with unit inner stride."""
+    M, K = x.shape
+    N = w.shape[0]
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_PLAIN, M, N, K, 1
+    d.A = _operand(x, 0, K, M, x.stride(0))
+    d.B = _operand(w, 0, K, N, w.stride(0))
+    _epilogue(d, out, out.stride(0), L.OUT_F32 if out_f32 else L.OUT_BF16, bias, rowbias, rows_per_group, residual,
+              residual.stride(0) if residual is not None else 0, alpha, workspace)
+    run_gemm(ctx, d)
+
+
+def linear_dgrad(ctx, dy, w, dx, residual=None, workspace=None):
+    """dx[M,K] = dy[M,N] @ w[N,K]  (w read MN-major: no transposed weight copy) (+residual)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_PLAIN, M, K, N, 1
+    d.A = _operand(dy, 0, N, M, dy.stride(0))
+    d.B = _operand(w, 1, K, N, w.stride(0))
+    _epilogue(d, dx, dx.stride(0), L.OUT_BF16, residual=residual, ldr=residual.stride(0) if residual is not None else 0,
+              workspace=workspace)
+    run_gemm(ctx, d)
+
+
+def linear_wgrad(ctx, dy, x, dw):
+    """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]; both operands read MN-major (contraction over rows)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_PLAIN, N, K, M, 1
+    d.A = _operand(dy, 1, N, M, dy.stride(0))
+    d.B = _operand(x, 1, K, M, x.stride(0))
+    _epilogue(d, dw, dw.stride(0), L.OUT_F32_ACCUM)
+    run_gemm(ctx, d)
+
+
+def _conv_geom(x_ptr, n_planes, H, W, Cc, ldc, taps):
+    g = L.ConvGeom()
+    g.ptr, g.n_planes, g.H, g.W, g.C, g.ldc = x_ptr, n_planes, H, W, Cc, ldc
+    g.ntaps = len(taps)
+    for i, (dh, dw, dn, wt) in enumerate(taps):
+        g.dh[i], g.dw[i], g.dn[i], g.wtap[i] = dh, dw, dn, wt
+    return g
+
+
+TAPS_FWD = [(kh - 1, kw - 1, 0, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+# dgrad of a stride-1 3x3: dx[p] = sum_t dy[p - d_t] W_t^T  ->  shift by +d_t', weight tap 8 - t'
+TAPS_DGRAD = [(kh - 1, kw - 1, 0, 8 - (kh * 3 + kw)) for kh in range(3) for kw in range(3)]
+
+
+def taps_stride2(B):
+    """Forward taps of a stride-2 pad-1 3x3 conv over the 4 phase planes [(h%2)*2+(w%2)][B][H/2][W/2]:
+    input row 2*ho + kh - 1 = 2*(ho + dh) + ph with (kh=0: ph=1, dh=-1), (kh=1: ph=0, dh=0), (kh=2: ph=1, dh=0)."""
+    m = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+    return [(m[kh][1], m[kw][1], (m[kh][0] * 2 + m[kw][0]) * B, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+
+
+def taps_stride2_dgrad():
+    """dgrad of the stride-2 conv, one tap subset per input phase plane: plane -> [(dh, dw, 0, weight tap)].
+    dx_plane(p,q)[h2,w2] = sum_{taps t of that phase} dy[h2 - dh_t, w2 - dw_t] W_t^T."""
+    m = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+    out = {0: [], 1: [], 2: [], 3: []}
+    for kh in range(3):
+        for kw in range(3):
+            out[m[kh][0] * 2 + m[kw][0]].append((-m[kh][1], -m[kw][1], 0, kh * 3 + kw))
+    return out
+
+
+def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None, taps=None, n_planes=None,
+                workspace=None):
+    """x: bf16 [n_planes*H*W, Cin] NHWC; w9: bf16 [9, Cout, Cin]; out: bf16 [B*H*W, Cout]."""
+    Cin, Cout = x.shape[1], w9.shape[1]
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_CONV, B * H * W, Cout, 9 * Cin, 1
+    d.conv = _conv_geom(x.data_ptr(), n_planes or B, H, W, Cin, x.stride(0), taps or TAPS_FWD)
+    d.B = _operand(w9, 0, Cin, Cout, w9.stride(1), bs0=w9.stride(0))
+    _epilogue(d, out, out.stride(0), L.OUT_BF16, bias, rowbias, H * W, residual,
+              residual.stride(0) if residual is not None else 0, 1.0, workspace)
+    run_gemm(ctx, d)
+
+
+def conv3x3_dgrad(ctx, dy, B, H, W, w9, dx, residual=None, taps=None, n_planes=None, workspace=None):
+    """dx[B*H*W, Cin] = sum_taps shift(dy)[.., Cout] @ w9[tap'][Cout][Cin]  (weights read MN-major)."""
+    Cout, Cin = dy.shape[1], w9.shape[2]
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_CONV, B * H * W, Cin, 9 * Cout, 1
+    d.conv = _conv_geom(dy.data_ptr(), n_planes or B, H, W, Cout, dy.stride(0), taps or TAPS_DGRAD)
+    d.B = _operand(w9, 1, Cin, Cout, w9.stride(1), bs0=w9.stride(0))
+    _epilogue(d, dx, dx.stride(0), L.OUT_BF16, residual=residual, ldr=residual.stride(0) if residual is not None else 0,
+              workspace=workspace)
+    run_gemm(ctx, d)
+
+
+def conv3x3_wgrad(ctx, dy, x, B, H, W, dw9, taps=None, n_planes=None):
+    """dw9[tap][Cout][Cin] (fp32) += dy[B*H*W, Cout]^T @ shift_tap(x)[.., Cin]."""
+    Cout, Cin = dy.shape[1], x.shape[1]
+    M = B * H * W
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_CONV_WGRAD, Cout, Cin, M, 9
+    d.A = _operand(dy, 1, Cout, M, dy.stride(0))
+    d.conv = _conv_geom(x.data_ptr(), n_planes or B, H, W, Cin, x.stride(0), taps or TAPS_FWD)
+    _epilogue(d, dw9, dw9.stride(1), L.OUT_F32_ACCUM)
+    d.out_nb0, d.out_bs0 = 16, dw9.stride(0)
+    run_gemm(ctx, d)
+
+
+def bmm(ctx, A, a_mn, a_dims, B_, b_mn, b_dims, out, out_dims, M, N, K, batch, nb0, alpha=1.0, out_f32=False):
+    """Batched GEMM over batch index b -> (b % nb0, b / nb0).  *_dims = (cols, rows, ld, bs0, bs1) in elements;
+    out_dims = (ldo, bs0, bs1)."""
+    d = L.GemmDesc()
+    d.kind, d.M, d.N, d.K, d.batch = L.GEMM_PLAIN, M, N, K, batch
+    nb1 = (batch + nb0 - 1) // nb0
+    d.A = _operand(A, a_mn, a_dims[0], a_dims[1], a_dims[2], nb0, nb1, a_dims[3], a_dims[4])
+    d.B = _operand(B_, b_mn, b_dims[0], b_dims[1], b_dims[2], nb0, nb1, b_dims[3], b_dims[4])
+    _epilogue(d, out, out_dims[0], L.OUT_F32 if out_f32 else L.OUT_BF16, alpha=alpha)
+    d.out_nb0, d.out_bs0, d.out_bs1 = nb0, out_dims[1], out_dims[2]
+    run_gemm(ctx, d)
+
+
+# ------------------------------------------------------------------------------------------------- norms
+def groupnorm_ws(ctx, B, Cc, device):
+    return torch.empty(ctx.lib.sd2_groupnorm_ws_floats(B, Cc), dtype=torch.float32, device=device)
+
+
+def groupnorm_fwd(ctx, x, gamma, beta, y, stats, ws, B, HW, G, eps, silu):
+    Cc = x.shape[1]
+    ctx.check(
+        ctx.lib.sd2_groupnorm_fwd(ctx.h, _p(x), x.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0), _p(stats), _p(ws), B,
+                                  HW, Cc, G, float(eps), int(silu), _s()))
+
+
+def groupnorm_bwd(ctx, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, B, HW, G, silu, dx_add=None):
+    Cc = x.shape[1]
+    ctx.check(
+        ctx.lib.sd2_groupnorm_bwd(ctx.h, _p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), _p(beta), _p(stats),
+                                  _p(dx_add), dx_add.stride(0) if dx_add is not None else 0, _p(dx), dx.stride(0),
+                                  _p(dgamma), _p(dbeta), _p(ws), B, HW, Cc, G, int(silu), _s()))
+
+
+def layernorm_fwd(ctx, x, gamma, beta, y, stats, eps=1e-5):
+    rows, Cc = x.shape
+    ctx.check(ctx.lib.sd2_layernorm_fwd(ctx.h, _p(x), _p(gamma), _p(beta), _p(y), _p(stats), rows, Cc, float(eps), _s()))
+
+
+def layernorm_ws(ctx, rows, Cc, device):
+    return torch.empty(ctx.lib.sd2_layernorm_ws_floats(rows, Cc), dtype=torch.float32, device=device)
+
+
+def layernorm_bwd(ctx, dy, x, gamma, stats, dx, dgamma, dbeta, ws, dx_add=None):
+    rows, Cc = x.shape
+    ctx.check(
+        ctx.lib.sd2_layernorm_bwd(ctx.h, _p(dy), _p(x), _p(gamma), _p(stats), _p(dx_add), _p(dx), _p(dgamma), _p(dbeta),
+                                  _p(ws), rows, Cc, _s()))
+
+
+# ------------------------------------------------------------------------------------------------- pointwise
+def softmax_fwd(ctx, S, P, rows, cols):
+    ctx.check(ctx.lib.sd2_softmax_fwd(ctx.h, _p(S), S.stride(-2), _p(P), P.stride(-2), rows, cols, _s()))
+
+
+def softmax_bwd(ctx, P, dP, dS, rows, cols, scale):
+    ctx.check(
+        ctx.lib.sd2_softmax_bwd(ctx.h, _p(P), P.stride(-2), _p(dP), dP.stride(-2), _p(dS), dS.stride(-2), rows, cols,
+                                float(scale), _s()))
+
+
+def geglu_fwd(ctx, h, y):
+    ctx.check(ctx.lib.sd2_geglu_fwd(ctx.h, _p(h), _p(y), h.shape[0], y.shape[1], _s()))
+
+
+def geglu_bwd(ctx, h, dy, dh):
+    ctx.check(ctx.lib.sd2_geglu_bwd(ctx.h, _p(h), _p(dy), _p(dh), h.shape[0], dy.shape[1], _s()))
+
+
+def silu_fwd(ctx, x, y):
+    ctx.check(ctx.lib.sd2_silu_fwd(ctx.h, _p(x), _p(y), x.numel(), _s()))
+
+
+def silu_bwd(ctx, x, dy, dx):
+    ctx.check(ctx.lib.sd2_silu_bwd(ctx.h, _p(x), _p(dy), _p(dx), x.numel(), _s()))
+
+
+def axpby(ctx, a, alpha, b, beta, out):
+    ctx.check(ctx.lib.sd2_axpby(ctx.h, _p(a), float(alpha), _p(b), float(beta), _p(out), a.numel(), _s()))
+
+
+def copy2d(ctx, src, dst, rows, cols, accumulate=False):
+    ctx.check(ctx.lib.sd2_copy2d(ctx.h, _p(src), src.stride(0), _p(dst), dst.stride(0), rows, cols, int(accumulate), _s()))
+
+
+def upsample2x_fwd(ctx, x, y, B, H, W):
+    ctx.check(ctx.lib.sd2_upsample2x_fwd(ctx.h, _p(x), _p(y), B, H, W, x.shape[1], _s()))
+
+
+def upsample2x_bwd(ctx, dy, dx, B, H, W):
+    ctx.check(ctx.lib.sd2_upsample2x_bwd(ctx.h, _p(dy), _p(dx), B, H, W, dy.shape[1], _s()))
+
+
+def phase_split(ctx, x, planes, B, H, W):
+    ctx.check(ctx.lib.sd2_phase_split(ctx.h, _p(x), _p(planes), B, H, W, x.shape[1], _s()))
+
+
+def phase_merge(ctx, planes, x, B, H, W):
+    ctx.check(ctx.lib.sd2_phase_merge(ctx.h, _p(planes), _p(x), B, H, W, x.shape[1], _s()))
+
+
+def colsum(ctx, x, out, groups, rows_per_group, accumulate):
+    N = x.shape[1]
+    ldo = out.stride(0) if out.dim() == 2 else 0
+    ctx.check(ctx.lib.sd2_colsum(ctx.h, _p(x), x.stride(0), _p(out), ldo, groups, rows_per_group, N, int(accumulate), _s()))
+
+
+def cast_f32_to_bf16(ctx, src, dst):
+    ctx.check(ctx.lib.sd2_cast_f32_to_bf16(ctx.h, _p(src), _p(dst), src.numel(), _s()))
+
+
+def pad_cast_rows(ctx, src, cols_src, dst, cols_dst, rows):
+    ctx.check(ctx.lib.sd2_pad_cast_rows(ctx.h, _p(src), cols_src, _p(dst), cols_dst, rows, _s()))
+
+
+def unpad_accum_rows(ctx, src, cols_src, dst, cols_dst, rows, accumulate=True):
+    ctx.check(ctx.lib.sd2_unpad_accum_rows(ctx.h, _p(src), cols_src, _p(dst), cols_dst, rows, int(accumulate), _s()))
+
+
+def mse_head(ctx, pred8, noise, pred_nchw, dpred8, loss_acc, gscale, B, H, W):
+    ctx.check(
+        ctx.lib.sd2_mse_head(ctx.h, _p(pred8), _p(noise), _DT[noise.dtype], _p(pred_nchw), _p(dpred8), _p(loss_acc),
+                             float(gscale), B, H, W, _s()))

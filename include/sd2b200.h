@@ -1,0 +1,164 @@
+/* sd2b200 - C ABI of the B200-native (sm_100a) SD-2 UNet training hot path.
+ *
+ * Drop-in boundary: this is what a maintainer of fanzhongyi/diffusion binds (ctypes) underneath
+ * the unchanged Python surface `StableDiffusion.forward()/loss()` (reference diffusion/models/stable_diffusion.py:154-187)
+ * and `stable_diffusion_2(...)` (reference diffusion/models/models.py:28-112).  The reference itself has no native
+ * code; each entry point names the third-party library call it replaces.
+ *
+ * Conventions:
+ *   - every function returns 0 on success, non-zero on error (message via sd2_last_error); never throws/exits;
+ *   - the CALLER owns every buffer; the library allocates no tensor memory and keeps no pointers past a call;
+ *   - all work is enqueued on the caller-supplied stream (a cudaStream_t passed as void*), no synchronisation;
+ *   - activations are NHWC bf16 ([pixels][channels]); fp32 for statistics, gradients and master parameters;
+ *   - one sd2_ctx per host thread at a time.
+ */
+#ifndef SD2B200_H
+#define SD2B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD2_VERSION 100
+
+typedef struct sd2_ctx sd2_ctx;
+typedef void* sd2_stream; /* cudaStream_t */
+
+enum { SD2_DT_F32 = 0, SD2_DT_BF16 = 1, SD2_DT_F16 = 2 };
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+int sd2_version(void);
+int sd2_ctx_create(int device, sd2_ctx** out);
+int sd2_ctx_destroy(sd2_ctx* ctx);
+const char* sd2_last_error(sd2_ctx* ctx);
+int sd2_num_sms(sd2_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long sd2_launch_count(sd2_ctx* ctx);
+
+/* ---- K1: timesteps + noise + DDPM add_noise + sinusoidal timestep embedding ------------------------------------
+ * Replaces torch.randint / torch.randn_like / DDPMScheduler.add_noise / diffusers Timesteps
+ * (reference stable_diffusion.py:177,179,180 and the first op of :183).  Bit-exact with torch's CUDA Philox stream:
+ * `seed`/`philox_offset` are the torch CUDA generator's state; *offset_used receives how far to advance it.
+ * latents: [B,4,H,W] NCHW in lat_dtype.  Outputs: timesteps int64 [B]; noise [B,4,H,W] lat_dtype;
+ * noised_nchw (optional, lat_dtype); noised_nhwc8 bf16 [B,H,W,8] (channels 4..7 zero) feeding conv_in;
+ * temb bf16 [B, temb_dim] = [cos | sin] embedding rounded through lat_dtype like the reference. */
+int sd2_noise_sched_fwd(sd2_ctx* ctx, uint64_t seed, uint64_t philox_offset, const void* latents, int lat_dtype, int B,
+                        int H, int W, const float* alphas_cumprod, int num_train_timesteps, int64_t* out_timesteps,
+                        void* out_noise, void* out_noised_nchw, void* out_noised_nhwc8, void* out_temb, int temb_dim,
+                        uint64_t* offset_used, sd2_stream stream);
+
+/* ---- tcgen05 GEMM / implicit-GEMM convolution -----------------------------------------------------------------
+ * Replaces cuBLASLt (nn.Linear), cuDNN (nn.Conv2d) and their autograd backward (dgrad, wgrad). */
+enum { SD2_GEMM_PLAIN = 0, SD2_GEMM_CONV = 1, SD2_GEMM_CONV_WGRAD = 2 };
+enum { SD2_OUT_BF16 = 0, SD2_OUT_F32 = 1, SD2_OUT_F32_ACCUM = 2 };
+
+typedef struct sd2_operand {
+  const void* ptr; /* bf16 */
+  int mn_major;    /* 0: contraction dim contiguous ([rows][K]); 1: M/N dim contiguous ([K][rows]) */
+  int cols, rows;  /* extents: cols = contiguous dim, rows = strided dim */
+  long long ld;    /* elements between consecutive rows (multiple of 8) */
+  int nb0, nb1;    /* batch b -> (b % nb0, b / nb0); nb0 = 0: operand shared by all batches */
+  long long bs0, bs1;
+} sd2_operand;
+
+typedef struct sd2_conv_geom {
+  const void* ptr; /* bf16 NHWC activations: [n_planes][H][W] pixels of C channels, pixel stride ldc */
+  int n_planes, H, W, C;
+  long long ldc;
+  int ntaps;       /* 9 for 3x3; subsets for stride-2 phase dgrad */
+  int dh[9], dw[9], dn[9], wtap[9]; /* per tap: spatial shift, plane offset, weight tap index */
+} sd2_conv_geom;
+
+typedef struct sd2_gemm_desc {
+  int kind;
+  int M, N, K;     /* per-batch extents; K = contraction length (PLAIN / CONV_WGRAD: pixels) */
+  int batch;       /* PLAIN: number of batches; CONV_WGRAD: taps (set by library) */
+  sd2_operand A, B;   /* CONV: B = weights [tap][rows][cols] with bs0 = tap stride; A ignored (conv used) */
+  sd2_conv_geom conv; /* CONV: the A operand; CONV_WGRAD: the B operand (A = dy^T, mn_major) */
+  int out_mode;
+  void* out;
+  long long ldo;
+  int out_nb0;
+  long long out_bs0, out_bs1;
+  const void* residual; /* bf16 [M][ldr] or null */
+  long long ldr;
+  const float* bias;    /* [N] or null */
+  const float* rowbias; /* [M / rows_per_group][ld_rowbias] or null (per-image time-embedding bias) */
+  int rows_per_group;
+  long long ld_rowbias;
+  float alpha;
+  void* workspace;      /* split-K scratch (fp32), may be null */
+  long long workspace_bytes;
+  int max_splits;       /* 0 = auto */
+} sd2_gemm_desc;
+
+int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream);
+
+/* ---- normalisation (replaces ATen group_norm / layer_norm fwd+bwd under composer LPGroupNorm/LPLayerNorm,
+ *      reference diffusion/train.py:91-108) ---------------------------------------------------------------------- */
+/* x,y: bf16 [B][HW][C] (pixel stride ldx / ldy); stats: fp32 [B][G][2] = (mean, rstd); ws: fp32 scratch
+ * of sd2_groupnorm_ws_floats(B, C) floats. silu != 0 fuses y = silu(gn(x)). */
+long long sd2_groupnorm_ws_floats(int B, int C);
+int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* gamma, const float* beta, void* y,
+                      long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
+                      sd2_stream stream);
+/* dx = d(loss)/dx (+ dx_add if non-null); dgamma/dbeta accumulated (+=) in fp32 */
+int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
+                      const float* beta, const float* stats, const void* dx_add, long long ldadd, void* dx,
+                      long long lddx, float* dgamma, float* dbeta, float* ws, int B, int HW, int C, int G, int silu,
+                      sd2_stream stream);
+/* LayerNorm over the last dim of [rows][C]; stats fp32 [rows][2] */
+int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, float* stats,
+                      long long rows, int C, float eps, sd2_stream stream);
+long long sd2_layernorm_ws_floats(long long rows, int C);
+int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* gamma, const float* stats,
+                      const void* dx_add, void* dx, float* dgamma, float* dbeta, float* ws, long long rows, int C,
+                      sd2_stream stream);
+
+/* ---- attention pieces (materialised-score path; replaces xformers / SDPA, reference models.py:109-111) ------- */
+int sd2_softmax_fwd(sd2_ctx* ctx, const float* S, long long lds, void* P, long long ldp, long long rows, int cols,
+                    sd2_stream stream);
+/* dS = P * (dP - rowsum(dP*P)) * scale  -> bf16 */
+int sd2_softmax_bwd(sd2_ctx* ctx, const void* P, long long ldp, const float* dP, long long lddp, void* dS,
+                    long long ldds, long long rows, int cols, float scale, sd2_stream stream);
+
+/* ---- pointwise / layout kernels -------------------------------------------------------------------------------- */
+/* GEGLU: h = [a | g] ([rows][2*C]) -> y = a * gelu_erf(g) ([rows][C]) */
+int sd2_geglu_fwd(sd2_ctx* ctx, const void* h, void* y, long long rows, int C, sd2_stream stream);
+int sd2_geglu_bwd(sd2_ctx* ctx, const void* h, const void* dy, void* dh, long long rows, int C, sd2_stream stream);
+int sd2_silu_fwd(sd2_ctx* ctx, const void* x, void* y, long long n, sd2_stream stream);
+int sd2_silu_bwd(sd2_ctx* ctx, const void* x, const void* dy, void* dx, long long n, sd2_stream stream);
+/* out = alpha*a + beta*b (b may be null); bf16 */
+int sd2_axpby(sd2_ctx* ctx, const void* a, float alpha, const void* b, float beta, void* out, long long n,
+              sd2_stream stream);
+/* strided 2-D copy: dst[r][0..cols) = src[r][0..cols), row strides in elements (cols % 8 == 0); optional add */
+int sd2_copy2d(sd2_ctx* ctx, const void* src, long long lds, void* dst, long long ldd, long long rows, int cols,
+               int accumulate, sd2_stream stream);
+int sd2_upsample2x_fwd(sd2_ctx* ctx, const void* x, void* y, int B, int H, int W, int C, sd2_stream stream);
+int sd2_upsample2x_bwd(sd2_ctx* ctx, const void* dy, void* dx, int B, int H, int W, int C, sd2_stream stream);
+/* stride-2 phase split: x [B][H][W][C] -> planes [4][B][H/2][W/2][C], plane = (h%2)*2 + (w%2); and inverse */
+int sd2_phase_split(sd2_ctx* ctx, const void* x, void* planes, int B, int H, int W, int C, sd2_stream stream);
+int sd2_phase_merge(sd2_ctx* ctx, const void* planes, void* x, int B, int H, int W, int C, sd2_stream stream);
+/* out[g][n] (+)= sum over rows r in group g of x[r][n]; x bf16 [groups*rows_per_group][ldx]; out fp32 */
+int sd2_colsum(sd2_ctx* ctx, const void* x, long long ldx, float* out, long long ldo, int groups,
+               long long rows_per_group, int N, int accumulate, sd2_stream stream);
+int sd2_cast_f32_to_bf16(sd2_ctx* ctx, const float* src, void* dst, long long n, sd2_stream stream);
+/* dst[r][0..cols_dst) bf16 = src[r][0..cols_src) fp32 zero-padded; and the transposed accumulate-back for grads */
+int sd2_pad_cast_rows(sd2_ctx* ctx, const float* src, int cols_src, void* dst, int cols_dst, long long rows,
+                      sd2_stream stream);
+int sd2_unpad_accum_rows(sd2_ctx* ctx, const float* src, int cols_src, float* dst, int cols_dst, long long rows,
+                         int accumulate, sd2_stream stream);
+
+/* ---- loss head: replaces F.mse_loss + MeanSquaredError.update + their backward (reference
+ *      stable_diffusion.py:76,101,185-187,241-242) ---------------------------------------------------------------
+ * pred_nhwc8: bf16 [B][H][W][8] (conv_out output, 4 valid channels); noise: [B,4,H,W] in noise_dtype.
+ * Writes loss_acc[0] += sum((pred-noise)^2), loss_acc[1] += count (fp32, caller zeroes), pred_nchw in noise_dtype,
+ * and dpred_nhwc8 = gscale * 2 (pred - noise) / numel (bf16, channels 4..7 zero). */
+int sd2_mse_head(sd2_ctx* ctx, const void* pred_nhwc8, const void* noise, int noise_dtype, void* pred_nchw,
+                 void* dpred_nhwc8, float* loss_acc, float gscale, int B, int H, int W, sd2_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD2B200_H */

@@ -1,0 +1,402 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (ctypes) and checked against
+torch reference ops on the same device (fp32 math on the bf16-rounded inputs)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from diffusion_b200 import ops
+    return ops.get_ctx(torch.device('cuda', 0))
+
+
+def bf(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return (torch.randn(*shape, device='cuda', generator=g) * scale).to(torch.bfloat16)
+
+
+def close(a, b, rtol=2e-2, atol=None, name=''):
+    a, b = a.float(), b.float()
+    if atol is None:
+        atol = 2e-2 * b.abs().max().item() + 1e-6
+    err = (a - b).abs()
+    ok = bool((err <= atol + rtol * b.abs()).all())
+    assert ok, f'{name}: max err {err.max().item():.4g} (ref max {b.abs().max().item():.4g}, atol {atol:.3g})'
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize('shape', [(16, 4, 32, 32), (16, 4, 64, 64), (2, 4, 32, 32), (3, 4, 8, 8)])
+def test_k1_bit_exact(ctx, dtype, shape):
+    from diffusion_b200 import ops
+    from oracle.ddpm import DDPMScheduler
+    from oracle.unet import get_timestep_embedding
+    dev = torch.device('cuda', 0)
+    sched = DDPMScheduler()
+    latents = torch.randn(*shape, device=dev).to(dtype)
+    torch.manual_seed(17)
+    gen = torch.cuda.default_generators[0]
+    seed, off0 = gen.initial_seed(), gen.get_offset()
+    # reference order (stable_diffusion.py:177,179,180)
+    ts_ref = torch.randint(0, 1000, (shape[0],), device=dev)
+    noise_ref = torch.randn_like(latents)
+    noised_ref = sched.add_noise(latents, noise_ref, ts_ref)
+    off_ref = gen.get_offset()
+    ac = sched.alphas_cumprod.to(dev)
+    ts, noise, nhwc8, temb, nchw, used = ops.noise_sched_fwd(ctx, latents, ac, seed, off0, 320, want_noised_nchw=True)
+    torch.cuda.synchronize()
+    assert used == off_ref - off0, 'philox offset bookkeeping differs from torch'
+    assert torch.equal(ts, ts_ref), 'timesteps not bit-exact'
+    assert torch.equal(noise.view(torch.int16 if dtype != torch.float32 else torch.int32),
+                       noise_ref.view(torch.int16 if dtype != torch.float32 else torch.int32)), 'noise not bit-exact'
+    close(nchw, noised_ref, rtol=1e-2, atol=1e-2, name='noised')
+    assert (nchw.float() - noised_ref.float()).abs().max().item() <= 2 * 2.0**-7 * noised_ref.float().abs().max().item()
+    # nhwc8 view of the same values
+    ref8 = noised_ref.permute(0, 2, 3, 1).to(torch.bfloat16)
+    close(nhwc8[..., :4], ref8, rtol=1e-2, atol=2e-2, name='noised_nhwc8')
+    assert float(nhwc8[..., 4:].abs().max()) == 0.0
+    temb_ref = get_timestep_embedding(ts_ref, 320, True, 0).to(dtype).to(torch.bfloat16)
+    close(temb, temb_ref, rtol=0, atol=1e-2, name='temb')
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+LIN_SHAPES = [
+    (256, 320, 320), (16384, 320, 320), (1024, 1280, 5120), (4096, 640, 2560), (2048, 2560, 320), (256, 1280, 11520),
+    (16, 1280, 320), (1232, 640, 1024), (300, 192, 136), (128, 64, 64), (77, 80, 1024), (2048, 5120, 640),
+]
+
+
+@pytest.mark.parametrize('M,N,K', LIN_SHAPES)
+def test_linear_fwd(ctx, M, N, K):
+    from diffusion_b200 import ops
+    x, w = bf(M, K, seed=1), bf(N, K, scale=K**-0.5, seed=2)
+    bias = torch.randn(N, device='cuda')
+    res = bf(M, N, seed=3)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+    ops.linear_fwd(ctx, x, w, out, bias=bias, residual=res, workspace=ws)
+    ref = x.float() @ w.float().t() + bias + res.float()
+    close(out, ref, name=f'linear_fwd {M}x{N}x{K}')
+    out2 = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+    ops.linear_fwd(ctx, x, w, out2)  # no workspace -> no split-K
+    close(out2, x.float() @ w.float().t(), name=f'linear_fwd plain {M}x{N}x{K}')
+
+
+@pytest.mark.parametrize('M,N,K', LIN_SHAPES)
+def test_linear_dgrad(ctx, M, N, K):
+    from diffusion_b200 import ops
+    dy, w = bf(M, N, seed=4), bf(N, K, scale=N**-0.5, seed=5)
+    dx = torch.empty(M, K, dtype=torch.bfloat16, device='cuda')
+    ops.linear_dgrad(ctx, dy, w, dx)
+    close(dx, dy.float() @ w.float(), name=f'linear_dgrad {M}x{N}x{K}')
+
+
+@pytest.mark.parametrize('M,N,K', LIN_SHAPES)
+def test_linear_wgrad(ctx, M, N, K):
+    from diffusion_b200 import ops
+    dy, x = bf(M, N, seed=6), bf(M, K, seed=7)
+    dw = torch.ones(N, K, dtype=torch.float32, device='cuda')
+    ops.linear_wgrad(ctx, dy, x, dw)
+    ref = dy.float().t() @ x.float() + 1.0
+    close(dw, ref, rtol=1e-3, atol=1e-3 * ref.abs().max().item(), name=f'linear_wgrad {M}x{N}x{K}')
+
+
+def test_linear_f32_rowbias_alpha(ctx):
+    from diffusion_b200 import ops
+    M, N, K = 2048, 320, 640
+    x, w = bf(M, K, seed=1), bf(N, K, scale=K**-0.5, seed=2)
+    rb = torch.randn(M // 256, N, device='cuda')
+    out = torch.empty(M, N, dtype=torch.float32, device='cuda')
+    ops.linear_fwd(ctx, x, w, out, rowbias=rb, rows_per_group=256, alpha=0.125, out_f32=True)
+    ref = 0.125 * (x.float() @ w.float().t()) + rb.repeat_interleave(256, 0)
+    close(out, ref, rtol=1e-3, atol=1e-3, name='f32 rowbias')
+
+
+# ------------------------------------------------------------------------------------------------ conv
+CONV_SHAPES = [(16, 32, 32, 320, 320), (16, 16, 16, 640, 640), (16, 8, 8, 1280, 1280), (16, 4, 4, 1280, 1280),
+               (2, 32, 32, 64, 64), (2, 4, 4, 256, 256), (2, 8, 8, 384, 128), (4, 64, 64, 64, 128), (2, 32, 32, 8, 64),
+               (2, 32, 32, 64, 8), (16, 4, 4, 2560, 1280)]
+
+
+def conv_ref(x, w9, B, H, W, stride=1):
+    Cin = x.shape[1]
+    xn = x.float().view(B, H, W, Cin).permute(0, 3, 1, 2)
+    wt = w9.float().view(3, 3, w9.shape[1], Cin).permute(2, 3, 0, 1)
+    return F.conv2d(xn, wt, padding=1, stride=stride)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', CONV_SHAPES)
+def test_conv3x3_fwd(ctx, B, H, W, Cin, Cout):
+    from diffusion_b200 import ops
+    x = bf(B * H * W, Cin, seed=1)
+    w9 = bf(9, Cout, Cin, scale=(9 * Cin)**-0.5, seed=2)
+    bias = torch.randn(Cout, device='cuda')
+    rb = torch.randn(B, Cout, device='cuda')
+    res = bf(B * H * W, Cout, seed=3)
+    out = torch.empty(B * H * W, Cout, dtype=torch.bfloat16, device='cuda')
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+    ops.conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=bias, rowbias=rb, residual=res, workspace=ws)
+    ref = conv_ref(x, w9, B, H, W) + bias[None, :, None, None] + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout) + res.float()
+    close(out, ref, name='conv fwd')
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', CONV_SHAPES)
+def test_conv3x3_dgrad_wgrad(ctx, B, H, W, Cin, Cout):
+    from diffusion_b200 import ops
+    x = bf(B * H * W, Cin, seed=1).float().requires_grad_(True)
+    w9 = bf(9, Cout, Cin, scale=(9 * Cin)**-0.5, seed=2).float().requires_grad_(True)
+    dy = bf(B * H * W, Cout, seed=5)
+    y = conv_ref(x, w9, B, H, W).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    y.backward(dy.float())
+    dx = torch.empty(B * H * W, Cin, dtype=torch.bfloat16, device='cuda')
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+    ops.conv3x3_dgrad(ctx, dy, B, H, W, w9.detach().to(torch.bfloat16), dx, workspace=ws)
+    close(dx, x.grad, name='conv dgrad')
+    dw = torch.zeros(9, Cout, Cin, dtype=torch.float32, device='cuda')
+    ops.conv3x3_wgrad(ctx, dy, x.detach().to(torch.bfloat16), B, H, W, dw)
+    close(dw, w9.grad, rtol=2e-3, atol=2e-3 * w9.grad.abs().max().item(), name='conv wgrad')
+
+
+@pytest.mark.parametrize('B,H,W,Cc', [(16, 32, 32, 320), (16, 8, 8, 1280), (2, 32, 32, 64), (2, 8, 8, 256)])
+def test_conv3x3_stride2(ctx, B, H, W, Cc):
+    from diffusion_b200 import ops
+    Ho, Wo = H // 2, W // 2
+    x = bf(B * H * W, Cc, seed=1).float().requires_grad_(True)
+    w9 = bf(9, Cc, Cc, scale=(9 * Cc)**-0.5, seed=2).float().requires_grad_(True)
+    dy = bf(B * Ho * Wo, Cc, seed=5)
+    y = conv_ref(x, w9, B, H, W, stride=2).permute(0, 2, 3, 1).reshape(B * Ho * Wo, Cc)
+    y.backward(dy.float())
+    xb, wb = x.detach().to(torch.bfloat16), w9.detach().to(torch.bfloat16)
+    planes = torch.empty(4 * B * Ho * Wo, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.phase_split(ctx, xb, planes, B, H, W)
+    taps = ops.taps_stride2(B)
+    out = torch.empty(B * Ho * Wo, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.conv3x3_fwd(ctx, planes, B, Ho, Wo, wb, out, taps=taps, n_planes=4 * B)
+    close(out, y.detach(), name='s2 fwd')
+    dw = torch.zeros(9, Cc, Cc, dtype=torch.float32, device='cuda')
+    ops.conv3x3_wgrad(ctx, dy, planes, B, Ho, Wo, dw, taps=taps, n_planes=4 * B)
+    close(dw, w9.grad, rtol=2e-3, atol=2e-3 * w9.grad.abs().max().item(), name='s2 wgrad')
+    dplanes = torch.empty_like(planes)
+    for plane, sub in ops.taps_stride2_dgrad().items():
+        ops.conv3x3_dgrad(ctx, dy, B, Ho, Wo, wb, dplanes[plane * B * Ho * Wo:(plane + 1) * B * Ho * Wo], taps=sub)
+    dx = torch.empty(B * H * W, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.phase_merge(ctx, dplanes, dx, B, H, W)
+    close(dx, x.grad, name='s2 dgrad')
+
+
+# ------------------------------------------------------------------------------------------------ batched (attention)
+@pytest.mark.parametrize('B,heads,Nq,Nk', [(2, 5, 1024, 1024), (2, 10, 256, 77), (1, 4, 64, 64), (2, 2, 16, 77)])
+def test_attention_pieces(ctx, B, heads, Nq, Nk):
+    from diffusion_b200 import ops
+    Cc, d = heads * 64, 64
+    q, k, v = bf(B * Nq, Cc, seed=1), bf(B * Nk, Cc, seed=2), bf(B * Nk, Cc, seed=3)
+    ldp = (Nk + 7) // 8 * 8
+    S = torch.empty(B * heads, Nq, ldp, dtype=torch.float32, device='cuda')
+    scale = d**-0.5
+    # S[b,h] = scale * Q[b,:,h,:] K[b,:,h,:]^T ; batch index = b*heads + h -> nb0 = heads
+    ops.bmm(ctx, q, 0, (d, Nq, Cc, d, Nq * Cc), k, 0, (d, Nk, Cc, d, Nk * Cc), S, (ldp, Nq * ldp, heads * Nq * ldp), Nq, Nk, d,
+            B * heads, heads, alpha=scale, out_f32=True)
+    qh = q.float().view(B, Nq, heads, d).transpose(1, 2)
+    kh = k.float().view(B, Nk, heads, d).transpose(1, 2)
+    vh = v.float().view(B, Nk, heads, d).transpose(1, 2)
+    S_ref = (qh @ kh.transpose(-1, -2)) * scale
+    close(S.view(B, heads, Nq, ldp)[..., :Nk], S_ref, rtol=1e-3, atol=1e-3 * S_ref.abs().max().item(), name='QK^T')
+    P = torch.empty(B * heads, Nq, ldp, dtype=torch.bfloat16, device='cuda')
+    ops.softmax_fwd(ctx, S, P, B * heads * Nq, Nk)
+    P_ref = torch.softmax(S_ref, -1)
+    close(P.view(B, heads, Nq, ldp)[..., :Nk], P_ref, rtol=1e-2, atol=4e-3, name='softmax')
+    O = torch.empty(B * Nq, Cc, dtype=torch.bfloat16, device='cuda')
+    # O[b,:,h,:] = P[b,h] V[b,:,h,:]   (V read MN-major: [Nk rows][d contiguous])
+    ops.bmm(ctx, P, 0, (Nk, Nq, ldp, Nq * ldp, heads * Nq * ldp), v, 1, (d, Nk, Cc, d, Nk * Cc), O, (Cc, d, Nq * Cc), Nq, d, Nk,
+            B * heads, heads)
+    O_ref = (P.view(B, heads, Nq, ldp)[..., :Nk].float() @ vh).transpose(1, 2).reshape(B * Nq, Cc)
+    close(O, O_ref, name='PV')
+    # backward pieces: dP = dO V^T ; dS ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
+    dO = bf(B * Nq, Cc, seed=9)
+    dP = torch.empty(B * heads, Nq, ldp, dtype=torch.float32, device='cuda')
+    ops.bmm(ctx, dO, 0, (d, Nq, Cc, d, Nq * Cc), v, 0, (d, Nk, Cc, d, Nk * Cc), dP, (ldp, Nq * ldp, heads * Nq * ldp), Nq, Nk, d,
+            B * heads, heads, out_f32=True)
+    doh = dO.float().view(B, Nq, heads, d).transpose(1, 2)
+    dP_ref = doh @ vh.transpose(-1, -2)
+    close(dP.view(B, heads, Nq, ldp)[..., :Nk], dP_ref, rtol=1e-3, atol=1e-3 * dP_ref.abs().max().item(), name='dP')
+    dS = torch.empty(B * heads, Nq, ldp, dtype=torch.bfloat16, device='cuda')
+    ops.softmax_bwd(ctx, P, dP, dS, B * heads * Nq, Nk, scale)
+    Pf = P.view(B, heads, Nq, ldp)[..., :Nk].float()
+    dS_ref = Pf * (dP_ref - (dP_ref * Pf).sum(-1, keepdim=True)) * scale
+    close(dS.view(B, heads, Nq, ldp)[..., :Nk], dS_ref, rtol=2e-2, atol=2e-2 * dS_ref.abs().max().item(), name='dS')
+    dSf = dS.view(B, heads, Nq, ldp)[..., :Nk].float()
+    dQ = torch.empty(B * Nq, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.bmm(ctx, dS, 0, (Nk, Nq, ldp, Nq * ldp, heads * Nq * ldp), k, 1, (d, Nk, Cc, d, Nk * Cc), dQ, (Cc, d, Nq * Cc), Nq, d, Nk,
+            B * heads, heads)
+    close(dQ, (dSf @ kh).transpose(1, 2).reshape(B * Nq, Cc), name='dQ')
+    dK = torch.empty(B * Nk, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.bmm(ctx, dS, 1, (Nk, Nq, ldp, Nq * ldp, heads * Nq * ldp), q, 1, (d, Nq, Cc, d, Nq * Cc), dK, (Cc, d, Nk * Cc), Nk, d, Nq,
+            B * heads, heads)
+    close(dK, (dSf.transpose(-1, -2) @ qh).transpose(1, 2).reshape(B * Nk, Cc), name='dK')
+    dV = torch.empty(B * Nk, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.bmm(ctx, P, 1, (Nk, Nq, ldp, Nq * ldp, heads * Nq * ldp), dO, 1, (d, Nq, Cc, d, Nq * Cc), dV, (Cc, d, Nk * Cc), Nk, d, Nq,
+            B * heads, heads)
+    close(dV, (Pf.transpose(-1, -2) @ doh).transpose(1, 2).reshape(B * Nk, Cc), name='dV')
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize('B,HW,Cc,silu', [(16, 1024, 320, 1), (16, 64, 1920, 1), (2, 1024, 64, 1), (2, 16, 256, 0),
+                                         (4, 4096, 320, 0), (16, 16, 2560, 1), (2, 256, 192, 1)])
+def test_groupnorm(ctx, B, HW, Cc, silu):
+    from diffusion_b200 import ops
+    G, eps = 32, 1e-5
+    x = (bf(B * HW, Cc, seed=1).float() * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = (torch.randn(Cc, device='cuda') * 0.2 + 1).requires_grad_(True)
+    beta = (torch.randn(Cc, device='cuda') * 0.2).requires_grad_(True)
+    y = torch.empty_like(x)
+    stats = torch.empty(B, G, 2, device='cuda')
+    ws = ops.groupnorm_ws(ctx, B, Cc, x.device)
+    ops.groupnorm_fwd(ctx, x, gamma.detach(), beta.detach(), y, stats, ws, B, HW, G, eps, silu)
+    xr = x.float().view(B, HW, Cc).permute(0, 2, 1).requires_grad_(True)
+    ref = F.group_norm(xr, G, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    close(y.view(B, HW, Cc), ref.permute(0, 2, 1), rtol=1e-2, atol=2e-2, name='gn fwd')
+    dy = bf(B * HW, Cc, seed=2)
+    add = bf(B * HW, Cc, seed=3)
+    ref.backward(dy.float().view(B, HW, Cc).permute(0, 2, 1))
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(Cc, device='cuda'), torch.zeros(Cc, device='cuda')
+    ops.groupnorm_bwd(ctx, dy, x, gamma.detach(), beta.detach(), stats, dx, dg, db, ws, B, HW, G, silu, dx_add=add)
+    close(dx.view(B, HW, Cc), xr.grad.permute(0, 2, 1) + add.float().view(B, HW, Cc), rtol=2e-2, atol=3e-2, name='gn dx')
+    close(dg, gamma.grad, rtol=1e-2, atol=1e-2 * gamma.grad.abs().max().item(), name='gn dgamma')
+    close(db, beta.grad, rtol=1e-2, atol=1e-2 * beta.grad.abs().max().item(), name='gn dbeta')
+
+
+@pytest.mark.parametrize('rows,Cc', [(16384, 320), (4096, 640), (1024, 1280), (2048, 64), (32, 256)])
+def test_layernorm(ctx, rows, Cc):
+    from diffusion_b200 import ops
+    x = (bf(rows, Cc, seed=1).float() * 2 + 0.5).to(torch.bfloat16)
+    gamma = (torch.randn(Cc, device='cuda') * 0.2 + 1).requires_grad_(True)
+    beta = (torch.randn(Cc, device='cuda') * 0.2).requires_grad_(True)
+    y = torch.empty_like(x)
+    stats = torch.empty(rows, 2, device='cuda')
+    ops.layernorm_fwd(ctx, x, gamma.detach(), beta.detach(), y, stats)
+    xr = x.float().requires_grad_(True)
+    ref = F.layer_norm(xr, (Cc,), gamma, beta, 1e-5)
+    close(y, ref, rtol=1e-2, atol=2e-2, name='ln fwd')
+    dy, add = bf(rows, Cc, seed=2), bf(rows, Cc, seed=3)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(Cc, device='cuda'), torch.zeros(Cc, device='cuda')
+    ws = ops.layernorm_ws(ctx, rows, Cc, x.device)
+    ops.layernorm_bwd(ctx, dy, x, gamma.detach(), stats, dx, dg, db, ws, dx_add=add)
+    close(dx, xr.grad + add.float(), rtol=2e-2, atol=3e-2, name='ln dx')
+    close(dg, gamma.grad, rtol=1e-2, atol=1e-2 * gamma.grad.abs().max().item(), name='ln dgamma')
+    close(db, beta.grad, rtol=1e-2, atol=1e-2 * beta.grad.abs().max().item(), name='ln dbeta')
+
+
+# ------------------------------------------------------------------------------------------------ pointwise
+def test_geglu_silu_axpby(ctx):
+    from diffusion_b200 import ops
+    rows, Cc = 4096, 1280
+    h = bf(rows, 2 * Cc, seed=1)
+    y = torch.empty(rows, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.geglu_fwd(ctx, h, y)
+    hr = h.float().requires_grad_(True)
+    a, g = hr.chunk(2, -1)
+    ref = a * F.gelu(g)
+    close(y, ref, name='geglu fwd')
+    dy = bf(rows, Cc, seed=2)
+    ref.backward(dy.float())
+    dh = torch.empty_like(h)
+    ops.geglu_bwd(ctx, h, dy, dh)
+    close(dh, hr.grad, name='geglu bwd')
+    x = bf(16, 1280, seed=3)
+    ys = torch.empty_like(x)
+    ops.silu_fwd(ctx, x, ys)
+    xr = x.float().requires_grad_(True)
+    rs = F.silu(xr)
+    close(ys, rs, name='silu')
+    d2 = bf(16, 1280, seed=4)
+    rs.backward(d2.float())
+    dxs = torch.empty_like(x)
+    ops.silu_bwd(ctx, x, d2, dxs)
+    close(dxs, xr.grad, name='silu bwd')
+    o = torch.empty_like(x)
+    ops.axpby(ctx, x, 0.5, d2, 2.0, o)
+    close(o, 0.5 * x.float() + 2 * d2.float(), name='axpby')
+
+
+def test_layout_kernels(ctx):
+    from diffusion_b200 import ops
+    B, H, W, Cc = 2, 8, 8, 64
+    x = bf(B * H * W, Cc, seed=1)
+    y = torch.empty(B * 4 * H * W, Cc, dtype=torch.bfloat16, device='cuda')
+    ops.upsample2x_fwd(ctx, x, y, B, H, W)
+    ref = F.interpolate(x.float().view(B, H, W, Cc).permute(0, 3, 1, 2), scale_factor=2.0, mode='nearest')
+    assert torch.equal(y.view(B, 2 * H, 2 * W, Cc).float(), ref.permute(0, 2, 3, 1))
+    dy = bf(B * 4 * H * W, Cc, seed=2)
+    dx = torch.empty_like(x)
+    ops.upsample2x_bwd(ctx, dy, dx, B, H, W)
+    dref = dy.float().view(B, H, 2, W, 2, Cc).sum((2, 4))
+    close(dx.view(B, H, W, Cc), dref, name='upsample bwd')
+    planes = torch.empty_like(x)
+    ops.phase_split(ctx, x, planes, B, H, W)
+    xv = x.view(B, H, W, Cc)
+    for ph in range(2):
+        for pw in range(2):
+            assert torch.equal(planes.view(4, B, H // 2, W // 2, Cc)[ph * 2 + pw], xv[:, ph::2, pw::2])
+    back = torch.empty_like(x)
+    ops.phase_merge(ctx, planes, back, B, H, W)
+    assert torch.equal(back, x)
+    cat = torch.zeros(B * H * W, 2 * Cc, dtype=torch.bfloat16, device='cuda')
+    ops.copy2d(ctx, x, cat[:, Cc:], B * H * W, Cc)
+    assert torch.equal(cat[:, Cc:], x) and float(cat[:, :Cc].abs().max()) == 0
+    ops.copy2d(ctx, x, cat[:, Cc:], B * H * W, Cc, accumulate=True)
+    close(cat[:, Cc:], 2 * x.float(), name='copy2d acc')
+
+
+@pytest.mark.parametrize('groups,rpg,N', [(1, 16384, 320), (16, 1024, 320), (16, 16, 1280), (1, 37, 64)])
+def test_colsum(ctx, groups, rpg, N):
+    from diffusion_b200 import ops
+    x = bf(groups * rpg, N, seed=1)
+    out = torch.full((groups, N), 7.0, device='cuda')
+    ops.colsum(ctx, x, out, groups, rpg, accumulate=False)
+    ref = x.float().view(groups, rpg, N).sum(1)
+    close(out, ref, rtol=1e-3, atol=1e-3 * ref.abs().max().item(), name='colsum')
+    ops.colsum(ctx, x, out, groups, rpg, accumulate=True)
+    close(out, 2 * ref, rtol=1e-3, atol=2e-3 * ref.abs().max().item(), name='colsum acc')
+
+
+def test_casts_and_mse(ctx):
+    from diffusion_b200 import ops
+    src = torch.randn(1000003, device='cuda')
+    dst = torch.empty(1000003, dtype=torch.bfloat16, device='cuda')
+    ops.cast_f32_to_bf16(ctx, src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+    w = torch.randn(9 * 320, 4, device='cuda')
+    wp = torch.empty(9 * 320, 8, dtype=torch.bfloat16, device='cuda')
+    ops.pad_cast_rows(ctx, w, 4, wp, 8, 9 * 320)
+    assert torch.equal(wp[:, :4], w.to(torch.bfloat16)) and float(wp[:, 4:].abs().max()) == 0
+    g8 = torch.randn(9 * 320, 8, device='cuda')
+    g4 = torch.ones(9 * 320, 4, device='cuda')
+    ops.unpad_accum_rows(ctx, g8, 8, g4, 4, 9 * 320)
+    close(g4, g8[:, :4] + 1, rtol=1e-6, atol=1e-6, name='unpad')
+    B, H, W = 16, 32, 32
+    for dt in (torch.bfloat16, torch.float32, torch.float16):
+        pred8 = bf(B * H * W, 8, seed=1)
+        noise = torch.randn(B, 4, H, W, device='cuda').to(dt)
+        pred_nchw = torch.empty_like(noise)
+        dpred = torch.empty_like(pred8)
+        acc = torch.zeros(2, device='cuda')
+        ops.mse_head(ctx, pred8, noise, pred_nchw, dpred, acc, 1.0, B, H, W)
+        p = pred8[:, :4].float().view(B, H, W, 4).permute(0, 3, 1, 2)
+        loss_ref = F.mse_loss(p, noise.float())
+        assert abs(acc[0].item() / acc[1].item() - loss_ref.item()) < 1e-4 * loss_ref.item()
+        assert acc[1].item() == B * 4 * H * W
+        close(pred_nchw, p.to(dt), rtol=0, atol=0, name='pred nchw')
+        dref = (2 * (p - noise.float()) / p.numel()).permute(0, 2, 3, 1).reshape(B * H * W, 4)
+        close(dpred[:, :4], dref, rtol=1e-2, atol=1e-2 * dref.abs().max().item(), name='dpred')
+        assert float(dpred[:, 4:].abs().max()) == 0
