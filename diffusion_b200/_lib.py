@@ -100,6 +100,11 @@ SIGNATURES = {
     'sd2_launch_count': (_ll, [_vp]),
     'sd2_noise_sched_fwd': (_i, [_vp, _u64, _u64, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i,
                                  C.POINTER(_u64), _vp]),
+    'sd2_timestep_embedding': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp]),
+    'sd2_nchw4_to_nhwc8': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    'sd2_nhwc8_to_nchw4': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'sd2_scale_by_scalar': (_i, [_vp, _vp, _ll, _vp, _vp]),
+    'sd2_fill_f32': (_i, [_vp, _vp, _ll, _f, _vp]),
     'sd2_gemm': (_i, [_vp, C.POINTER(GemmDesc), _vp]),
     'sd2_groupnorm_ws_floats': (_ll, [_i, _i]),
     'sd2_groupnorm_fwd': (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
@@ -148,3 +153,37 @@ def load(auto_build=True):
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class DryLib:
+    """Host-logic test double (SD2_DRY_RUN=1, used by the CPU test-suite only): every entry point type-checks its
+    arguments against SIGNATURES and counts the call; nothing is computed.  Never used by the product path."""
+
+    def __init__(self):
+        self.calls = {}
+        for name, (res, args) in SIGNATURES.items():
+            setattr(self, name, self._make(name, res, args))
+
+    def _make(self, name, res, args):
+
+        def fn(*a):
+            if len(a) != len(args):
+                raise TypeError(f'{name}: expected {len(args)} arguments, got {len(a)}')
+            for i, (t, v) in enumerate(zip(args, a)):
+                try:
+                    if hasattr(t, 'from_param'):
+                        t.from_param(v)
+                except Exception as e:  # noqa: BLE001
+                    raise TypeError(f'{name}: argument {i} ({v!r}) is not a {t}') from e
+            self.calls[name] = self.calls.get(name, 0) + 1
+            if name == 'sd2_groupnorm_ws_floats':
+                return a[0] * 32 * a[1] * 2
+            if name == 'sd2_layernorm_ws_floats':
+                return 148 * 4 * a[1] * 2
+            if name == 'sd2_last_error':
+                return b'dry run'
+            if name == 'sd2_num_sms':
+                return 148
+            return 0
+
+        return fn

@@ -107,9 +107,107 @@ __global__ void __launch_bounds__(256) k1_noise_sched_kernel(uint64_t seed, uint
   }
 }
 
+template <typename T>
+__global__ void temb_kernel(const int64_t* __restrict__ ts, int B, __nv_bfloat16* __restrict__ out, int temb_dim) {
+  const int half = temb_dim / 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)B * half;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / half), i = (int)(e % half);
+    const float exponent = __fdiv_rn(__fmul_rn(-9.210340371976184f, (float)i), (float)half);
+    const float arg = __fmul_rn((float)ts[b], expf(exponent));
+    out[(long long)b * temb_dim + i] = __float2bfloat16_rn(Cvt<T>::rt(cosf(arg)));
+    out[(long long)b * temb_dim + half + i] = __float2bfloat16_rn(Cvt<T>::rt(sinf(arg)));
+  }
+}
+
+// one thread per pixel
+template <typename T>
+__global__ void nchw4_to_nhwc8_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int HW) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * HW;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, hw = i % HW;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = Cvt<T>::ld(src, (b * 4 + c) * HW + hw);
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = 0u; u.w = 0u;
+    *reinterpret_cast<uint4*>(dst + i * 8) = u;
+  }
+}
+template <typename T>
+__global__ void nhwc8_to_nchw4_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, int B, int HW) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * HW;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, hw = i % HW;
+    const uint4 u = *reinterpret_cast<const uint4*>(src + i * 8);
+    const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+    Cvt<T>::st(dst, (b * 4 + 0) * HW + hw, a.x);
+    Cvt<T>::st(dst, (b * 4 + 1) * HW + hw, a.y);
+    Cvt<T>::st(dst, (b * 4 + 2) * HW + hw, c.x);
+    Cvt<T>::st(dst, (b * 4 + 3) * HW + hw, c.y);
+  }
+}
+__global__ void scale_by_scalar_kernel(__nv_bfloat16* __restrict__ x, long long n, const float* __restrict__ scalar) {
+  const float s = *scalar;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * s);
+}
+__global__ void fill_f32_kernel2(float* __restrict__ x, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
+}
+
 }  // namespace sd2
 
 using namespace sd2;
+
+#define SD2_DISPATCH_DT(dt, CALL)                                  \
+  if ((dt) == SD2_DT_F32) { CALL(float); }                         \
+  else if ((dt) == SD2_DT_BF16) { CALL(__nv_bfloat16); }           \
+  else if ((dt) == SD2_DT_F16) { CALL(__half); }                   \
+  else return fail(ctx, "unsupported dtype");
+
+extern "C" int sd2_timestep_embedding(sd2_ctx* ctx, const int64_t* timesteps, int B, void* out_temb, int temb_dim,
+                                      int round_dtype, sd2_stream stream_) {
+  if (!ctx) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int blocks = grid_for((long long)B * temb_dim / 2, 256, ctx->num_sms);
+#define CALL(T) temb_kernel<T><<<blocks, 256, 0, stream>>>(timesteps, B, reinterpret_cast<__nv_bfloat16*>(out_temb), temb_dim)
+  SD2_DISPATCH_DT(round_dtype, CALL)
+#undef CALL
+  return check_launch(ctx, "timestep_embedding");
+}
+extern "C" int sd2_nchw4_to_nhwc8(sd2_ctx* ctx, const void* src, int src_dtype, void* dst, int B, int H, int W,
+                                  sd2_stream stream_) {
+  if (!ctx) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int blocks = grid_for((long long)B * H * W, 256, ctx->num_sms);
+#define CALL(T) nchw4_to_nhwc8_kernel<T><<<blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H * W)
+  SD2_DISPATCH_DT(src_dtype, CALL)
+#undef CALL
+  return check_launch(ctx, "nchw4_to_nhwc8");
+}
+extern "C" int sd2_nhwc8_to_nchw4(sd2_ctx* ctx, const void* src, void* dst, int dst_dtype, int B, int H, int W,
+                                  sd2_stream stream_) {
+  if (!ctx) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int blocks = grid_for((long long)B * H * W, 256, ctx->num_sms);
+#define CALL(T) nhwc8_to_nchw4_kernel<T><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<T*>(dst), B, H * W)
+  SD2_DISPATCH_DT(dst_dtype, CALL)
+#undef CALL
+  return check_launch(ctx, "nhwc8_to_nchw4");
+}
+extern "C" int sd2_scale_by_scalar(sd2_ctx* ctx, void* x, long long n, const float* scalar, sd2_stream stream_) {
+  if (!ctx) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  scale_by_scalar_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(x), n, scalar);
+  return check_launch(ctx, "scale_by_scalar");
+}
+extern "C" int sd2_fill_f32(sd2_ctx* ctx, float* x, long long n, float value, sd2_stream stream_) {
+  if (!ctx) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  fill_f32_kernel2<<<grid_for(n, 256, ctx->num_sms), 256, 0, stream>>>(x, n, value);
+  return check_launch(ctx, "fill_f32");
+}
 
 extern "C" int sd2_noise_sched_fwd(sd2_ctx* ctx, uint64_t seed, uint64_t philox_offset, const void* latents,
                                    int lat_dtype, int B, int H, int W, const float* alphas_cumprod,

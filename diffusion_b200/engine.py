@@ -1,0 +1,627 @@
+"""Static kernel schedule of the SD-2 UNet training step (forward + backward) over the sm_100a kernels.
+
+The engine walks the parameter skeleton (diffusion_b200/unet.py) once per input geometry and records two flat lists
+of kernel launches (`fwd`, `bwd`) over pre-allocated NHWC bf16 activation buffers - no per-step Python graph, no
+autograd tape inside the UNet; after warm-up the two lists are replayed as CUDA graphs.
+
+Parameters live in three flat arenas with identical offsets:
+  p32 - fp32 master weights (the nn.Parameters are views into it; 3x3 conv weights are stored [kh][kw][Cout][Cin] and
+        exposed with PyTorch's (Cout,Cin,kh,kw) shape through strides, so the implicit-GEMM kernels read/write them
+        coalesced and no per-step transposition exists),
+  p16 - bf16 shadow used by the tensor-core kernels (one cast kernel per step),
+  g32 - fp32 gradients (param.grad are views into it; one contiguous buffer for the DDP all-reduce).
+
+Reference semantics restated: diffusers UNet2DConditionModel.forward, called from
+reference diffusion/models/stable_diffusion.py:183; bf16 autocast + fp32 accumulation/statistics as composer runs it
+(reference diffusion/train.py:91-108).
+"""
+from functools import partial
+
+import torch
+
+from diffusion_b200 import ops
+
+BF16 = torch.bfloat16
+
+
+class Node:
+    """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
+    __slots__ = ('data', 'grad', 'gw', 'M', 'C')
+
+    def __init__(self, data):
+        self.data, self.grad, self.gw = data, None, False
+        self.M, self.C = data.shape
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class ParamArena:
+
+    def __init__(self, unet, device):
+        self.entries = {}
+        off = 0
+        plist = list(unet.named_parameters())
+        for name, p in plist:
+            if p.device != device:
+                raise RuntimeError('all UNet parameters must live on the engine device')
+            self.entries[name] = (off, p.numel(), tuple(p.shape))
+            off = _align(off + p.numel())
+        self.total = off
+        self.p32 = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g32 = torch.zeros(off, dtype=torch.float32, device=device)
+        self.p16 = torch.zeros(off, dtype=BF16, device=device)
+        self.params = {}
+        with torch.no_grad():
+            for name, p in plist:
+                view = self._view(self.p32, name)
+                view.copy_(p.data.float())
+                p.data = view
+                p.grad = None
+                self.params[name] = p
+
+    def _view(self, arena, name):
+        off, n, shape = self.entries[name]
+        flat = arena[off:off + n]
+        if len(shape) == 4 and shape[-1] == 3:  # 3x3 conv: storage [kh][kw][Cout][Cin]
+            return flat.view(3, 3, shape[0], shape[1]).permute(2, 3, 0, 1)
+        return flat.view(shape)
+
+    def storage(self, arena, name):
+        """Storage-layout view: [9, Cout, Cin] for 3x3 convs, [Cout, Cin] for 1x1 convs, natural shape otherwise."""
+        off, n, shape = self.entries[name]
+        flat = arena[off:off + n]
+        if len(shape) == 4 and shape[-1] == 3:
+            return flat.view(9, shape[0], shape[1])
+        if len(shape) == 4:
+            return flat.view(shape[0], shape[1])
+        return flat.view(shape)
+
+    def fused(self, arena, names):
+        """One [sum(out), in] view over adjacent linear weights (to_q|to_k|to_v)."""
+        off0, _, shape0 = self.entries[names[0]]
+        rows, off = 0, off0
+        for nm in names:
+            o, n, shape = self.entries[nm]
+            if o != off or shape[1] != shape0[1]:
+                raise RuntimeError(f'parameters {names} are not adjacent in the arena')
+            off, rows = o + n, rows + shape[0]
+        return arena[off0:off].view(rows, shape0[1])
+
+    def grad_view(self, name):
+        return self._view(self.g32, name)
+
+    def bound(self):
+        return all(p.data_ptr() == self.p32.data_ptr() + 4 * self.entries[n][0] for n, p in self.params.items())
+
+
+class Engine:
+
+    def __init__(self, unet, B, H, W, L, shared=None):
+        dev = unet.conv_in.weight.device
+        self.ctx = ops.get_ctx(dev)
+        self.dev = dev
+        self.cfg = unet.config
+        self.arena = shared.arena if (shared is not None and shared.arena.bound()) else ParamArena(unet, dev)
+        self.B, self.H, self.W, self.L = B, H, W, L
+        self.fwd, self.bwd, self._bwd_builders = [], [], []
+        self.ws = shared.ws if shared is not None else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.G = self.cfg['norm_num_groups']
+        cmax = max(self.cfg['block_out_channels']) * 2
+        self.gn_ws = ops.groupnorm_ws(self.ctx, B, cmax, dev)
+        self.ln_ws = ops.layernorm_ws(self.ctx, B * H * W, max(self.cfg['block_out_channels']), dev)
+        self.act_bytes = 0
+        self._smax = 0  # elements of the largest attention score matrix
+        self._attn_recs = []
+        # static inputs (written by K1 / the prep kernels)
+        c0 = self.cfg['block_out_channels'][0]
+        self.in_x8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
+        self.in_temb = torch.zeros(B, c0, dtype=BF16, device=dev)
+        self.in_ctx = torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
+        self.pred8 = None
+        self.dpred8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
+        self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._build()
+        self.S32 = torch.empty(max(self._smax, 8), dtype=torch.float32, device=dev)
+        self.dS16 = torch.empty(max(self._smax, 8), dtype=BF16, device=dev)
+        for rec in self._attn_recs:
+            rec['S'] = self.S32
+            rec['dS'] = self.dS16
+        self.graph_fwd = self.graph_bwd = None
+
+    def params_bound(self):
+        return self.arena.bound()
+
+    def prepare_inputs(self, sample, timestep, enc):
+        """Inputs of a plain `unet(sample, timestep, encoder_hidden_states)` call -> the static input buffers."""
+        B = self.B
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], dtype=torch.int64, device=self.dev)
+        timestep = timestep.to(device=self.dev, dtype=torch.int64).expand(B).contiguous()
+        ops.timestep_embedding(self.ctx, timestep, self.in_temb, sample.dtype)
+        ops.nchw4_to_nhwc8(self.ctx, sample.contiguous(), self.in_x8, B, self.H, self.W)
+        self.set_context(enc)
+
+    def set_context(self, enc):
+        self.in_ctx.copy_(enc.reshape(self.B * self.L, -1))
+
+    # ---------------------------------------------------------------------------------------------- helpers
+    def node(self, M, C, dtype=BF16):
+        t = torch.empty(M, C, dtype=dtype, device=self.dev)
+        self.act_bytes += t.numel() * t.element_size()
+        return Node(t)
+
+    def buf(self, *shape, dtype=BF16, zero=False):
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
+        self.act_bytes += t.numel() * t.element_size()
+        return t
+
+    def w16(self, name):
+        return self.arena.storage(self.arena.p16, name)
+
+    def p32(self, name):
+        return self.arena.storage(self.arena.p32, name)
+
+    def g32(self, name):
+        return self.arena.storage(self.arena.g32, name)
+
+    def f(self, fn, *a, **k):
+        self.fwd.append(partial(fn, self.ctx, *a, **k))
+
+    def b(self, fn, *a, **k):
+        self.bwd.append(partial(fn, self.ctx, *a, **k))
+
+    def _gout(self, node):
+        """Gradient buffer of `node` for a backward op to write: (buffer, accumulate?)."""
+        if node.grad is None:
+            node.grad = torch.empty_like(node.data)
+            self.act_bytes += node.grad.numel() * 2
+        acc, node.gw = node.gw, True
+        return node.grad, acc
+
+    def _pass(self, g, node):
+        """d(node) += g for an identity edge: alias the buffer when node has no gradient yet."""
+        if not node.gw:
+            node.grad, node.gw = g, True
+        else:
+            self.b(ops.axpby, node.grad, 1.0, g, 1.0, node.grad)
+
+    # ---------------------------------------------------------------------------------------------- records
+    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None):
+        w = self.w16(wname) if w16 is None else w16
+        gwv = self.g32(wname) if gw is None else gw
+        N = w.shape[0]
+        out = self.node(x.M, N)
+        bias = self.p32(bname) if bname else None
+        self.f(ops.linear_fwd, x.data, w, out.data, bias=bias, residual=residual.data if residual else None,
+               workspace=self.ws)
+
+        def bwd():
+            g = out.grad
+            assert out.gw, f'no gradient reaches output of {wname}'
+            if residual is not None:
+                self._pass(g, residual)
+            if x is not None and x.data is not self.in_ctx and x.data is not self.in_temb:
+                gx, acc = self._gout(x)
+                self.b(ops.linear_dgrad, g, w, gx, residual=gx if acc else None, workspace=self.ws)
+            self.b(ops.linear_wgrad, g, x.data, gwv)
+            if bname:
+                self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    def silu(self, x):
+        out = self.node(x.M, x.C)
+        self.f(ops.silu_fwd, x.data, out.data)
+
+        def bwd():
+            gx, acc = self._gout(x)
+            assert not acc
+            self.b(ops.silu_bwd, x.data, out.grad, gx)
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    def groupnorm(self, x, prefix, eps, silu, HW):
+        y = self.node(x.M, x.C)
+        stats = self.buf(self.B, self.G, 2, dtype=torch.float32)
+        gamma, beta = self.p32(prefix + '.weight'), self.p32(prefix + '.bias')
+        self.f(ops.groupnorm_fwd, x.data, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
+
+        def bwd():
+            assert y.gw
+            gx, acc = self._gout(x)
+            self.b(ops.groupnorm_bwd, y.grad, x.data, gamma, beta, stats, gx, self.g32(prefix + '.weight'),
+                   self.g32(prefix + '.bias'), self.gn_ws, self.B, HW, self.G, silu, dx_add=gx if acc else None)
+
+        self._bwd_builders.append(bwd)
+        return y
+
+    def layernorm(self, x, prefix):
+        y = self.node(x.M, x.C)
+        stats = self.buf(x.M, 2, dtype=torch.float32)
+        gamma, beta = self.p32(prefix + '.weight'), self.p32(prefix + '.bias')
+        self.f(ops.layernorm_fwd, x.data, gamma, beta, y.data, stats)
+
+        def bwd():
+            assert y.gw
+            gx, acc = self._gout(x)
+            self.b(ops.layernorm_bwd, y.grad, x.data, gamma, stats, gx, self.g32(prefix + '.weight'),
+                   self.g32(prefix + '.bias'), self.ln_ws, dx_add=gx if acc else None)
+
+        self._bwd_builders.append(bwd)
+        return y
+
+    def conv3(self, x, Hc, Wc, prefix, rowbias=None, residual=None, rowbias_bwd=None):
+        """3x3 stride-1 conv (+bias +per-image bias +residual).  rowbias_bwd(g) is called with the output gradient."""
+        w, bias = self.w16(prefix + '.weight'), self.p32(prefix + '.bias')
+        out = self.node(x.M, w.shape[1])
+        B = self.B
+        self.f(ops.conv3x3_fwd, x.data, B, Hc, Wc, w, out.data, bias=bias, rowbias=rowbias,
+               residual=residual.data if residual else None, workspace=self.ws)
+
+        def bwd():
+            g = out.grad
+            assert out.gw
+            if residual is not None:
+                self._pass(g, residual)
+            if rowbias_bwd is not None:
+                rowbias_bwd(g)
+            gx, acc = self._gout(x)
+            self.b(ops.conv3x3_dgrad, g, B, Hc, Wc, w, gx, residual=gx if acc else None, workspace=self.ws)
+            self.b(ops.conv3x3_wgrad, g, x.data, B, Hc, Wc, self.g32(prefix + '.weight'))
+            self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, x.M, True)
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    def downsample(self, x, Hc, Wc, prefix):
+        B, C = self.B, x.C
+        Ho, Wo = Hc // 2, Wc // 2
+        Mo = B * Ho * Wo
+        w, bias = self.w16(prefix + '.weight'), self.p32(prefix + '.bias')
+        planes = self.buf(4 * Mo, C)
+        out = self.node(Mo, C)
+        taps = ops.taps_stride2(B)
+        self.f(ops.phase_split, x.data, planes, B, Hc, Wc)
+        self.f(ops.conv3x3_fwd, planes, B, Ho, Wo, w, out.data, bias=bias, taps=taps, n_planes=4 * B, workspace=self.ws)
+
+        def bwd():
+            g = out.grad
+            assert out.gw
+            dplanes = self.buf(4 * Mo, C)
+            for plane, sub in ops.taps_stride2_dgrad().items():
+                self.b(ops.conv3x3_dgrad, g, B, Ho, Wo, w, dplanes[plane * Mo:(plane + 1) * Mo], taps=sub, workspace=self.ws)
+            gx, acc = self._gout(x)
+            if acc:
+                tmp = self.buf(x.M, C)
+                self.b(ops.phase_merge, dplanes, tmp, B, Hc, Wc)
+                self.b(ops.copy2d, tmp, gx, x.M, C, True)
+            else:
+                self.b(ops.phase_merge, dplanes, gx, B, Hc, Wc)
+            self.b(ops.conv3x3_wgrad, g, planes, B, Ho, Wo, self.g32(prefix + '.weight'), taps=taps, n_planes=4 * B)
+            self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, Mo, True)
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    def upsample(self, x, Hc, Wc, prefix):
+        up = self.node(4 * x.M, x.C)
+        self.f(ops.upsample2x_fwd, x.data, up.data, self.B, Hc, Wc)
+
+        def bwd():
+            assert up.gw
+            gx, acc = self._gout(x)
+            assert not acc
+            self.b(ops.upsample2x_bwd, up.grad, gx, self.B, Hc, Wc)
+
+        self._bwd_builders.append(bwd)
+        return self.conv3(up, 2 * Hc, 2 * Wc, prefix)
+
+    def concat(self, a, b_):
+        out = self.node(a.M, a.C + b_.C)
+        self.f(ops.copy2d, a.data, out.data[:, :a.C], a.M, a.C)
+        self.f(ops.copy2d, b_.data, out.data[:, a.C:], a.M, b_.C)
+
+        def bwd():
+            assert out.gw
+            ga, acc_a = self._gout(a)
+            self.b(ops.copy2d, out.grad[:, :a.C], ga, a.M, a.C, acc_a)
+            gb, acc_b = self._gout(b_)
+            self.b(ops.copy2d, out.grad[:, a.C:], gb, a.M, b_.C, acc_b)
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    def geglu(self, h):
+        y = self.node(h.M, h.C // 2)
+        self.f(ops.geglu_fwd, h.data, y.data)
+
+        def bwd():
+            gh, acc = self._gout(h)
+            assert not acc
+            self.b(ops.geglu_bwd, h.data, y.grad, gh)
+
+        self._bwd_builders.append(bwd)
+        return y
+
+    def attention(self, q, k, v, qn, kvn, q_col, k_col, v_col, Nq, Nk, heads, C):
+        """softmax(q k^T / sqrt(d)) v per (image, head).  q/k/v are column slices (offset *_col) of nodes qn / kvn.
+        Materialised-score path: S (fp32 scratch) -> P (bf16, saved) -> O."""
+        B, d = self.B, C // heads
+        ldp = _align(Nk, 8)
+        scale = float(d)**-0.5
+        nbh = B * heads
+        P = self.buf(nbh, Nq, ldp)
+        out = self.node(B * Nq, C)
+        self._smax = max(self._smax, nbh * Nq * ldp)
+        rec = {}
+        self._attn_recs.append(rec)
+        ldq, ldk = qn.C, kvn.C
+        qd = (d, Nq, ldq, d, Nq * ldq)
+        kd = (d, Nk, ldk, d, Nk * ldk)
+        sd = (ldp, Nq * ldp, heads * Nq * ldp)
+        pd = (Nk, Nq, ldp, Nq * ldp, heads * Nq * ldp)
+        od = (C, d, Nq * C)
+
+        nS = nbh * Nq * ldp
+
+        def fwd_fn(ctx):
+            S = rec['S'][:nS].view(nbh, Nq, ldp)
+            ops.bmm(ctx, q, 0, qd, k, 0, kd, S, sd, Nq, Nk, d, nbh, heads, alpha=scale, out_f32=True)
+            ops.softmax_fwd(ctx, S, P, nbh * Nq, Nk)
+            ops.bmm(ctx, P, 0, pd, v, 1, kd, out.data, od, Nq, d, Nk, nbh, heads)
+
+        self.fwd.append(partial(fwd_fn, self.ctx))
+
+        def bwd():
+            assert out.gw
+            dO = out.grad
+            if qn.grad is None:
+                qn.grad = torch.empty_like(qn.data)
+            if kvn.grad is None:
+                kvn.grad = torch.empty_like(kvn.data)
+            dq = qn.grad[:, q_col:q_col + C]
+            dk = kvn.grad[:, k_col:k_col + C]
+            dv = kvn.grad[:, v_col:v_col + C]
+            dqd = (ldq, d, Nq * ldq)
+            dkd = (ldk, d, Nk * ldk)
+            dOd = (d, Nq, C, d, Nq * C)
+
+            def bwd_fn(ctx):
+                dP, dS = rec['S'][:nS].view(nbh, Nq, ldp), rec['dS'][:nS].view(nbh, Nq, ldp)
+                ops.bmm(ctx, dO, 0, dOd, v, 0, kd, dP, sd, Nq, Nk, d, nbh, heads, out_f32=True)
+                ops.softmax_bwd(ctx, P, dP, dS, nbh * Nq, Nk, scale)
+                ops.bmm(ctx, dS, 0, pd, k, 1, kd, dq, dqd, Nq, d, Nk, nbh, heads)
+                ops.bmm(ctx, dS, 1, pd, q, 1, qd, dk, dkd, Nk, d, Nq, nbh, heads)
+                ops.bmm(ctx, P, 1, pd, dO, 1, dOd, dv, dkd, Nk, d, Nq, nbh, heads)
+
+            self.bwd.append(partial(bwd_fn, self.ctx))
+            qn.gw = kvn.gw = True
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    # ---------------------------------------------------------------------------------------------- blocks
+    def resnet(self, x, prefix, Hc, Wc, semb):
+        arena = self.arena
+        B, HW = self.B, Hc * Wc
+        eps = self.cfg['norm_eps']
+        cout = arena.entries[prefix + '.conv1.weight'][2][0]
+        has_sc = (prefix + '.conv_shortcut.weight') in arena.entries
+        a1 = self.groupnorm(x, prefix + '.norm1', eps, 1, HW)
+        # time-embedding projection -> per-image bias (fp32) added in conv1's epilogue
+        wt, bt = self.w16(prefix + '.time_emb_proj.weight'), self.p32(prefix + '.time_emb_proj.bias')
+        rb = self.buf(B, cout, dtype=torch.float32)
+        self.f(ops.linear_fwd, semb.data, wt, rb, bias=bt, out_f32=True)
+        d_tp32 = self.buf(B, cout, dtype=torch.float32)
+        d_tp16 = self.buf(B, cout)
+
+        def tproj_bwd(g):
+            # d(time_emb_proj out)[b] = sum over the image's pixels of d(h1)
+            self.b(ops.colsum, g, d_tp32, B, HW, False)
+            self.b(ops.cast_f32_to_bf16, d_tp32.view(-1), d_tp16.view(-1))
+            gs, acc = self._gout(semb)
+            self.b(ops.linear_dgrad, d_tp16, wt, gs, residual=gs if acc else None)
+            self.b(ops.linear_wgrad, d_tp16, semb.data, self.g32(prefix + '.time_emb_proj.weight'))
+            self.b(ops.colsum, d_tp16, self.g32(prefix + '.time_emb_proj.bias'), 1, B, True)
+
+        h1 = self.conv3(a1, Hc, Wc, prefix + '.conv1', rowbias=rb, rowbias_bwd=tproj_bwd)
+        a2 = self.groupnorm(h1, prefix + '.norm2', eps, 1, HW)
+        sc = self.linear(x, prefix + '.conv_shortcut.weight', prefix + '.conv_shortcut.bias') if has_sc else x
+        return self.conv3(a2, Hc, Wc, prefix + '.conv2', residual=sc)
+
+    def transformer(self, x, prefix, Hc, Wc, heads):
+        arena = self.arena
+        C, B, L = x.C, self.B, self.L
+        HW = Hc * Wc
+        n = self.groupnorm(x, prefix + '.norm', 1e-6, 0, HW)
+        h0 = self.linear(n, prefix + '.proj_in.weight', prefix + '.proj_in.bias')
+        tb = prefix + '.transformer_blocks.0'
+        # --- self attention
+        l1 = self.layernorm(h0, tb + '.norm1')
+        names = [tb + '.attn1.to_q.weight', tb + '.attn1.to_k.weight', tb + '.attn1.to_v.weight']
+        qkv = self.linear(l1, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names))
+        o1 = self.attention(qkv.data[:, :C], qkv.data[:, C:2 * C], qkv.data[:, 2 * C:], qkv, qkv, 0, C, 2 * C, HW, HW, heads, C)
+        h1 = self.linear(o1, tb + '.attn1.to_out.0.weight', tb + '.attn1.to_out.0.bias', residual=h0)
+        # --- cross attention over the text context
+        l2 = self.layernorm(h1, tb + '.norm2')
+        q2 = self.linear(l2, tb + '.attn2.to_q.weight')
+        names = [tb + '.attn2.to_k.weight', tb + '.attn2.to_v.weight']
+        kv = self.linear(self.ctx_node, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names))
+        o2 = self.attention(q2.data, kv.data[:, :C], kv.data[:, C:], q2, kv, 0, 0, C, HW, L, heads, C)
+        h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1)
+        # --- GEGLU feed-forward
+        l3 = self.layernorm(h2, tb + '.norm3')
+        ff1 = self.linear(l3, tb + '.ff.net.0.proj.weight', tb + '.ff.net.0.proj.bias')
+        gg = self.geglu(ff1)
+        h3 = self.linear(gg, tb + '.ff.net.2.weight', tb + '.ff.net.2.bias', residual=h2)
+        return self.linear(h3, prefix + '.proj_out.weight', prefix + '.proj_out.bias', residual=x)
+
+    # ---------------------------------------------------------------------------------------------- whole network
+    def _build(self):
+        cfg, arena, ctx = self.cfg, self.arena, self.ctx
+        B, H, W = self.B, self.H, self.W
+        boc, heads = cfg['block_out_channels'], cfg['attention_head_dim']
+        M = B * H * W
+        # ---- per-step weight refresh: fp32 master -> bf16 shadow (+ the two padded special cases)
+        self.f(ops.cast_f32_to_bf16, arena.p32, arena.p16)
+        cin_w = self.p32('conv_in.weight')  # storage [9, C0, 4]
+        self.w_in16 = self.buf(9, boc[0], 8)
+        self.f(ops.pad_cast_rows, cin_w.reshape(-1), 4, self.w_in16, 8, 9 * boc[0])
+        self.b_out8 = self.buf(8, dtype=torch.float32, zero=True)
+        b_out = self.p32('conv_out.bias')
+        self.f(ops.unpad_accum_rows, b_out, 4, self.b_out8, 4, 1, False)
+        # ---- time embedding
+        self.ctx_node = Node(self.in_ctx)
+        temb = Node(self.in_temb)
+        e1 = self.linear(temb, 'time_embedding.linear_1.weight', 'time_embedding.linear_1.bias')
+        emb = self.linear(self.silu(e1), 'time_embedding.linear_2.weight', 'time_embedding.linear_2.bias')
+        semb = self.silu(emb)
+        # ---- conv_in (4 latent channels zero-padded to 8 so that the pixel stride is 16 bytes)
+        x8 = Node(self.in_x8)
+        x = self.node(M, boc[0])
+        self.f(ops.conv3x3_fwd, x8.data, B, H, W, self.w_in16, x.data, bias=self.p32('conv_in.bias'), workspace=self.ws)
+        gw_in = self.buf(9, boc[0], 8, dtype=torch.float32)
+        x0 = x  # `x` is rebound below; the closure must keep conv_in's own output node
+
+        def conv_in_bwd():
+            assert x0.gw
+            self.b(ops.fill_f32, gw_in, 0.0)
+            self.b(ops.conv3x3_wgrad, x0.grad, x8.data, B, H, W, gw_in)
+            self.b(ops.unpad_accum_rows, gw_in.view(-1), 8, self.g32('conv_in.weight').reshape(-1), 4, 9 * boc[0], True)
+            self.b(ops.colsum, x0.grad, self.g32('conv_in.bias'), 1, M, True)
+
+        self._bwd_builders.append(conv_in_bwd)
+        # ---- down path
+        skips = [(x, H, W)]
+        Hc, Wc = H, W
+        for i, t in enumerate(cfg['down_block_types']):
+            for j in range(cfg['layers_per_block']):
+                x = self.resnet(x, f'down_blocks.{i}.resnets.{j}', Hc, Wc, semb)
+                if t == 'CrossAttnDownBlock2D':
+                    x = self.transformer(x, f'down_blocks.{i}.attentions.{j}', Hc, Wc, heads[i])
+                skips.append((x, Hc, Wc))
+            if i != len(boc) - 1:
+                x = self.downsample(x, Hc, Wc, f'down_blocks.{i}.downsamplers.0.conv')
+                Hc, Wc = Hc // 2, Wc // 2
+                skips.append((x, Hc, Wc))
+        # ---- mid
+        x = self.resnet(x, 'mid_block.resnets.0', Hc, Wc, semb)
+        x = self.transformer(x, 'mid_block.attentions.0', Hc, Wc, heads[-1])
+        x = self.resnet(x, 'mid_block.resnets.1', Hc, Wc, semb)
+        # ---- up path
+        rheads = heads[::-1]
+        for i, t in enumerate(cfg['up_block_types']):
+            for j in range(cfg['layers_per_block'] + 1):
+                s, sh, sw = skips.pop()
+                assert (sh, sw) == (Hc, Wc)
+                x = self.resnet(self.concat(x, s), f'up_blocks.{i}.resnets.{j}', Hc, Wc, semb)
+                if t == 'CrossAttnUpBlock2D':
+                    x = self.transformer(x, f'up_blocks.{i}.attentions.{j}', Hc, Wc, rheads[i])
+            if i != len(boc) - 1:
+                x = self.upsample(x, Hc, Wc, f'up_blocks.{i}.upsamplers.0.conv')
+                Hc, Wc = Hc * 2, Wc * 2
+        # ---- head: GN + SiLU + conv_out (4 output channels padded to 8)
+        n = self.groupnorm(x, 'conv_norm_out', cfg['norm_eps'], 1, H * W)
+        w_out = self.w16('conv_out.weight')  # [9, 4, C0]
+        self.pred8 = self.buf(M, 8)
+        self.f(ops.conv3x3_fwd, n.data, B, H, W, w_out, self.pred8, bias=self.b_out8, workspace=self.ws)
+        gb8 = self.buf(8, dtype=torch.float32)
+
+        def head_bwd():
+            g = self.dpred8
+            gn_, acc = self._gout(n)
+            self.b(ops.conv3x3_dgrad, g, B, H, W, w_out, gn_, workspace=self.ws)
+            self.b(ops.conv3x3_wgrad, g[:, :4], n.data, B, H, W, self.g32('conv_out.weight'))
+            self.b(ops.colsum, g, gb8, 1, M, False)
+            self.b(ops.unpad_accum_rows, gb8, 8, self.g32('conv_out.bias'), 4, 1, True)
+
+        self._bwd_builders.append(head_bwd)
+        for builder in reversed(self._bwd_builders):
+            builder()
+        self._bwd_builders = None
+
+    # ---------------------------------------------------------------------------------------------- execution
+    def run_forward(self):
+        if self.graph_fwd is not None:
+            self.graph_fwd.replay()
+        else:
+            for op in self.fwd:
+                op()
+
+    def run_backward(self):
+        if self.graph_bwd is not None:
+            self.graph_bwd.replay()
+        else:
+            for op in self.bwd:
+                op()
+
+    def capture_graphs(self):
+        """Capture the two static schedules as CUDA graphs (call after at least one eager warm-up step)."""
+        torch.cuda.synchronize(self.dev)
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(gf, stream=s):
+                for op in self.fwd:
+                    op()
+            with torch.cuda.graph(gb, stream=s):
+                for op in self.bwd:
+                    op()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph_fwd, self.graph_bwd = gf, gb
+
+    @property
+    def launches_per_step(self):
+        return getattr(self, '_launches_per_step', None)
+
+
+# ==================================================================================================== autograd glue
+class _UNetFn(torch.autograd.Function):
+    """pred = UNet(sample, t, ctx) on the static schedule; backward replays the backward schedule and hands the
+    parameter gradients (views of the g32 arena) to autograd."""
+
+    @staticmethod
+    def forward(ctx_, eng, prepared, sample, timestep, enc, *params):
+        if not prepared:
+            eng.prepare_inputs(sample, timestep, enc)
+        eng.run_forward()
+        pred = torch.empty(eng.B, 4, eng.H, eng.W, dtype=BF16, device=eng.dev)
+        ops.nhwc8_to_nchw4(eng.ctx, eng.pred8, pred, eng.B, eng.H, eng.W)
+        ctx_.eng = eng
+        ctx_.nparams = len(params)
+        return pred
+
+    @staticmethod
+    def backward(ctx_, gpred):
+        eng = ctx_.eng
+        arena = eng.arena
+        fused = getattr(eng, '_fused_loss_scale', None)
+        if fused is not None and gpred.stride() == (0, 0, 0, 0):
+            # gradient comes from the fused MSE head: dpred8 already holds 2(pred-noise)/N, scale by dL/dloss
+            ops.scale_by_scalar(eng.ctx, eng.dpred8, fused)
+            eng._fused_loss_scale = None
+        else:
+            ops.nchw4_to_nhwc8(eng.ctx, gpred.contiguous(), eng.dpred8, eng.B, eng.H, eng.W)
+        plist = list(arena.params.items())
+        accumulate = all(p.grad is not None and p.grad.data_ptr() == arena.g32.data_ptr() + 4 * arena.entries[n][0]
+                         for n, p in plist)
+        if not accumulate:
+            arena.g32.zero_()
+        eng.run_backward()
+        if accumulate:  # gradients were accumulated in place into the arena that param.grad already views
+            return (None,) * (5 + ctx_.nparams)
+        grads = tuple(arena.grad_view(n) for n, _ in plist)
+        return (None, None, None, None, None) + grads
+
+
+def unet_apply(unet, sample, timestep, enc, prepared=False):
+    B, C, H, W = sample.shape
+    eng = unet.engine(B, H, W, enc.shape[1])
+    params = [p for _, p in eng.arena.params.items()]
+    return _UNetFn.apply(eng, prepared, sample, timestep, enc, *params)

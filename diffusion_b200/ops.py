@@ -15,7 +15,11 @@ _ctx_cache = {}
 class Ctx:
     """Per-device sd2_ctx handle."""
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, dry=False):
+        self.dry = dry
+        if dry:  # CPU host-logic tests only (SD2_DRY_RUN=1): calls are type-checked and counted, nothing runs
+            self.lib, self.h, self.device, self.num_sms = L.DryLib(), C.c_void_p(1), torch.device('cpu'), 148
+            return
         self.lib = L.load()
         h = C.c_void_p()
         rc = self.lib.sd2_ctx_create(int(device_index), C.byref(h))
@@ -35,7 +39,16 @@ class Ctx:
         return self.lib.sd2_launch_count(self.h)
 
 
+def dry_run():
+    import os
+    return os.environ.get('SD2_DRY_RUN') == '1'
+
+
 def get_ctx(device=None) -> Ctx:
+    if dry_run():
+        if 'dry' not in _ctx_cache:
+            _ctx_cache['dry'] = Ctx(0, dry=True)
+        return _ctx_cache['dry']
     idx = torch.cuda.current_device() if device is None else torch.device(device).index
     if idx is None:
         idx = torch.cuda.current_device()
@@ -49,6 +62,8 @@ def _p(t):
 
 
 def _s():
+    if dry_run():
+        return None
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -56,7 +71,8 @@ _DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F
 
 
 # ------------------------------------------------------------------------------------------------- K1
-def noise_sched_fwd(ctx, latents, alphas_cumprod, seed, offset, temb_dim, want_noised_nchw=False):
+def noise_sched_fwd(ctx, latents, alphas_cumprod, seed, offset, temb_dim, want_noised_nchw=False, out_nhwc8=None,
+                    out_temb=None):
     """Returns (timesteps i64[B], noise like latents, noised_nhwc8 bf16 [B,H,W,8], temb bf16 [B,temb_dim],
     noised_nchw or None, philox offset consumed)."""
     B, Cc, H, W = latents.shape
@@ -64,8 +80,8 @@ def noise_sched_fwd(ctx, latents, alphas_cumprod, seed, offset, temb_dim, want_n
     dev = latents.device
     ts = torch.empty(B, dtype=torch.int64, device=dev)
     noise = torch.empty_like(latents)
-    nhwc8 = torch.empty(B, H, W, 8, dtype=torch.bfloat16, device=dev)
-    temb = torch.empty(B, temb_dim, dtype=torch.bfloat16, device=dev)
+    nhwc8 = out_nhwc8 if out_nhwc8 is not None else torch.empty(B, H, W, 8, dtype=torch.bfloat16, device=dev)
+    temb = out_temb if out_temb is not None else torch.empty(B, temb_dim, dtype=torch.bfloat16, device=dev)
     nchw = torch.empty_like(latents) if want_noised_nchw else None
     used = C.c_uint64(0)
     ctx.check(
@@ -73,6 +89,28 @@ def noise_sched_fwd(ctx, latents, alphas_cumprod, seed, offset, temb_dim, want_n
                                     _p(alphas_cumprod), alphas_cumprod.numel(), _p(ts), _p(noise), _p(nchw), _p(nhwc8),
                                     _p(temb), temb_dim, C.byref(used), _s()))
     return ts, noise, nhwc8, temb, nchw, used.value
+
+
+def timestep_embedding(ctx, timesteps, out_temb, round_dtype):
+    ctx.check(
+        ctx.lib.sd2_timestep_embedding(ctx.h, _p(timesteps), timesteps.numel(), _p(out_temb), out_temb.shape[1],
+                                       _DT[round_dtype], _s()))
+
+
+def nchw4_to_nhwc8(ctx, src, dst8, B, H, W):
+    ctx.check(ctx.lib.sd2_nchw4_to_nhwc8(ctx.h, _p(src), _DT[src.dtype], _p(dst8), B, H, W, _s()))
+
+
+def nhwc8_to_nchw4(ctx, src8, dst, B, H, W):
+    ctx.check(ctx.lib.sd2_nhwc8_to_nchw4(ctx.h, _p(src8), _p(dst), _DT[dst.dtype], B, H, W, _s()))
+
+
+def scale_by_scalar(ctx, x, scalar):
+    ctx.check(ctx.lib.sd2_scale_by_scalar(ctx.h, _p(x), x.numel(), _p(scalar), _s()))
+
+
+def fill_f32(ctx, x, value):
+    ctx.check(ctx.lib.sd2_fill_f32(ctx.h, _p(x), x.numel(), float(value), _s()))
 
 
 # ------------------------------------------------------------------------------------------------- GEMM
@@ -188,8 +226,9 @@ def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None
 
 
 def conv3x3_dgrad(ctx, dy, B, H, W, w9, dx, residual=None, taps=None, n_planes=None, workspace=None):
-    """dx[B*H*W, Cin] = sum_taps shift(dy)[.., Cout] @ w9[tap'][Cout][Cin]  (weights read MN-major)."""
-    Cout, Cin = dy.shape[1], w9.shape[2]
+    """dx[B*H*W, Cin] = sum_taps shift(dy)[.., Cout] @ w9[tap'][Cout][Cin]  (weights read MN-major).
+    dy may carry zero-padded channels beyond w9's Cout (conv_out: 4 real of 8)."""
+    Cout, Cin = w9.shape[1], w9.shape[2]
     d = L.GemmDesc()
     d.kind, d.M, d.N, d.K, d.batch = L.GEMM_CONV, B * H * W, Cin, 9 * Cout, 1
     d.conv = _conv_geom(dy.data_ptr(), n_planes or B, H, W, Cout, dy.stride(0), taps or TAPS_DGRAD)

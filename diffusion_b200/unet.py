@@ -138,7 +138,8 @@ class UNet2DConditionModel(nn.Module):
         """Static kernel schedule for one input geometry (built lazily, cached)."""
         from diffusion_b200.engine import Engine
         dev = self.conv_in.weight.device
-        if dev.type != 'cuda':
+        from diffusion_b200.ops import dry_run
+        if dev.type != 'cuda' and not dry_run():
             raise RuntimeError('diffusion_b200 runs on sm_100a GPUs only (no CPU fallback): move the model to CUDA')
         key = (B, H, W, ctx_len, dev.index)
         eng = self._engines.get(key)

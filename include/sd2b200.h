@@ -48,6 +48,18 @@ int sd2_noise_sched_fwd(sd2_ctx* ctx, uint64_t seed, uint64_t philox_offset, con
                         void* out_noise, void* out_noised_nchw, void* out_noised_nhwc8, void* out_temb, int temb_dim,
                         uint64_t* offset_used, sd2_stream stream);
 
+/* Stand-alone pieces of K1 for callers that bring their own timesteps / samples (diffusers-style
+ * `unet(sample, timestep, encoder_hidden_states)`): sinusoidal embedding and NCHW(4) <-> NHWC(8) bf16 conversion. */
+int sd2_timestep_embedding(sd2_ctx* ctx, const int64_t* timesteps, int B, void* out_temb, int temb_dim, int round_dtype,
+                           sd2_stream stream);
+int sd2_nchw4_to_nhwc8(sd2_ctx* ctx, const void* src, int src_dtype, void* dst_nhwc8, int B, int H, int W,
+                       sd2_stream stream);
+int sd2_nhwc8_to_nchw4(sd2_ctx* ctx, const void* src_nhwc8, void* dst, int dst_dtype, int B, int H, int W,
+                       sd2_stream stream);
+/* x (bf16, n elements) *= *scalar (fp32 on device) */
+int sd2_scale_by_scalar(sd2_ctx* ctx, void* x, long long n, const float* scalar, sd2_stream stream);
+int sd2_fill_f32(sd2_ctx* ctx, float* x, long long n, float value, sd2_stream stream);
+
 /* ---- tcgen05 GEMM / implicit-GEMM convolution -----------------------------------------------------------------
  * Replaces cuBLASLt (nn.Linear), cuDNN (nn.Conv2d) and their autograd backward (dgrad, wgrad). */
 enum { SD2_GEMM_PLAIN = 0, SD2_GEMM_CONV = 1, SD2_GEMM_CONV_WGRAD = 2 };
