@@ -24,6 +24,10 @@ from diffusion_b200 import ops
 BF16 = torch.bfloat16
 
 
+_GEMM_FUNCS = (ops.linear_fwd, ops.linear_dgrad, ops.linear_wgrad, ops.conv3x3_fwd, ops.conv3x3_dgrad, ops.conv3x3_wgrad,
+               ops.bmm)
+
+
 class Node:
     """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
     __slots__ = ('data', 'grad', 'gw', 'M', 'C')
@@ -106,14 +110,24 @@ class Engine:
         self.arena = shared.arena if (shared is not None and shared.arena.bound()) else ParamArena(unet, dev)
         self.B, self.H, self.W, self.L = B, H, W, L
         self.fwd, self.bwd, self._bwd_builders = [], [], []
+        self._touched, self.grad_ready = set(), {}
         self.ws = shared.ws if shared is not None else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         self.G = self.cfg['norm_num_groups']
         cmax = max(self.cfg['block_out_channels']) * 2
         self.gn_ws = ops.groupnorm_ws(self.ctx, B, cmax, dev)
         self.ln_ws = ops.layernorm_ws(self.ctx, B * H * W, max(self.cfg['block_out_channels']), dev)
         self.act_bytes = 0
-        self._smax = 0  # elements of the largest attention score matrix
-        self._attn_recs = []
+        # attention score scratch (S / dP in fp32, dS in bf16), shared by all layers: sized for the largest level
+        smax, hw = 8, H * W
+        for i, t in enumerate(self.cfg['down_block_types']):
+            if t == 'CrossAttnDownBlock2D':
+                smax = max(smax, B * self.cfg['attention_head_dim'][i] * hw * _align(max(hw, L), 8))
+            hw //= 4
+        smax = max(smax, B * self.cfg['attention_head_dim'][-1] * (hw * 4) * _align(max(hw * 4, L), 8))
+        self.S32 = torch.empty(smax, dtype=torch.float32, device=dev)
+        self.dS16 = torch.empty(smax, dtype=BF16, device=dev)
+        self.gemm_flops = 0  # algorithmic 2*M*N*K of every tensor-core GEMM recorded (fwd + bwd)
+        self.fwd_is_gemm, self.bwd_is_gemm = [], []
         # static inputs (written by K1 / the prep kernels)
         c0 = self.cfg['block_out_channels'][0]
         self.in_x8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
@@ -123,11 +137,6 @@ class Engine:
         self.dpred8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
         self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         self._build()
-        self.S32 = torch.empty(max(self._smax, 8), dtype=torch.float32, device=dev)
-        self.dS16 = torch.empty(max(self._smax, 8), dtype=BF16, device=dev)
-        for rec in self._attn_recs:
-            rec['S'] = self.S32
-            rec['dS'] = self.dS16
         self.graph_fwd = self.graph_bwd = None
 
     def params_bound(self):
@@ -164,13 +173,31 @@ class Engine:
         return self.arena.storage(self.arena.p32, name)
 
     def g32(self, name):
+        self._touched.add(name)  # called from backward builders only: records which builder completes this gradient
         return self.arena.storage(self.arena.g32, name)
 
     def f(self, fn, *a, **k):
         self.fwd.append(partial(fn, self.ctx, *a, **k))
+        self.fwd_is_gemm.append(fn in _GEMM_FUNCS)
+        self._count_flops(fn, a)
 
     def b(self, fn, *a, **k):
         self.bwd.append(partial(fn, self.ctx, *a, **k))
+        self.bwd_is_gemm.append(fn in _GEMM_FUNCS)
+        self._count_flops(fn, a)
+
+    def _count_flops(self, fn, a):
+        if fn in (ops.linear_fwd, ops.linear_dgrad):
+            self.gemm_flops += 2 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0 if fn is ops.linear_fwd else 1]
+        elif fn is ops.linear_wgrad:
+            self.gemm_flops += 2 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1]
+        elif fn in (ops.conv3x3_fwd, ops.conv3x3_dgrad):  # (x, B, H, W, w9, ...)
+            taps = 9
+            self.gemm_flops += 2 * a[1] * a[2] * a[3] * a[4].shape[1] * a[4].shape[2] * taps
+        elif fn is ops.conv3x3_wgrad:  # (dy, x, B, H, W, dw9)
+            self.gemm_flops += 2 * a[2] * a[3] * a[4] * a[5].shape[1] * min(a[5].shape[2], a[1].shape[1]) * 9
+        elif fn is ops.bmm:  # (..., M, N, K, batch, nb0) at positions 9..12
+            self.gemm_flops += 2 * a[9] * a[10] * a[11] * a[12]
 
     def _gout(self, node):
         """Gradient buffer of `node` for a backward op to write: (buffer, accumulate?)."""
@@ -188,9 +215,9 @@ class Engine:
             self.b(ops.axpby, node.grad, 1.0, g, 1.0, node.grad)
 
     # ---------------------------------------------------------------------------------------------- records
-    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None):
+    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None, gnames=()):
         w = self.w16(wname) if w16 is None else w16
-        gwv = self.g32(wname) if gw is None else gw
+        gwv = self.arena.storage(self.arena.g32, wname) if gw is None else gw
         N = w.shape[0]
         out = self.node(x.M, N)
         bias = self.p32(bname) if bname else None
@@ -205,6 +232,7 @@ class Engine:
             if x is not None and x.data is not self.in_ctx and x.data is not self.in_temb:
                 gx, acc = self._gout(x)
                 self.b(ops.linear_dgrad, g, w, gx, residual=gx if acc else None, workspace=self.ws)
+            self._touched.update(gnames or (wname,))
             self.b(ops.linear_wgrad, g, x.data, gwv)
             if bname:
                 self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
@@ -356,9 +384,6 @@ class Engine:
         nbh = B * heads
         P = self.buf(nbh, Nq, ldp)
         out = self.node(B * Nq, C)
-        self._smax = max(self._smax, nbh * Nq * ldp)
-        rec = {}
-        self._attn_recs.append(rec)
         ldq, ldk = qn.C, kvn.C
         qd = (d, Nq, ldq, d, Nq * ldq)
         kd = (d, Nk, ldk, d, Nk * ldk)
@@ -367,14 +392,11 @@ class Engine:
         od = (C, d, Nq * C)
 
         nS = nbh * Nq * ldp
-
-        def fwd_fn(ctx):
-            S = rec['S'][:nS].view(nbh, Nq, ldp)
-            ops.bmm(ctx, q, 0, qd, k, 0, kd, S, sd, Nq, Nk, d, nbh, heads, alpha=scale, out_f32=True)
-            ops.softmax_fwd(ctx, S, P, nbh * Nq, Nk)
-            ops.bmm(ctx, P, 0, pd, v, 1, kd, out.data, od, Nq, d, Nk, nbh, heads)
-
-        self.fwd.append(partial(fwd_fn, self.ctx))
+        S = self.S32[:nS].view(nbh, Nq, ldp)
+        dS = self.dS16[:nS].view(nbh, Nq, ldp)
+        self.f(ops.bmm, q, 0, qd, k, 0, kd, S, sd, Nq, Nk, d, nbh, heads, alpha=scale, out_f32=True)
+        self.f(ops.softmax_fwd, S, P, nbh * Nq, Nk)
+        self.f(ops.bmm, P, 0, pd, v, 1, kd, out.data, od, Nq, d, Nk, nbh, heads)
 
         def bwd():
             assert out.gw
@@ -390,15 +412,12 @@ class Engine:
             dkd = (ldk, d, Nk * ldk)
             dOd = (d, Nq, C, d, Nq * C)
 
-            def bwd_fn(ctx):
-                dP, dS = rec['S'][:nS].view(nbh, Nq, ldp), rec['dS'][:nS].view(nbh, Nq, ldp)
-                ops.bmm(ctx, dO, 0, dOd, v, 0, kd, dP, sd, Nq, Nk, d, nbh, heads, out_f32=True)
-                ops.softmax_bwd(ctx, P, dP, dS, nbh * Nq, Nk, scale)
-                ops.bmm(ctx, dS, 0, pd, k, 1, kd, dq, dqd, Nq, d, Nk, nbh, heads)
-                ops.bmm(ctx, dS, 1, pd, q, 1, qd, dk, dkd, Nk, d, Nq, nbh, heads)
-                ops.bmm(ctx, P, 1, pd, dO, 1, dOd, dv, dkd, Nk, d, Nq, nbh, heads)
-
-            self.bwd.append(partial(bwd_fn, self.ctx))
+            dP = S  # the score scratch is free again in backward
+            self.b(ops.bmm, dO, 0, dOd, v, 0, kd, dP, sd, Nq, Nk, d, nbh, heads, out_f32=True)
+            self.b(ops.softmax_bwd, P, dP, dS, nbh * Nq, Nk, scale)
+            self.b(ops.bmm, dS, 0, pd, k, 1, kd, dq, dqd, Nq, d, Nk, nbh, heads)
+            self.b(ops.bmm, dS, 1, pd, q, 1, qd, dk, dkd, Nk, d, Nq, nbh, heads)
+            self.b(ops.bmm, P, 1, pd, dO, 1, dOd, dv, dkd, Nk, d, Nq, nbh, heads)
             qn.gw = kvn.gw = True
 
         self._bwd_builders.append(bwd)
@@ -443,14 +462,15 @@ class Engine:
         # --- self attention
         l1 = self.layernorm(h0, tb + '.norm1')
         names = [tb + '.attn1.to_q.weight', tb + '.attn1.to_k.weight', tb + '.attn1.to_v.weight']
-        qkv = self.linear(l1, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names))
+        qkv = self.linear(l1, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names), gnames=names)
         o1 = self.attention(qkv.data[:, :C], qkv.data[:, C:2 * C], qkv.data[:, 2 * C:], qkv, qkv, 0, C, 2 * C, HW, HW, heads, C)
         h1 = self.linear(o1, tb + '.attn1.to_out.0.weight', tb + '.attn1.to_out.0.bias', residual=h0)
         # --- cross attention over the text context
         l2 = self.layernorm(h1, tb + '.norm2')
         q2 = self.linear(l2, tb + '.attn2.to_q.weight')
         names = [tb + '.attn2.to_k.weight', tb + '.attn2.to_v.weight']
-        kv = self.linear(self.ctx_node, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names))
+        kv = self.linear(self.ctx_node, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names),
+                         gnames=names)
         o2 = self.attention(q2.data, kv.data[:, :C], kv.data[:, C:], q2, kv, 0, 0, C, HW, L, heads, C)
         h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1)
         # --- GEGLU feed-forward
@@ -541,8 +561,56 @@ class Engine:
 
         self._bwd_builders.append(head_bwd)
         for builder in reversed(self._bwd_builders):
+            self._touched = set()
             builder()
+            for name in self._touched:  # gradient of `name` is final once bwd[:len(self.bwd)] has run
+                self.grad_ready[name] = len(self.bwd)
         self._bwd_builders = None
+        missing = [n for n in arena.entries if n not in self.grad_ready]
+        assert not missing, f'parameters without a gradient-producing op: {missing[:5]}'
+        self._make_buckets()
+
+    # ---------------------------------------------------------------------------------------------- data parallel (K5)
+    def _make_buckets(self, n_buckets=8):
+        """Contiguous arena ranges, in the order their gradients complete during backward (end of the arena first).
+        bucket = (elem_begin, elem_end, bwd_op_index_after_which_it_is_complete)."""
+        arena = self.arena
+        names = list(arena.entries)  # arena (= forward) order
+        target = arena.total / n_buckets
+        buckets, hi, ready = [], arena.total, 0
+        for name in reversed(names):
+            off = arena.entries[name][0]
+            ready = max(ready, self.grad_ready[name])
+            if hi - off >= target or off == 0:
+                buckets.append([off, hi, ready])
+                hi, ready = off, 0
+        # a bucket can only be sent once every earlier-sent bucket boundary is also respected: make `ready` monotone
+        for i in range(1, len(buckets)):
+            buckets[i][2] = max(buckets[i][2], buckets[i - 1][2])
+        buckets[-1][2] = len(self.bwd)
+        self.buckets = [tuple(b) for b in buckets]
+        self.segments = sorted(set(b[2] for b in self.buckets))
+
+    def enable_grad_sync(self, group=None):
+        """Average gradients over the data-parallel group, bucket by bucket, overlapped with the rest of backward."""
+        import torch.distributed as dist
+        self.dp_group = group
+        self.dp_world = dist.get_world_size(group)
+        self.comm_stream = torch.cuda.Stream(self.dev) if self.dev.type == 'cuda' else None
+        self.sync_grads = True
+
+    def _allreduce_bucket(self, lo, hi):
+        import torch.distributed as dist
+        flat = self.arena.g32[lo:hi]
+        if self.comm_stream is None:  # CPU (gloo) path used by the host-logic tests
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.dp_group)
+            flat.div_(self.dp_world)
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.dp_group)
 
     # ---------------------------------------------------------------------------------------------- execution
     def run_forward(self):
@@ -553,32 +621,70 @@ class Engine:
                 op()
 
     def run_backward(self):
-        if self.graph_bwd is not None:
-            self.graph_bwd.replay()
-        else:
-            for op in self.bwd:
-                op()
+        sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
+        if not sync:
+            if self.graph_bwd is not None:
+                for g in self.graph_bwd:
+                    g.replay()
+            else:
+                for op in self.bwd:
+                    op()
+            return
+        # segment k ends where bucket(s) with ready == segments[k] become final -> launch their all-reduce on the
+        # communication stream while the next segment computes
+        start = 0
+        for k, end in enumerate(self.segments):
+            if self.graph_bwd is not None:
+                self.graph_bwd[k].replay()
+            else:
+                for op in self.bwd[start:end]:
+                    op()
+            for lo, hi, ready in self.buckets:
+                if ready == end:
+                    self._allreduce_bucket(lo, hi)
+            start = end
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
 
     def capture_graphs(self):
         """Capture the two static schedules as CUDA graphs (call after at least one eager warm-up step)."""
         torch.cuda.synchronize(self.dev)
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
-        gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        gf, gbs = torch.cuda.CUDAGraph(), []
         with torch.cuda.stream(s):
             with torch.cuda.graph(gf, stream=s):
                 for op in self.fwd:
                     op()
-            with torch.cuda.graph(gb, stream=s):
-                for op in self.bwd:
-                    op()
+            start = 0
+            for end in self.segments:  # one graph per gradient-bucket segment (all-reduces are issued in between)
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb, stream=s):
+                    for op in self.bwd[start:end]:
+                        op()
+                gbs.append(gb)
+                start = end
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
-        self.graph_fwd, self.graph_bwd = gf, gb
+        self.graph_fwd, self.graph_bwd = gf, gbs
 
-    @property
-    def launches_per_step(self):
-        return getattr(self, '_launches_per_step', None)
+    def capture_gemm_only(self):
+        """A CUDA graph holding only the tensor-core GEMM launches of one step (forward + backward), replayed by
+        bench.py to time the dominant kernel family on its own stream with CUDA events (roofline.achieved)."""
+        torch.cuda.synchronize(self.dev)
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        g = torch.cuda.CUDAGraph()
+        n = 0
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                for op, is_gemm in list(zip(self.fwd, self.fwd_is_gemm)) + list(zip(self.bwd, self.bwd_is_gemm)):
+                    if is_gemm:
+                        op()
+                        n += 1
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        return g, n
 
 
 # ==================================================================================================== autograd glue
