@@ -20,8 +20,8 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                         const uint32_t box[4], std::string* err) {
+bool encode_tmap_4d(CUtensorMap* out, int dtype, int swizzle_bytes, const void* ptr, const uint64_t dims[4],
+                    const uint64_t strides_bytes[3], const uint32_t box[4], std::string* err) {
   EncodeTiledFn fn = get_encode_tiled();
   if (!fn) {
     if (err) *err = "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)";
@@ -34,9 +34,12 @@ bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[
     bx[i] = box[i];
   }
   for (int i = 0; i < 3; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = dtype == SD2_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, 4, const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) {
       char buf[256];
@@ -50,6 +53,27 @@ bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[
     return false;
   }
   return true;
+}
+
+bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4], std::string* err) {
+  return encode_tmap_4d(out, SD2_DT_BF16, 128, ptr, dims, strides_bytes, box, err);
+}
+
+// output tensor map of the GEMM epilogue: dims (N, M, nb0, nb1), box (chunk columns, 32 rows); the inner box row is
+// 128 B (SWIZZLE_128B: 64 bf16 / 32 fp32) or 64 B (SWIZZLE_64B: 32 bf16)
+static bool out_tmap(CUtensorMap* tm, void* ptr, bool f32, int chunk_cols, int N, int M, long long ldo, long long nb0,
+                     long long nb1, long long bs0, long long bs1, std::string* err) {
+  const uint64_t es = f32 ? 4 : 2;
+  if (nb0 < 1) nb0 = 1;
+  if (nb1 < 1) nb1 = 1;
+  const uint64_t s1 = (uint64_t)ldo * es;
+  const uint64_t s2 = nb0 > 1 ? (uint64_t)bs0 * es : s1 * (uint64_t)M;
+  const uint64_t s3 = nb1 > 1 ? (uint64_t)bs1 * es : (nb0 > 1 ? s2 * (uint64_t)nb0 : s2);
+  const uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, (uint64_t)nb0, (uint64_t)nb1};
+  const uint64_t strides[3] = {s1, s2, s3};
+  const uint32_t box[4] = {(uint32_t)chunk_cols, 32, 1, 1};
+  return encode_tmap_4d(tm, f32 ? SD2_DT_F32 : SD2_DT_BF16, (int)(chunk_cols * es), ptr, dims, strides, box, err);
 }
 
 // tensor map of a plain (possibly batched) operand; K-major box = (64, box_rows), MN-major box = (64, 64)
@@ -124,14 +148,13 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   if (!ctx || !d) return 1;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(ctx, "sd2_gemm: empty problem");
-  if (d->ldo % 8 != 0) return fail(ctx, "sd2_gemm: ldo must be a multiple of 8");
 
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   p.kind = d->kind;
   p.M = d->M;
   p.N = (d->N + 7) & ~7;  // stores are 8-wide; the caller's ldo covers the round-up (columns beyond N get zeros)
-  if (p.N > d->ldo && d->out_nb0 <= 1 && d->batch <= 1 && false) return fail(ctx, "sd2_gemm: ldo < round8(N)");
+  if (p.N > d->ldo) return fail(ctx, "sd2_gemm: ldo < round8(N)");
   p.alpha = d->alpha;
   p.bias = d->bias;
   p.rowbias = d->rowbias;
@@ -139,8 +162,6 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   p.ld_rowbias = d->ld_rowbias;
   p.residual = reinterpret_cast<const bf16*>(d->residual);
   p.ldr = d->ldr;
-  p.out = d->out;
-  p.ldo = d->ldo;
   p.out_nb0 = d->out_nb0 > 0 ? d->out_nb0 : 1;
   p.out_bs0 = d->out_bs0;
   p.out_bs1 = d->out_bs1;
@@ -218,38 +239,51 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     return fail(ctx, "sd2_gemm: unknown kind");
   }
 
-  // ---- split-K: fill the machine when there are few output tiles and a long contraction
-  const long long mt = (d->M + 127) / 128, nt = (p.N + BN - 1) / BN;
-  const long long tiles = mt * nt * batches;
-  int splits = 1;
-  const long long target = 2LL * ctx->num_sms;
-  if (tiles < target && p.total_kb >= 8) {
-    long long s = (target + tiles - 1) / tiles;
-    long long smax = p.total_kb / 4;
-    if (s > smax) s = smax;
-    if (s > 32) s = 32;
-    if (d->max_splits > 0 && s > d->max_splits) s = d->max_splits;
-    if (s < 1) s = 1;
-    splits = (int)s;
-  }
+  // ---- split-K: choose the K-split that minimises (waves over the SMs) x (k-blocks per item + epilogue), in units of
+  //      one 64-deep k-block; a direct-store output pays for the separate finalize pass, a reduce-add output does not
   const bool direct_store = d->out_mode == SD2_OUT_BF16 || d->out_mode == SD2_OUT_F32;
-  if (splits > 1 && direct_store) {
-    const long long need = (long long)splits * batches * d->M * p.N * 4;
-    if (batches != 1 || d->workspace == nullptr || d->workspace_bytes < need) splits = 1;
+  p.mt = (d->M + 127) / 128;
+  p.nt = (p.N + BN - 1) / BN;
+  p.batches = batches;
+  const long long tiles = (long long)p.mt * p.nt * batches;
+  int splits = 1;
+  {
+    long long smax = p.total_kb / 2;
+    if (smax > 32) smax = 32;
+    if (d->max_splits > 0 && smax > d->max_splits) smax = d->max_splits;
+    if (direct_store) {
+      if (batches != 1 || d->workspace == nullptr) smax = 1;
+      else {
+        const long long per_split = (long long)d->M * p.N * 4;
+        if (per_split > 0 && d->workspace_bytes / per_split < smax) smax = d->workspace_bytes / per_split;
+      }
+    }
+    const double epi = 4.0, fin = 12.0;
+    double best = 1e30;
+    for (long long s = 1; s <= smax; ++s) {
+      const long long waves = (tiles * s + ctx->num_sms - 1) / ctx->num_sms;
+      const long long kb = (p.total_kb + s - 1) / s;
+      const double cost = (double)waves * ((double)kb + epi) + ((s > 1 && direct_store) ? fin : 0.0);
+      if (cost < best * 0.97) {  // prefer fewer splits unless the gain is real
+        best = cost;
+        splits = (int)s;
+      }
+    }
   }
   p.splits = splits;
 
+  CUtensorMap tmO;
   cudaError_t e;
   if (splits > 1 && direct_store) {
     GemmKParams pp = p;
     pp.out_mode = OUT_F32_PARTIAL;
-    pp.out = d->workspace;
-    pp.ldo = p.N;
     pp.alpha = 1.f;
     pp.bias = nullptr;
     pp.rowbias = nullptr;
     pp.residual = nullptr;
-    e = launch_gemm_tc(tmA, tmB, pp, BN, a_mn, b_mn, batches, stream);
+    if (!out_tmap(&tmO, d->workspace, true, 32, p.N, d->M, p.N, splits, 1, (long long)d->M * p.N, 0, &err))
+      return fail(ctx, "sd2_gemm split-K workspace map: " + err);
+    e = launch_gemm_tc(tmA, tmB, tmO, pp, BN, a_mn, b_mn, ctx->num_sms, stream);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm launch: ") + cudaGetErrorString(e));
     e = launch_splitk_finalize(reinterpret_cast<const float*>(d->workspace), splits, d->M, p.N, d->alpha, d->bias,
                                d->rowbias, p.rows_per_group, d->ld_rowbias, p.residual, d->ldr, d->out, d->ldo,
@@ -263,8 +297,17 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   else if (d->out_mode == SD2_OUT_F32)
     p.out_mode = OUT_F32;
   else
-    p.out_mode = splits > 1 ? OUT_F32_ATOMIC : OUT_F32_ACCUM;
-  e = launch_gemm_tc(tmA, tmB, p, BN, a_mn, b_mn, batches, stream);
+    p.out_mode = OUT_F32_ACCUM;
+  {
+    const bool f32 = p.out_mode != OUT_BF16;
+    if (f32 && d->ldo % 4 != 0) return fail(ctx, "sd2_gemm: fp32 ldo must be a multiple of 4");
+    if (!f32 && d->ldo % 8 != 0) return fail(ctx, "sd2_gemm: bf16 ldo must be a multiple of 8");
+    const long long nb0 = batches > 1 ? (p.out_nb0 < batches ? p.out_nb0 : batches) : 1;
+    const long long nb1 = batches > 1 ? (batches + p.out_nb0 - 1) / p.out_nb0 : 1;
+    if (!out_tmap(&tmO, d->out, f32, f32 ? 32 : gemm_out_chunk(BN), p.N, d->M, d->ldo, nb0, nb1, d->out_bs0, d->out_bs1, &err))
+      return fail(ctx, "sd2_gemm output map: " + err);
+  }
+  e = launch_gemm_tc(tmA, tmB, tmO, p, BN, a_mn, b_mn, ctx->num_sms, stream);
   if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm launch: ") + cudaGetErrorString(e));
   ctx->launches += 1;
   return 0;

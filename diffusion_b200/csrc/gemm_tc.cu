@@ -1,12 +1,15 @@
 // tcgen05 / TMEM / TMA GEMM and implicit-GEMM 3x3 convolution for sm_100a.
 //
-// One CTA computes one 128 x BN fp32 accumulator tile in tensor memory:
-//   warp 0      : TMA producer  (cp.async.bulk.tensor 4-D boxes, SWIZZLE_128B, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> bias / per-image bias / residual -> global)
-// Two CTAs are co-resident per SM (<=113 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the
-// other's main loop.  Operands can be K-major (forward, activations x weights) or MN-major (dgrad reads the
-// weights transposed, wgrad contracts over pixels) - the same TMA boxes serve both, only the UMMA descriptors differ.
+// Persistent kernel, one CTA per SM, each CTA walks work items (128 x BN output tiles, optionally one K-split of a
+// tile) in a static round-robin order:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 4-D boxes, SWIZZLE_128B, mbarrier complete_tx) into a 4..8 stage ring
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32) into one of TWO
+//                 accumulator buffers in tensor memory, so the next tile's main loop overlaps this tile's epilogue
+//   warps 2..5  : epilogue: tcgen05.ld 32x32b -> registers -> alpha / bias / per-image bias / residual -> swizzled smem
+//                 staging -> TMA store (bf16 / fp32) or TMA reduce-add (fp32 weight gradients, split-K sums); every
+//                 global write is a full coalesced row segment issued by the copy engine, no per-thread stores or atomics
+// Operands can be K-major (forward, activations x weights) or MN-major (dgrad reads the weights transposed, wgrad
+// contracts over pixels) - the same TMA boxes serve both, only the UMMA descriptors differ.
 //
 // Replaces: cuDNN implicit-GEMM conv + cuBLASLt linear behind diffusers' nn.Conv2d / nn.Linear, called from
 // reference diffusion/models/stable_diffusion.py:183 (UNet forward) and the autograd backward of the same.
@@ -17,39 +20,67 @@ namespace sd2 {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+static constexpr int A_BYTES = BM * BK * 2;      // 16 KB
 static constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major box = 8 KB
+static constexpr int STG_BYTES = 4096;           // one epilogue staging buffer: 32 rows x 128 B
+static constexpr int STG_TOTAL = 4 * 2 * STG_BYTES;
+static constexpr int GEMM_THREADS = 192;
+static constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
 struct TileCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per buffer
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int OUT_CH = (BN % 64 == 0) ? 64 : 32;  // bf16 columns per TMA store box
 };
 
+int gemm_stages(int BN) {
+  const int stage_bytes = A_BYTES + BN * BK * 2;
+  int s = (SMEM_LIMIT - 1024 - 256 - STG_TOTAL) / stage_bytes;
+  return s < 2 ? 2 : (s > 8 ? 8 : s);
+}
+int gemm_out_chunk(int BN) { return (BN % 64 == 0) ? 64 : 32; }
+
+struct WorkItem {
+  int m_tile, n_tile, split, batch, kb0, nkb;
+};
+__device__ __forceinline__ WorkItem decode_item(const GemmKParams& p, int item) {
+  WorkItem w;
+  w.m_tile = item % p.mt;
+  int t = item / p.mt;
+  w.n_tile = t % p.nt;
+  t /= p.nt;
+  w.split = t % p.splits;
+  w.batch = t / p.splits;
+  w.kb0 = (int)(((long long)w.split * p.total_kb) / p.splits);
+  w.nkb = (int)(((long long)(w.split + 1) * p.total_kb) / p.splits) - w.kb0;
+  return w;
+}
+
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const GemmKParams p,
-                                                      const int stages) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmO, const GemmKParams p, const int stages) {
   using Cfg = TileCfg<BN>;
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide chunks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * Cfg::STAGE_BYTES);
+  uint8_t* stg_base = smem + (size_t)stages * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_TOTAL);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-  const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
-  const int kb0 = (int)(((long long)split * p.total_kb) / p.splits);
-  const int kb1 = (int)(((long long)(split + 1) * p.total_kb) / p.splits);
-  const int nkb = kb1 - kb0;
+  const int n_items = p.mt * p.nt * p.splits * p.batches;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -57,7 +88,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full_bar[a], 1);
+        mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -72,72 +106,81 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      // pixel-block origin of the shifted (conv) operand for this CTA / k-block
-      int cn0 = 0, ch0 = 0;
-      if (p.kind == KIND_CONV) {
-        if (p.cnb == 1) {
-          const int tiles_per_img = p.cH / p.cth;
-          cn0 = m_tile / tiles_per_img;
-          ch0 = (m_tile % tiles_per_img) * p.cth;
-        } else {
-          cn0 = m_tile * p.cnb;
-        }
-      }
-      const int ab0 = p.a_batched ? batch % p.a_nb0 : 0, ab1 = p.a_batched ? batch / p.a_nb0 : 0;
-      const int bb0 = p.b_batched ? batch % p.b_nb0 : 0, bb1 = p.b_batched ? batch / p.b_nb0 : 0;
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + i, s = i % stages;
-        const uint32_t ph = (uint32_t)(i / stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* a_dst = smem + (size_t)s * Cfg::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item);
+        // pixel-block origin of the shifted (conv) operand for this tile
+        int cn0 = 0, ch0 = 0;
         if (p.kind == KIND_CONV) {
-          const int tap = kb / p.cblks, cb = kb % p.cblks;
-          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-          tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, dw, ch0 + dh, cn0 + p.tap_dn[tap]);
-          const int tap_w = p.tap_w[tap];
-          if (!B_MN) {
-            tma_load_4d(b_dst, &tmB, &full_bar[s], cb * 64, n_tile * BN, tap_w, 0);
+          if (p.cnb == 1) {
+            const int tiles_per_img = p.cH / p.cth;
+            cn0 = w.m_tile / tiles_per_img;
+            ch0 = (w.m_tile % tiles_per_img) * p.cth;
           } else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_tile * BN + 64 * j, cb * 64, tap_w, 0);
+            cn0 = w.m_tile * p.cnb;
           }
-        } else {
-          if (!A_MN) {
-            tma_load_4d(a_dst, &tmA, &full_bar[s], kb * 64, m_tile * BM, ab0, ab1);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, &full_bar[s], m_tile * BM + 64 * j, kb * 64, ab0, ab1);
-          }
-          if (p.kind == KIND_PLAIN) {
-            if (!B_MN) {
-              tma_load_4d(b_dst, &tmB, &full_bar[s], kb * 64, n_tile * BN, bb0, bb1);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_tile * BN + 64 * j, kb * 64, bb0, bb1);
-            }
-          } else {  // KIND_CONV_WGRAD: B = activations shifted by the tap (= batch index), k-block = 64 pixels
-            const int tap = batch;
+        }
+        const int ab0 = p.a_batched ? w.batch % p.a_nb0 : 0, ab1 = p.a_batched ? w.batch / p.a_nb0 : 0;
+        const int bb0 = p.b_batched ? w.batch % p.b_nb0 : 0, bb1 = p.b_batched ? w.batch / p.b_nb0 : 0;
+        const int n_off = w.n_tile * BN, m_off = w.m_tile * BM;
+        for (int i = 0; i < w.nkb; ++i) {
+          const int kb = w.kb0 + i;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* a_dst = smem + (size_t)s * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (p.kind == KIND_CONV) {
+            const int tap = kb / p.cblks, cb = kb % p.cblks;
             const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-            int n0, h0;
-            if (p.cnb == 1) {
-              const int blocks_per_img = p.cH / p.cth;
-              n0 = kb / blocks_per_img;
-              h0 = (kb % blocks_per_img) * p.cth;
+            tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, dw, ch0 + dh, cn0 + p.tap_dn[tap]);
+            const int tap_w = p.tap_w[tap];
+            if (!B_MN) {
+              tma_load_4d(b_dst, &tmB, &full_bar[s], cb * 64, n_off, tap_w, 0);
             } else {
-              n0 = kb * p.cnb;
-              h0 = 0;
-            }
-            if (B_MN) {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_tile * BN + 64 * j, dw, h0 + dh,
-                            n0 + p.tap_dn[tap]);
+                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_off + 64 * j, cb * 64, tap_w, 0);
             }
+          } else {
+            if (!A_MN) {
+              tma_load_4d(a_dst, &tmA, &full_bar[s], kb * 64, m_off, ab0, ab1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, &full_bar[s], m_off + 64 * j, kb * 64, ab0, ab1);
+            }
+            if (p.kind == KIND_PLAIN) {
+              if (!B_MN) {
+                tma_load_4d(b_dst, &tmB, &full_bar[s], kb * 64, n_off, bb0, bb1);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_off + 64 * j, kb * 64, bb0, bb1);
+              }
+            } else {  // KIND_CONV_WGRAD: B = activations shifted by the tap (= batch index), k-block = 64 pixels
+              const int tap = w.batch;
+              const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+              int n0, h0;
+              if (p.cnb == 1) {
+                const int blocks_per_img = p.cH / p.cth;
+                n0 = kb / blocks_per_img;
+                h0 = (kb % blocks_per_img) * p.cth;
+              } else {
+                n0 = kb * p.cnb;
+                h0 = 0;
+              }
+              if (B_MN) {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_off + 64 * j, dw, h0 + dh,
+                              n0 + p.tap_dn[tap]);
+              }
+            }
+          }
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
       }
@@ -147,97 +190,149 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (uint32_t)(i / stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const WorkItem w = decode_item(p, item);
+        const int acc = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_STRIDE);
+        for (int i = 0; i < w.nkb; ++i) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * 2048, CHUNK_BYTES, 1024)
-                                      : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * 2048, CHUNK_BYTES, 1024)
-                                      : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * 2048, CHUNK_BYTES, 1024)
+                                        : umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * 2048, CHUNK_BYTES, 1024)
+                                        : umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
-        tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
+        tc_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      tc_commit(tmem_full_bar);  // accumulator complete
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
     const int q = warp & 3;
-    const long long row = (long long)m_tile * BM + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    long long out_off;
-    if (p.out_mode == OUT_F32_PARTIAL)
-      out_off = (long long)blockIdx.z * p.M * p.ldo;
-    else
-      out_off = (long long)(batch % p.out_nb0) * p.out_bs0 + (long long)(batch / p.out_nb0) * p.out_bs1;
-    const bool row_ok = row < p.M;
-    const float* rb = (p.rowbias != nullptr && row_ok) ? p.rowbias + (row / p.rows_per_group) * p.ld_rowbias : nullptr;
+    uint8_t* stg = stg_base + (size_t)(warp - 2) * 2 * STG_BYTES;
+    int sbuf = 0;
+    int it = 0;
+    const bool f32_out = p.out_mode != OUT_BF16;
+    const bool raw = p.out_mode == OUT_F32_PARTIAL;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const WorkItem w = decode_item(p, item);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const int row0 = w.m_tile * BM + q * 32;
+      const long long row = row0 + lane;
+      const bool row_ok = row < p.M;
+      int o2, o3;
+      long long res_off = 0;
+      if (raw) {
+        o2 = w.batch * p.splits + w.split;
+        o3 = 0;
+      } else {
+        o2 = w.batch % p.out_nb0;
+        o3 = w.batch / p.out_nb0;
+        res_off = (long long)o2 * p.out_bs0 + (long long)o3 * p.out_bs1;
+      }
+      const float* rb = (!raw && p.rowbias != nullptr && row_ok) ? p.rowbias + (row / p.rows_per_group) * p.ld_rowbias : nullptr;
+      const bf16* rs = (!raw && p.residual != nullptr && row_ok) ? p.residual + res_off + row * p.ldr : nullptr;
+      const float* bs = raw ? nullptr : p.bias;
+      const float alpha = raw ? 1.f : p.alpha;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_wait_ld();
-      const int n_base = n_tile * BN + c * 32;
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+        tmem_wait_ld();
+        if (c == BN / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int n_base = w.n_tile * BN + c * 32;
+        const bool new_buf = f32_out || Cfg::OUT_CH == 32 || (c & 1) == 0;
+        if (new_buf) {  // the buffer we are about to fill was handed to the copy engine two stores ago
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        uint8_t* buf = stg + sbuf * STG_BYTES;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = n_base + g * 8;
-        if (!row_ok || n >= p.N) continue;
-        float v[8];
+        for (int g = 0; g < 4; ++g) {
+          const int n = n_base + g * 8;
+          float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * p.alpha;
-        if (p.out_mode != OUT_F32_PARTIAL) {
-          if (p.bias != nullptr) {
-            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
-            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * alpha;
+          if (n < p.N) {
+            if (bs != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bs + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(bs + n + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (rb != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(rb + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(rb + n + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (rs != nullptr) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rs + n);
+              const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                           r3 = unpack_bf16x2(rr.w);
+              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+            }
           }
-          if (rb != nullptr) {
-            const float4 b0 = *reinterpret_cast<const float4*>(rb + n);
-            const float4 b1 = *reinterpret_cast<const float4*>(rb + n + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.residual != nullptr) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + out_off + row * p.ldr + n);
-            const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                         r3 = unpack_bf16x2(rr.w);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+          if (f32_out) {  // staging tile: 32 rows x 32 fp32 (128 B rows), SWIZZLE_128B
+            uint8_t* rowp = buf + lane * 128;
+            *reinterpret_cast<float4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            if (Cfg::OUT_CH == 64) {  // 32 rows x 64 bf16 (128 B rows), SWIZZLE_128B; this ld fills half a row
+              const int j = (c & 1) * 4 + g;
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+            } else {  // 32 rows x 32 bf16 (64 B rows), SWIZZLE_64B
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
           }
         }
-        if (p.out_mode == OUT_BF16) {
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + row * p.ldo + n) = o;
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + out_off + row * p.ldo + n;
-          if (p.out_mode == OUT_F32_ATOMIC) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(o + e, v[e]);
-          } else {
-            if (p.out_mode == OUT_F32_ACCUM) {
-              const float4 c0 = *reinterpret_cast<const float4*>(o);
-              const float4 c1 = *reinterpret_cast<const float4*>(o + 4);
-              v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
-              v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
-            }
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        const bool full = f32_out || Cfg::OUT_CH == 32 || (c & 1) == 1;
+        if (full) {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the async proxy (TMA)
+          __syncwarp();
+          const int col0 = (f32_out || Cfg::OUT_CH == 32) ? n_base : n_base - 32;
+          if (lane == 0 && row0 < p.M && col0 < p.N) {
+            if (p.out_mode == OUT_F32_ACCUM)
+              tma_reduce_add_4d(&tmO, buf, col0, row0, o2, o3);
+            else
+              tma_store_4d(&tmO, buf, col0, row0, o2, o3);
           }
+          if (lane == 0) bulk_commit();
+          sbuf ^= 1;
         }
       }
-      __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
     }
+    if (lane == 0) bulk_wait<0>();  // all stores / reductions of this warp have completed
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -289,25 +384,19 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
 
 // ---------------------------------------------------------------------------------------------- host side
 template <int BN, bool A_MN, bool B_MN>
-static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, dim3 grid, int stages,
-                              cudaStream_t stream) {
+static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
+                              int grid, int stages, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
-  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + STG_TOTAL + (2 * stages + 4) * 8 + 16 + 1024;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, 192, smem, stream>>>(tmA, tmB, p, stages);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmO, p, stages);
   return cudaGetLastError();
-}
-
-static int stages_for(int BN) {
-  const int stage_bytes = A_BYTES + BN * BK * 2;
-  int s = (112 * 1024 - 1024 - 256) / stage_bytes;
-  return s < 2 ? 2 : (s > 6 ? 6 : s);
 }
 
 int pick_bn(int N, bool b_mn) {
@@ -329,12 +418,13 @@ int pick_bn(int N, bool b_mn) {
   return best;
 }
 
-cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int BN, bool a_mn,
-                           bool b_mn, int batches, cudaStream_t stream) {
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, batches * p.splits);
-  const int st = stages_for(BN);
+cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
+                           int BN, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream) {
+  const long long items = (long long)p.mt * p.nt * p.splits * p.batches;
+  const int grid = (int)(items < num_sms ? items : num_sms);
+  const int st = gemm_stages(BN);
 #define SD2_GEMM_CASE(bn, amn, bmn) \
-  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn>(tmA, tmB, p, grid, st, stream);
+  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn>(tmA, tmB, tmO, p, grid, st, stream);
   SD2_GEMM_CASE(256, false, false) SD2_GEMM_CASE(160, false, false) SD2_GEMM_CASE(128, false, false)
   SD2_GEMM_CASE(64, false, false)
   SD2_GEMM_CASE(256, false, true) SD2_GEMM_CASE(128, false, true) SD2_GEMM_CASE(64, false, true)

@@ -10,17 +10,18 @@ enum GemmKind {
   KIND_CONV_WGRAD = 2,  // A = dy^T (MN-major, [pixels][Cout]), B = shifted NHWC activations (MN-major), batch index = tap
 };
 enum GemmOut {
-  OUT_BF16 = 0,         // bf16(alpha*acc + bias + rowbias + residual)
-  OUT_F32 = 1,          // fp32 store of alpha*acc (+bias)
-  OUT_F32_ACCUM = 2,    // fp32 out += alpha*acc (tile-owned read-modify-write)
-  OUT_F32_ATOMIC = 3,   // fp32 atomicAdd(out, alpha*acc)    (split-K weight gradients)
-  OUT_F32_PARTIAL = 4,  // fp32 raw accumulators into workspace[z][M][N] (split-K, finalized by splitk_finalize)
+  OUT_BF16 = 0,         // bf16(alpha*acc + bias + rowbias + residual), TMA store
+  OUT_F32 = 1,          // fp32 store of alpha*acc (+bias +rowbias), TMA store
+  OUT_F32_ACCUM = 2,    // fp32 out += alpha*acc, TMA reduce-add (weight gradients; also sums split-K partials)
+  OUT_F32_PARTIAL = 4,  // fp32 raw accumulators into workspace[batch*splits + split][M][N] (split-K, finalized by
+                        // splitk_finalize), TMA store
 };
 
 struct GemmKParams {
-  int M, N;            // output extent (per batch) used for store masking
+  int M, N;            // output extent (per batch) used for load masking (stores are clipped by the output tensor map)
   int total_kb;        // number of 64-deep K blocks
-  int splits;          // split-K factor; gridDim.z = batches * splits
+  int splits;          // split-K factor
+  int mt, nt, batches; // work decomposition: items = mt * nt * splits * batches (m fastest)
   int kind;
   int a_batched, b_batched;  // plain operands: does the batch index move this operand?
   int a_nb0, b_nb0;          // batch -> (batch % nb0, batch / nb0) = tensor-map coords 2,3
@@ -32,9 +33,8 @@ struct GemmKParams {
   signed char tap_w[9];
   // epilogue
   int out_mode;
-  void* out;
-  long long ldo, out_bs0, out_bs1;
-  int out_nb0;
+  int out_nb0;            // output batch -> tensor-map coords (batch % out_nb0, batch / out_nb0)
+  long long out_bs0, out_bs1;  // element strides of those coords (used for the residual address only)
   const bf16* residual;
   long long ldr;
   const float* bias;      // [N] or null

@@ -29,9 +29,14 @@ EncodeTiledFn get_encode_tiled();
 bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                          const uint32_t box[4], std::string* err);
 
+// generic form: dtype SD2_DT_F32 / SD2_DT_BF16, swizzle_bytes 128 / 64 / 32 / 0 (inner box row must not exceed it)
+bool encode_tmap_4d(CUtensorMap* out, int dtype, int swizzle_bytes, const void* ptr, const uint64_t dims[4],
+                    const uint64_t strides_bytes[3], const uint32_t box[4], std::string* err);
+
 int pick_bn(int N, bool b_mn);
-cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int BN, bool a_mn,
-                           bool b_mn, int batches, cudaStream_t stream);
+int gemm_out_chunk(int BN);
+cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
+                           int BN, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream);
 cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int N, float alpha, const float* bias,
                                    const float* rowbias, int rows_per_group, long long ld_rowbias, const bf16* residual,
                                    long long ldr, void* out, long long ldo, int out_f32, cudaStream_t stream);
