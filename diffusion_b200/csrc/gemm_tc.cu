@@ -105,124 +105,159 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const WorkItem w = decode_item(p, item);
-        // pixel-block origin of the shifted (conv) operand for this tile
-        int cn0 = 0, ch0 = 0;
-        if (p.kind == KIND_CONV) {
-          if (p.cnb == 1) {
-            const int tiles_per_img = p.cH / p.cth;
-            cn0 = w.m_tile / tiles_per_img;
-            ch0 = (w.m_tile % tiles_per_img) * p.cth;
-          } else {
-            cn0 = w.m_tile * p.cnb;
-          }
+    // The whole warp runs the (warp-uniform) control flow; one elected lane issues the copies.  Per k-block the
+    // loop is a barrier wait, one expect_tx and 2-5 TMA instructions: tap / channel-block / pixel-block counters are
+    // advanced incrementally (no division in the loop) so the producer stays far ahead of the tensor pipe.
+    int s = 0;
+    uint32_t ph = 0;
+    const int bpi = p.cnb == 1 ? p.cH / p.cth : 1;  // pixel blocks (M tiles or wgrad k-blocks) per image
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const WorkItem w = decode_item(p, item);
+      const int n_off = w.n_tile * BN, m_off = w.m_tile * BM;
+      const int ab0 = p.a_batched ? w.batch % p.a_nb0 : 0, ab1 = p.a_batched ? w.batch / p.a_nb0 : 0;
+      const int bb0 = p.b_batched ? w.batch % p.b_nb0 : 0, bb1 = p.b_batched ? w.batch / p.b_nb0 : 0;
+      // conv: pixel-block origin of this M tile; (tap, channel block) of the first k-block
+      int cn0 = 0, ch0 = 0, tap = 0, cb = 0;
+      // wgrad: (image, row) origin of the first 64-pixel k-block
+      int wn = 0, wh = 0;
+      int dh = 0, dw = 0, dn = 0, tw = 0;
+      if (p.kind == KIND_CONV) {
+        if (p.cnb == 1) {
+          cn0 = w.m_tile / bpi;
+          ch0 = (w.m_tile % bpi) * p.cth;
+        } else {
+          cn0 = w.m_tile * p.cnb;
         }
-        const int ab0 = p.a_batched ? w.batch % p.a_nb0 : 0, ab1 = p.a_batched ? w.batch / p.a_nb0 : 0;
-        const int bb0 = p.b_batched ? w.batch % p.b_nb0 : 0, bb1 = p.b_batched ? w.batch / p.b_nb0 : 0;
-        const int n_off = w.n_tile * BN, m_off = w.m_tile * BM;
-        for (int i = 0; i < w.nkb; ++i) {
-          const int kb = w.kb0 + i;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+        tap = w.kb0 / p.cblks;
+        cb = w.kb0 % p.cblks;
+      } else if (p.kind == KIND_CONV_WGRAD) {
+        tap = w.batch;
+        if (p.cnb == 1) {
+          wn = w.kb0 / bpi;
+          wh = (w.kb0 % bpi) * p.cth;
+        } else {
+          wn = w.kb0 * p.cnb;
+        }
+      }
+      if (p.kind != KIND_PLAIN) {
+        dh = p.tap_dh[tap];
+        dw = p.tap_dw[tap];
+        dn = p.tap_dn[tap];
+        tw = p.tap_w[tap];
+      }
+      int kcol = w.kb0 * 64;
+      for (int i = 0; i < w.nkb; ++i) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (elect_one()) {
           uint8_t* a_dst = smem + (size_t)s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint64_t* fb = &full_bar[s];
+          mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
           if (p.kind == KIND_CONV) {
-            const int tap = kb / p.cblks, cb = kb % p.cblks;
-            const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-            tma_load_4d(a_dst, &tmA, &full_bar[s], cb * 64, dw, ch0 + dh, cn0 + p.tap_dn[tap]);
-            const int tap_w = p.tap_w[tap];
+            tma_load_4d(a_dst, &tmA, fb, cb * 64, dw, ch0 + dh, cn0 + dn);
             if (!B_MN) {
-              tma_load_4d(b_dst, &tmB, &full_bar[s], cb * 64, n_off, tap_w, 0);
+              tma_load_4d(b_dst, &tmB, fb, cb * 64, n_off, tw, 0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_off + 64 * j, cb * 64, tap_w, 0);
+              for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, cb * 64, tw, 0);
             }
           } else {
             if (!A_MN) {
-              tma_load_4d(a_dst, &tmA, &full_bar[s], kb * 64, m_off, ab0, ab1);
+              tma_load_4d(a_dst, &tmA, fb, kcol, m_off, ab0, ab1);
             } else {
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
-                tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, &full_bar[s], m_off + 64 * j, kb * 64, ab0, ab1);
+              for (int j = 0; j < 2; ++j) tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, fb, m_off + 64 * j, kcol, ab0, ab1);
             }
             if (p.kind == KIND_PLAIN) {
               if (!B_MN) {
-                tma_load_4d(b_dst, &tmB, &full_bar[s], kb * 64, n_off, bb0, bb1);
+                tma_load_4d(b_dst, &tmB, fb, kcol, n_off, bb0, bb1);
               } else {
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                  tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_off + 64 * j, kb * 64, bb0, bb1);
+                for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, kcol, bb0, bb1);
               }
-            } else {  // KIND_CONV_WGRAD: B = activations shifted by the tap (= batch index), k-block = 64 pixels
-              const int tap = w.batch;
-              const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-              int n0, h0;
-              if (p.cnb == 1) {
-                const int blocks_per_img = p.cH / p.cth;
-                n0 = kb / blocks_per_img;
-                h0 = (kb % blocks_per_img) * p.cth;
-              } else {
-                n0 = kb * p.cnb;
-                h0 = 0;
-              }
-              if (B_MN) {
+            } else if (B_MN) {  // KIND_CONV_WGRAD: B = activations shifted by the tap, k-block = 64 pixels
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                  tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, &full_bar[s], n_off + 64 * j, dw, h0 + dh,
-                              n0 + p.tap_dn[tap]);
-              }
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, dw, wh + dh, wn + dn);
             }
           }
-          if (++s == stages) {
-            s = 0;
-            ph ^= 1u;
+        }
+        __syncwarp();
+        // advance the k-block coordinates (warp-uniform)
+        kcol += 64;
+        if (p.kind == KIND_CONV) {
+          if (++cb == p.cblks) {
+            cb = 0;
+            ++tap;
+            if (i + 1 < w.nkb) {
+              dh = p.tap_dh[tap];
+              dw = p.tap_dw[tap];
+              dn = p.tap_dn[tap];
+              tw = p.tap_w[tap];
+            }
           }
+        } else if (p.kind == KIND_CONV_WGRAD) {
+          if (p.cnb == 1) {
+            wh += p.cth;
+            if (wh == p.cH) {
+              wh = 0;
+              ++wn;
+            }
+          } else {
+            wn += p.cnb;
+          }
+        }
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const WorkItem w = decode_item(p, item);
-        const int acc = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator buffer
+    // ------------------------------------------------------------------ MMA issuer
+    // Warp-uniform loop; one elected lane (always the same one) issues the four K=16 MMAs of a stage and the commit.
+    // The 64-bit smem descriptors are built once; per stage / per K step only their 14-bit address field moves
+    // ((byte offset) >> 4 added to the low word), so a k-block costs a handful of instructions.
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t smem_a0 = smem_u32(smem);
+    const uint64_t adesc0 = A_MN ? umma_desc_sw128(smem_a0, CHUNK_BYTES, 1024) : umma_desc_sw128(smem_a0, 16, 1024);
+    const uint64_t bdesc0 = B_MN ? umma_desc_sw128(smem_a0 + A_BYTES, CHUNK_BYTES, 1024)
+                                 : umma_desc_sw128(smem_a0 + A_BYTES, 16, 1024);
+    constexpr uint64_t A_KSTEP = (A_MN ? 2048 : 32) >> 4, B_KSTEP = (B_MN ? 2048 : 32) >> 4;
+    constexpr uint64_t STAGE_STEP = Cfg::STAGE_BYTES >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    uint64_t ad = adesc0, bd = bdesc0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const WorkItem w = decode_item(p, item);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_STRIDE);
+      for (int i = 0; i < w.nkb; ++i) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_STRIDE);
-        for (int i = 0; i < w.nkb; ++i) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * 2048, CHUNK_BYTES, 1024)
-                                        : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * 2048, CHUNK_BYTES, 1024)
-                                        : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
-          }
+        if (elect_one()) {
+          tc_mma_bf16(d_tmem, ad, bd, idesc, i != 0 ? 1u : 0u);
+          tc_mma_bf16(d_tmem, ad + A_KSTEP, bd + B_KSTEP, idesc, 1u);
+          tc_mma_bf16(d_tmem, ad + 2 * A_KSTEP, bd + 2 * B_KSTEP, idesc, 1u);
+          tc_mma_bf16(d_tmem, ad + 3 * A_KSTEP, bd + 3 * B_KSTEP, idesc, 1u);
           tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
-          if (++s == stages) {
-            s = 0;
-            ph ^= 1u;
-          }
+          if (i == w.nkb - 1) tc_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        tc_commit(&tmem_full_bar[acc]);  // accumulator complete
+        __syncwarp();
+        ad += STAGE_STEP;
+        bd += STAGE_STEP;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+          ad = adesc0;
+          bd = bdesc0;
+        }
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
     const int q = warp & 3;
