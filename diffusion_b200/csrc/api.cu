@@ -1,5 +1,6 @@
 // C-ABI entry points: context lifecycle, TMA tensor-map construction and the sd2_gemm host-side planner
 // (tile shape, split-K, tensor maps) in front of gemm_tc.cu.  See include/sd2b200.h for the contract.
+#include <algorithm>
 #include <mutex>
 
 #include "gemm_tc.cuh"
@@ -112,6 +113,49 @@ static bool conv_tmap(CUtensorMap* tm, const sd2_conv_geom& g, int th, int nb, s
   return encode_tmap_bf16_4d(tm, g.ptr, dims, strides, box, err);
 }
 
+// Tile width and K-split of one GEMM launch, from a small cycle model of the persistent kernel:
+//   cycles = waves(items over the SMs) x (k-blocks per item x c_kb(BN) + epilogue(BN)) [+ finalize pass]
+// c_kb = the slower of the tensor pipe (2*BN cycles per 64-deep k-block of a 128 x BN tile) and the operand fetch of
+// one stage.  Narrow tiles are chosen only when the problem cannot fill the 148 SMs with wide ones.
+static void plan_gemm(const sd2_ctx* ctx, const sd2_gemm_desc* d, int N8, int total_kb, int batches, bool b_mn,
+                      bool direct_store, int* BN_out, int* splits_out) {
+  const int cands[4] = {256, 160, 128, 64};
+  const long long mt = (d->M + 127) / 128;
+  double best = 1e30;
+  int best_bn = 64, best_s = 1;
+  for (int ci = 0; ci < 4; ++ci) {
+    const int bn = cands[ci];
+    if (b_mn && bn % 64 != 0) continue;
+    const long long nt = (N8 + bn - 1) / bn;
+    const long long tiles = mt * nt * batches;
+    const double c_kb = std::max(2.0 * bn, 180.0 + 1.3 * bn);
+    const double epi = 600.0 + (bn / 32) * 200.0;
+    long long smax = total_kb / 2;
+    if (smax > 32) smax = 32;
+    if (d->max_splits > 0 && smax > d->max_splits) smax = d->max_splits;
+    if (direct_store) {
+      if (batches != 1 || d->workspace == nullptr) smax = 1;
+      else {
+        const long long per_split = (long long)d->M * N8 * 4;
+        if (per_split > 0 && d->workspace_bytes / per_split < smax) smax = d->workspace_bytes / per_split;
+      }
+    }
+    if (smax < 1) smax = 1;
+    for (long long s = 1; s <= smax; ++s) {
+      const long long waves = (tiles * s + ctx->num_sms - 1) / ctx->num_sms;
+      const long long kb = (total_kb + s - 1) / s;
+      const double cost = (double)waves * ((double)kb * c_kb + epi) + ((s > 1 && direct_store) ? 7000.0 : 0.0);
+      if (cost < best * 0.98) {  // candidates are visited wide-to-narrow, few-to-many splits: keep those on ties
+        best = cost;
+        best_bn = bn;
+        best_s = (int)s;
+      }
+    }
+  }
+  *BN_out = best_bn;
+  *splits_out = best_s;
+}
+
 }  // namespace sd2
 
 using namespace sd2;
@@ -170,12 +214,30 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   int batches = 1;
   CUtensorMap tmA, tmB;
   std::string err;
-  int BN;
+  int BN, splits = 1;
+  const bool direct_store = d->out_mode == SD2_OUT_BF16 || d->out_mode == SD2_OUT_F32;
+  {
+    int kb, nbatch = 1;
+    bool bmn;
+    if (d->kind == SD2_GEMM_PLAIN) {
+      kb = (d->K + 63) / 64;
+      nbatch = d->batch > 0 ? d->batch : 1;
+      bmn = d->B.mn_major != 0;
+    } else if (d->kind == SD2_GEMM_CONV) {
+      kb = d->conv.ntaps * ((d->conv.C + 63) / 64);
+      bmn = d->B.mn_major != 0;
+    } else {
+      kb = (d->K + 63) / 64;
+      nbatch = d->conv.ntaps;
+      bmn = true;
+    }
+    if (kb < 1 || nbatch < 1) return fail(ctx, "sd2_gemm: empty contraction / batch");
+    plan_gemm(ctx, d, p.N, kb, nbatch, bmn, direct_store, &BN, &splits);
+  }
 
   if (d->kind == SD2_GEMM_PLAIN) {
     a_mn = d->A.mn_major != 0;
     b_mn = d->B.mn_major != 0;
-    BN = pick_bn(d->N, b_mn);
     batches = d->batch > 0 ? d->batch : 1;
     p.total_kb = (d->K + 63) / 64;
     p.a_batched = d->A.nb0 > 0;
@@ -187,7 +249,6 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     const sd2_conv_geom& g = d->conv;
     a_mn = false;
     b_mn = d->B.mn_major != 0;
-    BN = pick_bn(d->N, b_mn);
     int th, nb;
     if (!conv_box(g, 128, &th, &nb)) return fail(ctx, "sd2_gemm conv: unsupported spatial geometry for a 128-pixel tile");
     p.cH = g.H;
@@ -214,7 +275,6 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     a_mn = true;
     b_mn = true;
     if (!d->A.mn_major) return fail(ctx, "sd2_gemm wgrad: A (dy) must be MN-major");
-    BN = pick_bn(d->N, true);
     int th, nb;
     if (!conv_box(g, 64, &th, &nb)) return fail(ctx, "sd2_gemm wgrad: unsupported spatial geometry for a 64-pixel k-block");
     p.cH = g.H;
@@ -239,37 +299,9 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     return fail(ctx, "sd2_gemm: unknown kind");
   }
 
-  // ---- split-K: choose the K-split that minimises (waves over the SMs) x (k-blocks per item + epilogue), in units of
-  //      one 64-deep k-block; a direct-store output pays for the separate finalize pass, a reduce-add output does not
-  const bool direct_store = d->out_mode == SD2_OUT_BF16 || d->out_mode == SD2_OUT_F32;
   p.mt = (d->M + 127) / 128;
   p.nt = (p.N + BN - 1) / BN;
   p.batches = batches;
-  const long long tiles = (long long)p.mt * p.nt * batches;
-  int splits = 1;
-  {
-    long long smax = p.total_kb / 2;
-    if (smax > 32) smax = 32;
-    if (d->max_splits > 0 && smax > d->max_splits) smax = d->max_splits;
-    if (direct_store) {
-      if (batches != 1 || d->workspace == nullptr) smax = 1;
-      else {
-        const long long per_split = (long long)d->M * p.N * 4;
-        if (per_split > 0 && d->workspace_bytes / per_split < smax) smax = d->workspace_bytes / per_split;
-      }
-    }
-    const double epi = 4.0, fin = 12.0;
-    double best = 1e30;
-    for (long long s = 1; s <= smax; ++s) {
-      const long long waves = (tiles * s + ctx->num_sms - 1) / ctx->num_sms;
-      const long long kb = (p.total_kb + s - 1) / s;
-      const double cost = (double)waves * ((double)kb + epi) + ((s > 1 && direct_store) ? fin : 0.0);
-      if (cost < best * 0.97) {  // prefer fewer splits unless the gain is real
-        best = cost;
-        splits = (int)s;
-      }
-    }
-  }
   p.splits = splits;
 
   CUtensorMap tmO;

@@ -59,6 +59,117 @@ __device__ __forceinline__ WorkItem decode_item(const GemmKParams& p, int item) 
   return w;
 }
 
+// ---------------------------------------------------------------------------------------------- epilogue pieces
+struct EpiTile {  // per work item, per thread (thread = one output row of the 32-row slab of its warp)
+  int row0, o2, o3, n_tile0, N, M, out_mode;
+  const float* rb;  // per-image bias row of this thread (or null)
+  const bf16* rs;   // residual row of this thread (or null)
+  bool has_bias;
+  float alpha;
+  float bv[8];      // bias of tile columns lane*8 .. lane*8+7
+};
+struct EpiPre {  // global operands of one 32-column chunk, fetched one chunk ahead
+  float4 rb[8];
+  uint4 rs[4];
+};
+struct EpiState {
+  int sbuf;
+};
+
+__device__ __forceinline__ void epi_prefetch(const EpiTile& t, int c, EpiPre& pre) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = t.n_tile0 + c * 32 + g * 8;
+    if (n < t.N) {
+      if (t.rb != nullptr) {
+        pre.rb[2 * g] = *reinterpret_cast<const float4*>(t.rb + n);
+        pre.rb[2 * g + 1] = *reinterpret_cast<const float4*>(t.rb + n + 4);
+      }
+      if (t.rs != nullptr) pre.rs[g] = *reinterpret_cast<const uint4*>(t.rs + n);
+    }
+  }
+}
+
+// One 32-column chunk of the accumulator: TMEM -> registers -> (+bias +rowbias +residual) -> swizzled staging -> TMA.
+template <int BN>
+__device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c, const EpiPre& cur, EpiPre& nxt,
+                                          uint32_t t_addr, uint8_t* stg, int lane, const CUtensorMap* tmO,
+                                          uint64_t* tmem_empty) {
+  constexpr int NCH = BN / 32;
+  constexpr int OUT_CH = (BN % 64 == 0) ? 64 : 32;
+  const bool f32_out = t.out_mode != OUT_BF16;
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+  tmem_wait_ld();
+  if (c == NCH - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty);
+  } else {
+    epi_prefetch(t, c + 1, nxt);
+  }
+  const int n_base = t.n_tile0 + c * 32;
+  const bool new_buf = f32_out || OUT_CH == 32 || (c & 1) == 0;
+  if (new_buf) {  // the buffer we are about to fill was handed to the copy engine two stores ago
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+  }
+  uint8_t* buf = stg + st.sbuf * STG_BYTES;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n_base + g * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * t.alpha;
+    if (t.has_bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __shfl_sync(0xffffffffu, t.bv[e], c * 4 + g);
+    }
+    if (n < t.N) {
+      if (t.rb != nullptr) {
+        const float4 b0 = cur.rb[2 * g], b1 = cur.rb[2 * g + 1];
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (t.rs != nullptr) {
+        const uint4 rr = cur.rs[g];
+        const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+        v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+      }
+    }
+    if (f32_out) {  // staging tile: 32 rows x 32 fp32 (128 B rows), SWIZZLE_128B
+      uint8_t* rowp = buf + lane * 128;
+      *reinterpret_cast<float4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      if (OUT_CH == 64) {  // 32 rows x 64 bf16 (128 B rows), SWIZZLE_128B; this ld fills half a row
+        const int j = (c & 1) * 4 + g;
+        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+      } else {  // 32 rows x 32 bf16 (64 B rows), SWIZZLE_64B
+        *reinterpret_cast<uint4*>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+      }
+    }
+  }
+  const bool full = f32_out || OUT_CH == 32 || (c & 1) == 1;
+  if (full) {
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the async proxy (TMA)
+    __syncwarp();
+    const int col0 = (f32_out || OUT_CH == 32) ? n_base : n_base - 32;
+    if (lane == 0 && t.row0 < t.M && col0 < t.N) {
+      if (t.out_mode == OUT_F32_ACCUM)
+        tma_reduce_add_4d(tmO, buf, col0, t.row0, t.o2, t.o3);
+      else
+        tma_store_4d(tmO, buf, col0, t.row0, t.o2, t.o3);
+    }
+    if (lane == 0) bulk_commit();
+    st.sbuf ^= 1;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -260,110 +371,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 4 TMEM lane quadrants)
+    // Global operands of the epilogue never sit on the critical path: the tile's bias lives in registers (8 columns
+    // per lane, broadcast by shuffles), per-image bias and residual of 32-column chunk c+1 are fetched while chunk c
+    // is processed, and chunk 0's are issued before the wait on the accumulator.
     const int q = warp & 3;
     uint8_t* stg = stg_base + (size_t)(warp - 2) * 2 * STG_BYTES;
-    int sbuf = 0;
+    EpiState st;
+    st.sbuf = 0;
     int it = 0;
-    const bool f32_out = p.out_mode != OUT_BF16;
     const bool raw = p.out_mode == OUT_F32_PARTIAL;
+    constexpr int NCH = BN / 32;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const WorkItem w = decode_item(p, item);
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      const int row0 = w.m_tile * BM + q * 32;
-      const long long row = row0 + lane;
+      EpiTile t;
+      t.row0 = w.m_tile * BM + q * 32;
+      const long long row = t.row0 + lane;
       const bool row_ok = row < p.M;
-      int o2, o3;
       long long res_off = 0;
       if (raw) {
-        o2 = w.batch * p.splits + w.split;
-        o3 = 0;
+        t.o2 = w.batch * p.splits + w.split;
+        t.o3 = 0;
       } else {
-        o2 = w.batch % p.out_nb0;
-        o3 = w.batch / p.out_nb0;
-        res_off = (long long)o2 * p.out_bs0 + (long long)o3 * p.out_bs1;
+        t.o2 = w.batch % p.out_nb0;
+        t.o3 = w.batch / p.out_nb0;
+        res_off = (long long)t.o2 * p.out_bs0 + (long long)t.o3 * p.out_bs1;
       }
-      const float* rb = (!raw && p.rowbias != nullptr && row_ok) ? p.rowbias + (row / p.rows_per_group) * p.ld_rowbias : nullptr;
-      const bf16* rs = (!raw && p.residual != nullptr && row_ok) ? p.residual + res_off + row * p.ldr : nullptr;
-      const float* bs = raw ? nullptr : p.bias;
-      const float alpha = raw ? 1.f : p.alpha;
+      t.n_tile0 = w.n_tile * BN;
+      t.rb = (!raw && p.rowbias != nullptr && row_ok) ? p.rowbias + (row / p.rows_per_group) * p.ld_rowbias : nullptr;
+      t.rs = (!raw && p.residual != nullptr && row_ok) ? p.residual + res_off + row * p.ldr : nullptr;
+      t.has_bias = !raw && p.bias != nullptr;
+      t.alpha = raw ? 1.f : p.alpha;
+      t.N = p.N;
+      t.M = p.M;
+      t.out_mode = p.out_mode;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t.bv[e] = 0.f;
+      if (t.has_bias && lane * 8 < BN && t.n_tile0 + lane * 8 < p.N) {
+        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + t.n_tile0 + lane * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(p.bias + t.n_tile0 + lane * 8 + 4);
+        t.bv[0] = b0.x; t.bv[1] = b0.y; t.bv[2] = b0.z; t.bv[3] = b0.w;
+        t.bv[4] = b1.x; t.bv[5] = b1.y; t.bv[6] = b1.z; t.bv[7] = b1.w;
+      }
+      EpiPre pa, pb;
+      epi_prefetch(t, 0, pa);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
-        tmem_wait_ld();
-        if (c == BN / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        const int n_base = w.n_tile * BN + c * 32;
-        const bool new_buf = f32_out || Cfg::OUT_CH == 32 || (c & 1) == 0;
-        if (new_buf) {  // the buffer we are about to fill was handed to the copy engine two stores ago
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-        }
-        uint8_t* buf = stg + sbuf * STG_BYTES;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n_base + g * 8;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]) * alpha;
-          if (n < p.N) {
-            if (bs != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bs + n);
-              const float4 b1 = *reinterpret_cast<const float4*>(bs + n + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (rb != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(rb + n);
-              const float4 b1 = *reinterpret_cast<const float4*>(rb + n + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (rs != nullptr) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(rs + n);
-              const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                           r3 = unpack_bf16x2(rr.w);
-              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-            }
-          }
-          if (f32_out) {  // staging tile: 32 rows x 32 fp32 (128 B rows), SWIZZLE_128B
-            uint8_t* rowp = buf + lane * 128;
-            *reinterpret_cast<float4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            if (Cfg::OUT_CH == 64) {  // 32 rows x 64 bf16 (128 B rows), SWIZZLE_128B; this ld fills half a row
-              const int j = (c & 1) * 4 + g;
-              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-            } else {  // 32 rows x 32 bf16 (64 B rows), SWIZZLE_64B
-              *reinterpret_cast<uint4*>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
-            }
-          }
-        }
-        const bool full = f32_out || Cfg::OUT_CH == 32 || (c & 1) == 1;
-        if (full) {
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the async proxy (TMA)
-          __syncwarp();
-          const int col0 = (f32_out || Cfg::OUT_CH == 32) ? n_base : n_base - 32;
-          if (lane == 0 && row0 < p.M && col0 < p.N) {
-            if (p.out_mode == OUT_F32_ACCUM)
-              tma_reduce_add_4d(&tmO, buf, col0, row0, o2, o3);
-            else
-              tma_store_4d(&tmO, buf, col0, row0, o2, o3);
-          }
-          if (lane == 0) bulk_commit();
-          sbuf ^= 1;
-        }
+      for (int c = 0; c < NCH; c += 2) {
+        epi_chunk<BN>(t, st, c, pa, pb, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
+        if (c + 1 < NCH) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
       }
     }
     if (lane == 0) bulk_wait<0>();  // all stores / reductions of this warp have completed
@@ -432,25 +491,6 @@ static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   }
   kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmO, p, stages);
   return cudaGetLastError();
-}
-
-int pick_bn(int N, bool b_mn) {
-  const int cands[4] = {256, 160, 128, 64};
-  int best = 64;
-  double best_cost = 1e30;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    if (b_mn && bn % 64 != 0) continue;
-    const int tiles = (N + bn - 1) / bn;
-    // narrow tiles re-read the 128-row A tile more often per flop (smem-bandwidth bound)
-    const double eff = bn >= 256 ? 1.0 : bn >= 160 ? 1.04 : bn >= 128 ? 1.08 : 1.5;
-    const double cost = (double)tiles * bn * eff;
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
-    }
-  }
-  return best;
 }
 
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,

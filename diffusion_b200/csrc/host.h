@@ -33,7 +33,6 @@ bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[
 bool encode_tmap_4d(CUtensorMap* out, int dtype, int swizzle_bytes, const void* ptr, const uint64_t dims[4],
                     const uint64_t strides_bytes[3], const uint32_t box[4], std::string* err);
 
-int pick_bn(int N, bool b_mn);
 int gemm_out_chunk(int BN);
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
                            int BN, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream);
