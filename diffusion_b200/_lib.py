@@ -130,6 +130,7 @@ SIGNATURES = {
     'sd2_pad_cast_rows': (_i, [_vp, _vp, _i, _vp, _i, _ll, _vp]),
     'sd2_unpad_accum_rows': (_i, [_vp, _vp, _i, _vp, _i, _ll, _i, _vp]),
     'sd2_mse_head': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
+    'sd2_adamw_step': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _i, _vp]),
 }
 
 _lib = None
@@ -177,7 +178,7 @@ class DryLib:
                     raise TypeError(f'{name}: argument {i} ({v!r}) is not a {t}') from e
             self.calls[name] = self.calls.get(name, 0) + 1
             if name == 'sd2_groupnorm_ws_floats':
-                return a[0] * 32 * a[1] * 2
+                return a[0] * 32 * a[1] * 2 + a[0] * 128
             if name == 'sd2_layernorm_ws_floats':
                 return 148 * 4 * a[1] * 2
             if name == 'sd2_last_error':

@@ -29,20 +29,37 @@ __host__ __device__ inline int gn_chunks(int HW) {
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm fwd
+// Cross-row-lane reduction used by the two statistics kernels: every thread holds 2 x 8 partial sums for channels
+// v*8..v*8+7; lanes r = 0..R-1 of the same channel vector are summed through shared memory without atomics:
+// sm[r][c][2] staging, then thread i < 2C adds its R entries into red[i] (red = sm + R*2C).
+__device__ __forceinline__ void gn_block_reduce(float* sm, const float* a, const float* b, int C, int R, int v, int r) {
+  if (r < R) {
+    float* o = sm + ((size_t)r * C + v * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) *reinterpret_cast<float4*>(o + 2 * e) = make_float4(a[e], b[e], a[e + 1], b[e + 1]);
+  }
+  __syncthreads();
+  float* red = sm + (size_t)R * C * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) {
+    float t = 0.f;
+    for (int rr = 0; rr < R; ++rr) t += sm[(size_t)rr * 2 * C + i];
+    red[i] = t;
+  }
+  __syncthreads();
+}
+
 // grid (P, B). Partial (sum, sumsq) per group over this block's pixel chunk -> ws[b][p][G][2]
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ ws,
                                                               int HW, int C, int G) {
-  extern __shared__ float sm[];  // [C][2]
+  extern __shared__ float sm[];  // [R][C][2] + [C][2]
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int V = C / 8, R = GN_THREADS / V;
   const int v = threadIdx.x % V, r = threadIdx.x / V;
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
-  __syncthreads();
   const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
-  if (r < R) {
-    float s[8], q[8];
+  float s[8], q[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  if (r < R) {
     const bf16* base = x + ((long long)b * HW) * ldx + v * 8;
     for (int row = row0 + r; row < row1; row += R) {
       float f[8];
@@ -53,23 +70,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
         q[e] += f[e] * f[e];
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sm[(v * 8 + e) * 2], s[e]);
-      atomicAdd(&sm[(v * 8 + e) * 2 + 1], q[e]);
-    }
   }
-  __syncthreads();
+  gn_block_reduce(sm, s, q, C, R, v, r);
+  const float* red = sm + (size_t)R * C * 2;
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += GN_THREADS) {
-    float s = 0.f, q = 0.f;
+    float a = 0.f, c2 = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      s += sm[c * 2];
-      q += sm[c * 2 + 1];
+      a += red[c * 2];
+      c2 += red[c * 2 + 1];
     }
     float* o = ws + (((long long)b * P + p) * G + g) * 2;
-    o[0] = s;
-    o[1] = q;
+    o[0] = a;
+    o[1] = c2;
   }
 }
 
@@ -139,19 +152,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ stats, float* __restrict__ ws, int HW,
                                                                   int C, int G, int silu) {
-  extern __shared__ float sm[];  // [C][2]
+  extern __shared__ float sm[];  // [R][C][2] + [C][2]
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int V = C / 8, R = GN_THREADS / V, cpg = C / G;
   const int v = threadIdx.x % V, r = threadIdx.x / V;
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
-  __syncthreads();
   const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
   if (r < R) {
-    float s1[8], s2[8], mean[8], rstd[8], ga[8], be[8];
+    float mean[8], rstd[8], ga[8], be[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = v * 8 + e, g = c / cpg;
-      s1[e] = s2[e] = 0.f;
       mean[e] = stats[((long long)b * G + g) * 2];
       rstd[e] = stats[((long long)b * G + g) * 2 + 1];
       ga[e] = gamma[c];
@@ -172,22 +185,60 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
         s2[e] += dyh * xh;
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sm[(v * 8 + e) * 2], s1[e]);
-      atomicAdd(&sm[(v * 8 + e) * 2 + 1], s2[e]);
+  }
+  gn_block_reduce(sm, s1, s2, C, R, v, r);
+  const float* red = sm + (size_t)R * C * 2;
+  float* o = ws + (((long long)b * P + p) * C) * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) o[i] = red[i];
+}
+
+// grid (G), block 256: one block per group.  Sums the per-chunk partials of its cpg channels for every image
+// (T[b][cl] in shared memory), then (a) per image: db_g = sum gamma_c * T1, ds_g = sum gamma_c * T2 -> gstat[b][g]
+// (consumed by the apply kernel), (b) per channel: dbeta_c += sum_b T1, dgamma_c += sum_b T2.
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
+                                                            float* __restrict__ gstat, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int B, int P, int C, int G) {
+  extern __shared__ float T[];  // [B][cpg][2]
+  const int g = blockIdx.x, cpg = C / G;
+  for (int idx = threadIdx.x; idx < B * cpg; idx += blockDim.x) {
+    const int b = idx / cpg, cl = idx % cpg;
+    const float* o = ws + (((long long)b * P) * C + g * cpg + cl) * 2;
+    float a1 = 0.f, a2 = 0.f;
+    for (int pp = 0; pp < P; ++pp) {
+      const float2 t = *reinterpret_cast<const float2*>(o + (long long)pp * C * 2);
+      a1 += t.x;
+      a2 += t.y;
     }
+    T[idx * 2] = a1;
+    T[idx * 2 + 1] = a2;
   }
   __syncthreads();
-  float* o = ws + (((long long)b * P + p) * C) * 2;
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) o[i] = sm[i];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float dbv = 0.f, ds = 0.f;
+    for (int cl = 0; cl < cpg; ++cl) {
+      const float ga = gamma[g * cpg + cl];
+      dbv += ga * T[(b * cpg + cl) * 2];
+      ds += ga * T[(b * cpg + cl) * 2 + 1];
+    }
+    gstat[((long long)b * G + g) * 2] = dbv;
+    gstat[((long long)b * G + g) * 2 + 1] = ds;
+  }
+  for (int cl = threadIdx.x; cl < cpg; cl += blockDim.x) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int b = 0; b < B; ++b) {
+      a1 += T[(b * cpg + cl) * 2];
+      a2 += T[(b * cpg + cl) * 2 + 1];
+    }
+    dbeta[g * cpg + cl] += a1;
+    dgamma[g * cpg + cl] += a2;
+  }
 }
 
 // grid (P, B): dx = rstd * (gamma*dyh - (db_g + xhat*ds_g)/n) (+ dx_add)
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
                                                                   const bf16* __restrict__ x, long long ldx,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  const float* __restrict__ stats, const float* __restrict__ ws,
+                                                                  const float* __restrict__ stats, const float* __restrict__ gstat,
                                                                   const bf16* __restrict__ dx_add, long long ldadd,
                                                                   bf16* __restrict__ dx, long long lddx, int HW, int C, int G,
                                                                   int silu) {
@@ -195,20 +246,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int cpg = C / G;
   if (threadIdx.x < G) {
-    const int g = threadIdx.x;
-    float ds = 0.f, dbv = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      float a1 = 0.f, a2 = 0.f;
-      for (int i = 0; i < P; ++i) {
-        const float* o = ws + (((long long)b * P + i) * C + c) * 2;
-        a1 += o[0];
-        a2 += o[1];
-      }
-      dbv += gamma[c] * a1;
-      ds += gamma[c] * a2;
-    }
-    s_ds[g] = ds;
-    s_db[g] = dbv;
+    s_db[threadIdx.x] = gstat[((long long)b * G + threadIdx.x) * 2];
+    s_ds[threadIdx.x] = gstat[((long long)b * G + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   const int V = C / 8, R = GN_THREADS / V;
@@ -249,18 +288,33 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __
   }
 }
 
-// dgamma[c] += sum_i ws[i][c][1], dbeta[c] += sum_i ws[i][c][0] over `n_part` partial slabs
-__global__ void affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C, float* __restrict__ dgamma,
-                                          float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// dgamma[c] += sum_i ws[i][c][1], dbeta[c] += sum_i ws[i][c][0] over `n_part` partial slabs.
+// grid (ceil(C/32)), block (32 channels, 8 partial lanes): coalesced float2 reads, smem tree over the 8 lanes.
+__global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sm[8][32][2];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float a1 = 0.f, a2 = 0.f;
-  for (int i = 0; i < n_part; ++i) {
-    a1 += ws[((long long)i * C + c) * 2];
-    a2 += ws[((long long)i * C + c) * 2 + 1];
+  if (c < C) {
+    for (int i = pl; i < n_part; i += 8) {
+      const float2 t = *reinterpret_cast<const float2*>(ws + ((long long)i * C + c) * 2);
+      a1 += t.x;
+      a2 += t.y;
+    }
   }
-  dbeta[c] += a1;
-  dgamma[c] += a2;
+  sm[pl][cl][0] = a1;
+  sm[pl][cl][1] = a2;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      a1 += sm[k][cl][0];
+      a2 += sm[k][cl][1];
+    }
+    dbeta[c] += a1;
+    dgamma[c] += a2;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
@@ -373,18 +427,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       }
     }
   }
+  // block-level sum of the per-warp partials: warps take turns adding into shared memory (each lane owns distinct
+  // channels, so the read-modify-writes are conflict-free and need no atomics)
+  for (int wturn = 0; wturn < (int)(blockDim.x >> 5); ++wturn) {
+    if ((int)(threadIdx.x >> 5) == wturn) {
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j) {
-    const int v = lane + 32 * j;
-    if (v < V) {
+      for (int j = 0; j < LN_MAXV; ++j) {
+        const int v = lane + 32 * j;
+        if (v < V) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&sm[(v * 8 + e) * 2], ab[j][e]);
-        atomicAdd(&sm[(v * 8 + e) * 2 + 1], ag[j][e]);
+          for (int e = 0; e < 8; ++e) {
+            sm[(v * 8 + e) * 2] += ab[j][e];
+            sm[(v * 8 + e) * 2 + 1] += ag[j][e];
+          }
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   float* o = ws + (long long)blockIdx.x * C * 2;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) o[i] = sm[i];
 }
@@ -401,7 +461,7 @@ using namespace sd2;
 
 extern "C" {
 
-long long sd2_groupnorm_ws_floats(int B, int C) { return (long long)B * GN_MAXP * C * 2; }
+long long sd2_groupnorm_ws_floats(int B, int C) { return (long long)B * GN_MAXP * C * 2 + (long long)B * 64 * 2; }
 
 int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* gamma, const float* beta, void* y,
                       long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
@@ -410,7 +470,8 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_fwd: unsupported C/G");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const dim3 grid(gn_chunks(HW), B);
-  gn_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
+  const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
+  gn_stats_kernel<<<grid, GN_THREADS, red_smem, stream>>>(reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
   gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, gamma, beta,
                                                    reinterpret_cast<bf16*>(y), ldy, stats, ws, HW, C, G, eps, silu);
   return check_launch(ctx, "groupnorm_fwd", 2);
@@ -425,13 +486,15 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int P = gn_chunks(HW);
   const dim3 grid(P, B);
-  gn_bwd_stats_kernel<<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
+  const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
+  float* gstat = ws + (long long)B * GN_MAXP * C * 2;
+  gn_bwd_stats_kernel<<<grid, GN_THREADS, red_smem, stream>>>(
       reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws, HW, C, G, silu);
+  gn_bwd_reduce_kernel<<<G, 256, (size_t)B * (C / G) * 2 * sizeof(float), stream>>>(ws, gamma, gstat, dgamma, dbeta, B, P, C, G);
   gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy), lddy,
-                                                       reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws,
+                                                       reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, gstat,
                                                        reinterpret_cast<const bf16*>(dx_add), ldadd,
                                                        reinterpret_cast<bf16*>(dx), lddx, HW, C, G, silu);
-  affine_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, B * P, C, dgamma, dbeta);
   return check_launch(ctx, "groupnorm_bwd", 3);
 }
 
@@ -459,7 +522,7 @@ int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* 
                                                                 reinterpret_cast<const bf16*>(x), gamma, stats,
                                                                 reinterpret_cast<const bf16*>(dx_add),
                                                                 reinterpret_cast<bf16*>(dx), ws, rows, C);
-  affine_grad_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, blocks, C, dgamma, dbeta);
+  affine_grad_reduce_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, blocks, C, dgamma, dbeta);
   return check_launch(ctx, "layernorm_bwd", 2);
 }
 

@@ -373,3 +373,10 @@ def mse_head(ctx, pred8, noise, pred_nchw, dpred8, loss_acc, gscale, B, H, W):
     ctx.check(
         ctx.lib.sd2_mse_head(ctx.h, _p(pred8), _p(noise), _DT[noise.dtype], _p(pred_nchw), _p(dpred8), _p(loss_acc),
                              float(gscale), B, H, W, _s()))
+
+
+def adamw_step(ctx, p, g, m, v, p16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
+    """In-place fused AdamW over flat fp32 tensors (p16: optional bf16 shadow of p)."""
+    ctx.check(
+        ctx.lib.sd2_adamw_step(ctx.h, _p(p), _p(g), _p(m), _p(v), _p(p16), p.numel(), float(lr), float(beta1), float(beta2),
+                               float(eps), float(weight_decay), int(step), float(grad_scale), int(zero_grad), _s()))

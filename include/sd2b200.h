@@ -170,6 +170,13 @@ int sd2_unpad_accum_rows(sd2_ctx* ctx, const float* src, int cols_src, float* ds
 int sd2_mse_head(sd2_ctx* ctx, const void* pred_nhwc8, const void* noise, int noise_dtype, void* pred_nchw,
                  void* dpred_nhwc8, float* loss_acc, float gscale, int B, int H, int W, sd2_stream stream);
 
+/* ---- optimizer: replaces torch.optim.AdamW.step() (reference train.py:33, yaml SD-2-base-256.yaml:55-58) over one flat
+ *      fp32 range: p *= 1 - lr*wd; m,v moments; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  grad is multiplied by
+ *      grad_scale first; param_bf16 (optional) receives the bf16 shadow copy; zero_grad != 0 clears grad afterwards. */
+int sd2_adamw_step(sd2_ctx* ctx, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   float grad_scale, int zero_grad, sd2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
