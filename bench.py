@@ -135,7 +135,8 @@ def run_ours(args):
     B, R = args.batch, args.latent
     torch.manual_seed(17)  # identical init on every rank (reference train.py:29) ...
     model = stable_diffusion_2(pretrained=False, precomputed_latents=True, fsdp=False)
-    opt = torch.optim.AdamW(model.parameters(), lr=1.0e-4, weight_decay=0.01, fused=True)  # reference yaml :55-58
+    from diffusion_b200.optim import FusedAdamW
+    opt = FusedAdamW(model.parameters(), lr=1.0e-4, weight_decay=0.01)  # reference yaml :55-58 (torch AdamW defaults)
     torch.manual_seed(17 + rank)  # ... then per-rank noise / timestep / data streams (composer reseeds seed + rank)
     lat_h = torch.randn(B, 4, R, R).to(torch.bfloat16).pin_memory()
     ctx_h = torch.randn(B, 77, 1024).to(torch.bfloat16).pin_memory()

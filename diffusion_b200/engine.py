@@ -42,8 +42,18 @@ def _align(n, a=64):
 
 
 class ParamArena:
+    _live = []  # weak references to every arena (FusedAdamW finds the arena of its parameters here)
+
+    @classmethod
+    def live(cls):
+        out = [r() for r in cls._live]
+        cls._live = [r for r, a in zip(cls._live, out) if a is not None]
+        return [a for a in out if a is not None]
 
     def __init__(self, unet, device):
+        import weakref
+        ParamArena._live.append(weakref.ref(self))
+        self.shadow_version = None  # parameter-version stamp the bf16 shadow was last refreshed at
         self.entries = {}
         off = 0
         plist = list(unet.named_parameters())
@@ -98,6 +108,27 @@ class ParamArena:
 
     def bound(self):
         return all(p.data_ptr() == self.p32.data_ptr() + 4 * self.entries[n][0] for n, p in self.params.items())
+
+    def grads_bound(self):
+        return all(p.grad is not None and p.grad.data_ptr() == self.g32.data_ptr() + 4 * self.entries[n][0]
+                   for n, p in self.params.items())
+
+    def param_set(self):
+        return {id(p) for p in self.params.values()}
+
+    def version(self):
+        """Changes whenever any parameter is modified in place through torch (optimizer step, load_state_dict, EMA
+        swap): decides whether the bf16 shadow must be re-cast before a forward."""
+        return sum(p._version for p in self.params.values())
+
+    def mark_shadow_fresh(self):
+        self.shadow_version = self.version()
+
+    def refresh_shadow(self, ctx):
+        v = self.version()
+        if v != self.shadow_version:
+            ops.cast_f32_to_bf16(ctx, self.p32, self.p16)
+            self.shadow_version = v
 
 
 class Engine:
@@ -487,7 +518,6 @@ class Engine:
         boc, heads = cfg['block_out_channels'], cfg['attention_head_dim']
         M = B * H * W
         # ---- per-step weight refresh: fp32 master -> bf16 shadow (+ the two padded special cases)
-        self.f(ops.cast_f32_to_bf16, arena.p32, arena.p16)
         cin_w = self.p32('conv_in.weight')  # storage [9, C0, 4]
         self.w_in16 = self.buf(9, boc[0], 8)
         self.f(ops.pad_cast_rows, cin_w.reshape(-1), 4, self.w_in16, 8, 9 * boc[0])
@@ -614,6 +644,7 @@ class Engine:
 
     # ---------------------------------------------------------------------------------------------- execution
     def run_forward(self):
+        self.arena.refresh_shadow(self.ctx)  # fp32 master -> bf16 shadow, only if the weights changed outside FusedAdamW
         if self.graph_fwd is not None:
             self.graph_fwd.replay()
         else:

@@ -1,0 +1,82 @@
+"""Fused AdamW for the B200 UNet: same constructor and update rule as `torch.optim.AdamW`
+(the reference instantiates it from yaml, `diffusion/train.py:33`, `yamls/hydra-yamls/SD-2-base-256.yaml:55-58`), but
+one kernel launch per step over the flat fp32 parameter arena of the engine.  The same launch refreshes the bf16
+shadow weights the tensor-core kernels read and clears the gradient arena for the next accumulation, so the separate
+cast kernel, the memset and the 686-tensor multi-tensor-apply launches disappear from the step.
+
+Parameters that do not live in an engine arena (or before the first forward has built it) are updated tensor by
+tensor through the same kernel.
+"""
+import torch
+
+from diffusion_b200 import ops
+
+
+class FusedAdamW(torch.optim.Optimizer):
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, **_ignored):
+        if amsgrad:
+            raise ValueError('FusedAdamW: amsgrad is not implemented')
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError('FusedAdamW: invalid hyper-parameter')
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self._grads_cleared = False
+
+    def _arena_of(self, group):
+        """The engine arena holding every parameter (and gradient) of this group, if there is one."""
+        from diffusion_b200.engine import ParamArena
+        ps = [p for p in group['params'] if p.requires_grad]
+        if not ps:
+            return None
+        for arena in ParamArena.live():
+            mine = arena.param_set()
+            if all(id(p) in mine for p in ps) and len(ps) == len(mine) and arena.bound() and arena.grads_bound():
+                return arena
+        return None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        cleared = True
+        for group in self.param_groups:
+            lr, (b1, b2), eps, wd = group['lr'], group['betas'], group['eps'], group['weight_decay']
+            arena = self._arena_of(group)
+            if arena is not None:
+                st = self.state.setdefault('arena%d' % id(arena), {})
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(arena.p32)
+                    st['exp_avg_sq'] = torch.zeros_like(arena.p32)
+                st['step'] += 1
+                ctx = ops.get_ctx(arena.p32.device)
+                ops.adamw_step(ctx, arena.p32, arena.g32, st['exp_avg'], st['exp_avg_sq'], arena.p16, lr, b1, b2, eps, wd,
+                               st['step'], zero_grad=True)
+                arena.mark_shadow_fresh()
+                continue
+            cleared = False
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if p.device.type != 'cuda' or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError('FusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)')
+                st = self.state[p]
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p)
+                    st['exp_avg_sq'] = torch.zeros_like(p)
+                st['step'] += 1
+                ops.adamw_step(ops.get_ctx(p.device), p, p.grad, st['exp_avg'], st['exp_avg_sq'], None, lr, b1, b2, eps, wd,
+                               st['step'])
+        self._grads_cleared = cleared
+        return loss
+
+    def zero_grad(self, set_to_none=True):
+        """The arena path has already cleared the gradients inside step(); keep the `.grad` views bound so that the
+        next backward accumulates in place (no memset, no 686 gradient hand-offs through autograd)."""
+        if self._grads_cleared:
+            self._grads_cleared = False
+            return
+        super().zero_grad(set_to_none=set_to_none)
