@@ -14,7 +14,7 @@ _CSRC = os.path.join(_HERE, 'csrc')
 _ROOT = os.path.dirname(_HERE)
 _BUILD = os.path.join(_ROOT, 'build')
 LIB_PATH = os.path.join(_HERE, 'libsd2b200.so')
-SOURCES = ['api.cu', 'gemm_tc.cu', 'k1_noise_sched.cu', 'norm.cu', 'pointwise.cu']
+SOURCES = ['api.cu', 'gemm_tc.cu', 'attn.cu', 'k1_noise_sched.cu', 'norm.cu', 'pointwise.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
     '-Wno-deprecated-gpu-targets'
@@ -115,6 +115,10 @@ SIGNATURES = {
     'sd2_layernorm_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     'sd2_softmax_fwd': (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _i, _vp]),
     'sd2_softmax_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _f, _vp]),
+    'sd2_attn_fwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    'sd2_attn_bwd_ws_bytes': (_ll, [_i, _i, _i]),
+    'sd2_attn_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i,
+                          _i, _i, _i, _f, _vp]),
     'sd2_geglu_fwd': (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     'sd2_geglu_bwd': (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp]),
     'sd2_silu_fwd': (_i, [_vp, _vp, _vp, _ll, _vp]),
@@ -179,6 +183,8 @@ class DryLib:
             self.calls[name] = self.calls.get(name, 0) + 1
             if name == 'sd2_groupnorm_ws_floats':
                 return a[0] * 32 * a[1] * 2 + a[0] * 128
+            if name == 'sd2_attn_bwd_ws_bytes':
+                return a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * a[2] * 4
             if name == 'sd2_layernorm_ws_floats':
                 return 148 * 4 * a[1] * 2
             if name == 'sd2_last_error':

@@ -63,7 +63,7 @@ bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[
 
 // output tensor map of the GEMM epilogue: dims (N, M, nb0, nb1), box (chunk columns, 32 rows); the inner box row is
 // 128 B (SWIZZLE_128B: 64 bf16 / 32 fp32) or 64 B (SWIZZLE_64B: 32 bf16)
-static bool out_tmap(CUtensorMap* tm, void* ptr, bool f32, int chunk_cols, int N, int M, long long ldo, long long nb0,
+bool out_tmap(CUtensorMap* tm, void* ptr, bool f32, int chunk_cols, int N, int M, long long ldo, long long nb0,
                      long long nb1, long long bs0, long long bs1, std::string* err) {
   const uint64_t es = f32 ? 4 : 2;
   if (nb0 < 1) nb0 = 1;
@@ -78,7 +78,7 @@ static bool out_tmap(CUtensorMap* tm, void* ptr, bool f32, int chunk_cols, int N
 }
 
 // tensor map of a plain (possibly batched) operand; K-major box = (64, box_rows), MN-major box = (64, 64)
-static bool plain_tmap(CUtensorMap* tm, const sd2_operand& o, int box_rows, std::string* err) {
+bool plain_tmap(CUtensorMap* tm, const sd2_operand& o, int box_rows, std::string* err) {
   const uint64_t nb0 = o.nb0 > 0 ? (uint64_t)o.nb0 : 1, nb1 = o.nb0 > 0 && o.nb1 > 0 ? (uint64_t)o.nb1 : 1;
   const uint64_t dims[4] = {(uint64_t)o.cols, (uint64_t)o.rows, nb0, nb1};
   // strides must be non-zero multiples of 16 B even for extent-1 dims

@@ -1,0 +1,707 @@
+// Fused flash-style attention, forward and backward, head_dim 64, non-causal, for sm_100a (tcgen05 / TMEM / TMA).
+//
+// Replaces the xformers / SDPA memory-efficient attention diffusers' `Attention` calls inside every
+// BasicTransformerBlock (self-attention over HW tokens and cross-attention over the 77 x 1024 CLIP context;
+// reference diffusion/models/models.py:109-111 enables it, the call site is the UNet forward at
+// diffusion/models/stable_diffusion.py:183) and its backward.  Scores never touch HBM.
+//
+// Layout: q/k/v/o/do are column slices of NHWC-flattened activations: token row (b*N + i), head h at columns
+// h*64 .. h*64+63, row stride ld (elements).  lse is the base-2 log-sum-exp of the scaled scores, [B*heads][Nq] fp32.
+//
+// Forward  (CTA = one 128-query tile of one (b, h); 2 CTAs per SM):
+//   warp 0 TMA: Q once, K/V tiles (128 keys) through a 2-stage ring
+//   warp 1 MMA: S = Q K^T (M128 N128 K64) into TMEM; O_j = P_j V_j (M128 N64 K128, V read MN-major) into TMEM
+//   warps 2-5 : one thread per query row: two passes over S in TMEM (row max, then exp2), P (bf16) -> swizzled smem
+//               as the A operand of the second GEMM; running (m, l) and the fp32 output row stay in registers
+// Backward (CTA = one 128-key tile of one (b, h), loops over the query tiles; 1 CTA per SM):
+//   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - D) scale (bf16, smem)
+//   dV += P^T dO, dK += dS^T Q (accumulate in TMEM over the loop), dQ_i = dS K (TMEM -> smem -> TMA reduce-add fp32)
+//   The same smem image of a [128 x 64] tile serves as K-major operand of one GEMM and MN-major operand of another.
+#include "common.cuh"
+#include "host.h"
+
+namespace sd2 {
+
+static constexpr int AT_THREADS = 192;
+static constexpr int AT_TILE = 128 * 64 * 2;  // one [128 rows][64 bf16] tile, SWIZZLE_128B: 16 KB
+
+struct AttnParams {
+  int B, heads, Nq, Nk;
+  float c2;     // scale * log2(e)
+  float scale;
+  bf16* o;
+  long long ldo;
+  float* lse;         // [B*heads][Nq]
+  const float* dvec;  // [B*heads][Nq]  rowsum(dO * O)
+  bf16* dk;
+  long long lddk;
+  bf16* dv;
+  long long lddv;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ================================================================================================ forward
+__global__ void __launch_bounds__(AT_THREADS, 2)
+    attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + AT_TILE;      // stage s: K at s*2*AT_TILE, V at s*2*AT_TILE + AT_TILE
+  uint8_t* sP = sKV + 4 * AT_TILE;  // one 64-column half of P: [128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* p_empty = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint64_t* o_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nkt = (p.Nk + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&kv_full[s], 1);
+        mbar_init(&kv_empty[s], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(s_empty, 4);
+      mbar_init(p_full, 4);
+      mbar_init(p_empty, 1);
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 4);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, AT_TILE);
+      tma_load_4d(sQ, &tmQ, q_full, 0, qt * 128, h, b);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkt; ++j) {
+      const int s = j & 1;
+      mbar_wait(&kv_empty[s], (uint32_t)((j >> 1) & 1) ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE);
+        tma_load_4d(sKV + s * 2 * AT_TILE, &tmK, &kv_full[s], 0, j * 128, h, b);
+        tma_load_4d(sKV + s * 2 * AT_TILE + AT_TILE, &tmV, &kv_full[s], 0, j * 128, h, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dP0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t dK0 = umma_desc_sw128(smem_u32(sKV), 16, 1024);                 // stage 0 K, K-major
+    const uint64_t dV0 = umma_desc_sw128(smem_u32(sKV + AT_TILE), 8192, 1024);     // stage 0 V, MN-major
+    constexpr uint64_t STAGE = (2 * AT_TILE) >> 4;
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tS, dQ0 + 2 * ks, dK0 + 2 * ks, idesc_s, ks != 0 ? 1u : 0u);
+      tc_commit(s_full);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkt; ++j) {
+      const uint64_t dVs = dV0 + (uint64_t)(j & 1) * STAGE;
+      if (j > 0) mbar_wait(o_empty, (uint32_t)((j - 1) & 1));  // softmax warps have read O_{j-1}
+#pragma unroll 1
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        mbar_wait(p_full, (uint32_t)hlf);  // completion #(2j + hlf)
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc_mma_bf16(tO, dP0 + 2 * ks, dVs + (uint64_t)(hlf * 4 + ks) * 128, idesc_o, (hlf | ks) != 0 ? 1u : 0u);
+          tc_commit(p_empty);
+          if (hlf == 1) {
+            tc_commit(o_full);
+            tc_commit(&kv_empty[j & 1]);
+          }
+        }
+        __syncwarp();
+        if (hlf == 0 && j + 1 < nkt) {  // next score tile, issued between the two halves of P_j V_j
+          mbar_wait(s_empty, (uint32_t)(j & 1));  // S_j fully read
+          mbar_wait(&kv_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t dKs = dK0 + (uint64_t)((j + 1) & 1) * STAGE;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tS, dQ0 + 2 * ks, dKs + 2 * ks, idesc_s, ks != 0 ? 1u : 0u);
+            tc_commit(s_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + output (thread = query row)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float o[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) o[e] = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      const int nvalid = p.Nk - j * 128;  // columns >= nvalid are padding
+      mbar_wait(s_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32];
+        tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)(c * 32), rs);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(rs[e]));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float a = ex2((m - m_new) * p.c2);
+      const float mc = m_new * p.c2;
+      m = m_new;
+      float rowsum = 0.f;
+      // pass 2: P = exp2(S c2 - m c2) -> bf16 -> swizzled smem, one 64-column half at a time
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        if ((c & 1) == 0) mbar_wait(p_empty, (uint32_t)((c >> 1) & 1) ^ 1u);  // previous half consumed by the MMA
+        uint32_t rs[32];
+        tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)(c * 32), rs);
+        tmem_wait_ld();
+        if (c == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = c * 32 + g * 8 + e;
+            const float x = col < nvalid ? ex2(fmaf(__uint_as_float(rs[g * 8 + e]), p.c2, -mc)) : 0.f;
+            pv[e] = x;
+            rowsum += x;
+          }
+          uint4 u;
+          u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
+          u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
+          const int j16 = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(sP + r * 128 + ((j16 ^ (r & 7)) << 4)) = u;
+        }
+        if (c & 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
+        }
+      }
+      l = l * a + rowsum;
+      // O = O a + P_j V_j
+      mbar_wait(o_full, (uint32_t)(j & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ro[32];
+        tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(c * 32), ro);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[c * 32 + e] = fmaf(o[c * 32 + e], a, __uint_as_float(ro[e]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+    const int row = qt * 128 + r;
+    if (row < p.Nq) {
+      const float inv = 1.f / l;
+      bf16* dst = p.o + ((long long)b * p.Nq + row) * p.ldo + h * 64;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv); u.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+        u.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv); u.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + g * 8) = u;
+      }
+      p.lse[((long long)b * p.heads + h) * p.Nq + row] = m * p.c2 + __log2f(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ================================================================================================ backward
+// D[bh][i] = sum_d O[i][d] dO[i][d]; 8 lanes per (row, head): 16-byte loads, shuffle reduce.
+__global__ void attn_dot_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o, long long lddo,
+                                float* __restrict__ dvec, int B, int heads, int Nq) {
+  const long long total = (long long)B * Nq * heads * 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  long long rowh = i >> 3;
+  const int sub = (int)(i & 7);
+  const bool ok = i < total;
+  long long row = 0;
+  int h = 0;
+  if (ok) {
+    row = rowh / heads;
+    h = (int)(rowh % heads);
+    const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + h * 64 + sub * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(d_o + row * lddo + h * 64 + sub * 8);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+    const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+    acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (ok && sub == 0) {
+    const long long bb = row / Nq, qi = row % Nq;
+    dvec[(bb * heads + h) * Nq + qi] = acc;
+  }
+}
+
+// dst[r][0..cols) bf16 (row stride ldd) = src[r][0..cols) fp32 (dense)
+__global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long ldd, long long rows,
+                                       int cols) {
+  const int V = cols / 8;
+  const long long n = rows * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / V;
+    const int v = (int)(i % V);
+    const float4 a = *reinterpret_cast<const float4*>(src + r * cols + v * 8);
+    const float4 b = *reinterpret_cast<const float4*>(src + r * cols + v * 8 + 4);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + r * ldd + v * 8) = u;
+  }
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+    attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                    const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + AT_TILE;
+  uint8_t* sQ = sV + AT_TILE;        // [2]
+  uint8_t* sdO = sQ + 2 * AT_TILE;   // [2]
+  uint8_t* sPT = sdO + 2 * AT_TILE;  // P^T  : 2 query chunks x [128 key rows][128 B]
+  uint8_t* sdS = sPT + 2 * AT_TILE;  // dS^T : same layout
+  uint8_t* stg = sdS + 2 * AT_TILE;  // 4 warps x 2 x 4 KB fp32 staging for the dQ reduce-add
+  float* sLSE = reinterpret_cast<float*>(stg + 8 * 4096);  // [2][128]
+  float* sD = sLSE + 256;                                   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* sdp_empty = bars + 6;
+  uint64_t* pds_full = bars + 7;
+  uint64_t* pds_empty = bars + 8;
+  uint64_t* dq_full = bars + 9;
+  uint64_t* dq_empty = bars + 10;
+  uint64_t* dkv_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nqt = (p.Nq + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&qdo_full[s], 1);
+        mbar_init(&qdo_empty[s], 1);
+      }
+      mbar_init(sdp_full, 1);
+      mbar_init(sdp_empty, 4);
+      mbar_init(pds_full, 4);
+      mbar_init(pds_empty, 1);
+      mbar_init(dq_full, 1);
+      mbar_init(dq_empty, 4);
+      mbar_init(dkv_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
+                 tdQ = tmem_base + 384;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
+      tma_load_4d(sK, &tmK, kv_full, 0, kt * 128, h, b);
+      tma_load_4d(sV, &tmV, kv_full, 0, kt * 128, h, b);
+    }
+    __syncwarp();
+    for (int i = 0; i < nqt; ++i) {
+      const int s = i & 1;
+      mbar_wait(&qdo_empty[s], (uint32_t)((i >> 1) & 1) ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * AT_TILE);
+        tma_load_4d(sQ + s * AT_TILE, &tmQ, &qdo_full[s], 0, i * 128, h, b);
+        tma_load_4d(sdO + s * AT_TILE, &tmdO, &qdo_full[s], 0, i * 128, h, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : A K-major, B K-major
+    constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major (smem P^T / dS^T), B MN-major
+    constexpr uint32_t id_mn = umma_idesc_bf16(128, 64, 1, 1);   // dQ        : A MN-major (dS), B MN-major (K)
+    const uint64_t aK = umma_desc_sw128(smem_u32(sK), 16, 1024), aV = umma_desc_sw128(smem_u32(sV), 16, 1024);
+    const uint64_t bQ0 = umma_desc_sw128(smem_u32(sQ), 16, 1024), bdO0 = umma_desc_sw128(smem_u32(sdO), 16, 1024);
+    const uint64_t aPT = umma_desc_sw128(smem_u32(sPT), 16, 1024), adS = umma_desc_sw128(smem_u32(sdS), 16, 1024);
+    const uint64_t bQ0mn = umma_desc_sw128(smem_u32(sQ), 8192, 1024), bdO0mn = umma_desc_sw128(smem_u32(sdO), 8192, 1024);
+    const uint64_t adSmn = umma_desc_sw128(smem_u32(sdS), 16384, 1024);  // M chunks (64 queries) 16 KB apart
+    const uint64_t bKmn = umma_desc_sw128(smem_u32(sK), 8192, 1024);
+    constexpr uint64_t TS = AT_TILE >> 4;
+    mbar_wait(kv_full, 0);
+    mbar_wait(&qdo_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK + 2 * ks, bQ0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV + 2 * ks, bdO0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+      tc_commit(sdp_full);
+    }
+    __syncwarp();
+    for (int i = 0; i < nqt; ++i) {
+      const int s = i & 1;
+      mbar_wait(pds_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      if (i + 1 < nqt) {  // next tile's scores first: the compute warps get their input while dV/dK/dQ run
+        const int s1 = (i + 1) & 1;
+        mbar_wait(sdp_empty, (uint32_t)(i & 1));
+        mbar_wait(&qdo_full[s1], (uint32_t)(((i + 1) >> 1) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bQ = bQ0 + (uint64_t)s1 * TS, bdO = bdO0 + (uint64_t)s1 * TS;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK + 2 * ks, bQ + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV + 2 * ks, bdO + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+          tc_commit(sdp_full);
+        }
+        __syncwarp();
+      }
+      if (i > 0) mbar_wait(dq_empty, (uint32_t)((i - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bQ = bQ0mn + (uint64_t)s * TS, bdO = bdO0mn + (uint64_t)s * TS;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // K = 128 queries: chunk ks>>2 of P^T (16 KB apart), 32 B per K step inside
+          const uint64_t a = aPT + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
+          tc_mma_bf16(tdV, a, bdO + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = adS + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
+          tc_mma_bf16(tdK, a, bQ + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)  // K = 128 keys: 16 key rows (2048 B) per step in both operands
+          tc_mma_bf16(tdQ, adSmn + (uint64_t)ks * 128, bKmn + (uint64_t)ks * 128, id_mn, ks != 0 ? 1u : 0u);
+        tc_commit(pds_empty);
+        tc_commit(dq_full);
+        tc_commit(&qdo_empty[s]);
+        if (i == nqt - 1) tc_commit(dkv_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps (thread = key row / dQ row)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int key = kt * 128 + r;
+    const bool key_ok = key < p.Nk;
+    const long long bh = (long long)b * p.heads + h;
+    uint8_t* my_stg = stg + (size_t)(warp - 2) * 2 * 4096;
+    int sbuf = 0;
+    float nlse = INFINITY, nD = 0.f;
+    if (r < p.Nq) {
+      nlse = p.lse[bh * p.Nq + r];
+      nD = p.dvec[bh * p.Nq + r];
+    }
+    for (int i = 0; i < nqt; ++i) {
+      const int buf = i & 1;
+      sLSE[buf * 128 + r] = nlse;
+      sD[buf * 128 + r] = nD;
+      named_bar_sync(1, 128);
+      {  // prefetch the next tile's per-query statistics
+        const int qn = (i + 1) * 128 + r;
+        nlse = INFINITY;
+        nD = 0.f;
+        if (i + 1 < nqt && qn < p.Nq) {
+          nlse = p.lse[bh * p.Nq + qn];
+          nD = p.dvec[bh * p.Nq + qn];
+        }
+      }
+      mbar_wait(sdp_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      mbar_wait(pds_empty, (uint32_t)(i & 1) ^ 1u);  // P^T / dS^T smem consumed by the previous iteration's MMAs
+      const float* lse_t = sLSE + buf * 128;
+      const float* d_t = sD + buf * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(c * 32), rs);
+        tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(c * 32), rd);
+        tmem_wait_ld();
+        if (c == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_empty);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 l0 = *reinterpret_cast<const float4*>(lse_t + c * 32 + g * 8);
+          const float4 l1 = *reinterpret_cast<const float4*>(lse_t + c * 32 + g * 8 + 4);
+          const float4 d0 = *reinterpret_cast<const float4*>(d_t + c * 32 + g * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(d_t + c * 32 + g * 8 + 4);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          float pv[8], dsv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float pe = key_ok ? ex2(fmaf(__uint_as_float(rs[g * 8 + e]), p.c2, -ls[e])) : 0.f;
+            pv[e] = pe;
+            dsv[e] = pe * (__uint_as_float(rd[g * 8 + e]) - dd[e]) * p.scale;
+          }
+          uint4 up, ud;
+          up.x = pack_bf16x2(pv[0], pv[1]); up.y = pack_bf16x2(pv[2], pv[3]);
+          up.z = pack_bf16x2(pv[4], pv[5]); up.w = pack_bf16x2(pv[6], pv[7]);
+          ud.x = pack_bf16x2(dsv[0], dsv[1]); ud.y = pack_bf16x2(dsv[2], dsv[3]);
+          ud.z = pack_bf16x2(dsv[4], dsv[5]); ud.w = pack_bf16x2(dsv[6], dsv[7]);
+          const int off = (c >> 1) * AT_TILE + r * 128 + ((((c & 1) * 4 + g) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(sPT + off) = up;
+          *reinterpret_cast<uint4*>(sdS + off) = ud;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // dQ_i (rows = queries): TMEM -> fp32 staging -> TMA reduce-add into the fp32 accumulation buffer
+      mbar_wait(dq_full, (uint32_t)(i & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rq[32];
+        tmem_ld_32x32b_x32(tdQ + lane_off + (uint32_t)(c * 32), rq);
+        tmem_wait_ld();
+        if (c == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_empty);
+        }
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        uint8_t* bufp = my_stg + sbuf * 4096 + lane * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(bufp + ((g ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(rq[g * 4]), __uint_as_float(rq[g * 4 + 1]), __uint_as_float(rq[g * 4 + 2]),
+                          __uint_as_float(rq[g * 4 + 3]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (i * 128 + q * 32 < p.Nq) tma_reduce_add_4d(&tmDQ, my_stg + sbuf * 4096, c * 32, i * 128 + q * 32, h, b);
+          bulk_commit();
+        }
+        sbuf ^= 1;
+      }
+    }
+    // dV, dK of this key tile
+    mbar_wait(dkv_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      bf16* dst = (t == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (t == 0 ? p.lddv : p.lddk) + h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32((t == 0 ? tdV : tdK) + lane_off + (uint32_t)(c * 32), rr);
+        tmem_wait_ld();
+        if (key_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(rr[g * 8 + 0]), __uint_as_float(rr[g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(rr[g * 8 + 2]), __uint_as_float(rr[g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(rr[g * 8 + 4]), __uint_as_float(rr[g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(rr[g * 8 + 6]), __uint_as_float(rr[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static bool head_tmap(CUtensorMap* tm, const void* ptr, long long ld, int N, int heads, int B, std::string* err) {
+  sd2_operand o;
+  o.ptr = ptr;
+  o.mn_major = 0;
+  o.cols = 64;
+  o.rows = N;
+  o.ld = ld;
+  o.nb0 = heads;
+  o.nb1 = B;
+  o.bs0 = 64;
+  o.bs1 = (long long)N * ld;
+  return plain_tmap(tm, o, 128, err);
+}
+
+}  // namespace sd2
+
+using namespace sd2;
+
+extern "C" {
+
+int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                 void* o, long long ldo, float* lse, int B, int heads, int Nq, int Nk, int head_dim, float scale,
+                 sd2_stream stream_) {
+  if (!ctx) return 1;
+  if (head_dim != 64) return fail(ctx, "sd2_attn_fwd: head_dim must be 64");
+  if (B < 1 || heads < 1 || Nq < 1 || Nk < 1) return fail(ctx, "sd2_attn_fwd: empty problem");
+  if ((ldq | ldk | ldv | ldo) % 8) return fail(ctx, "sd2_attn_fwd: row strides must be multiples of 8");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CUtensorMap tmQ, tmK, tmV;
+  std::string err;
+  if (!head_tmap(&tmQ, q, ldq, Nq, heads, B, &err) || !head_tmap(&tmK, k, ldk, Nk, heads, B, &err) ||
+      !head_tmap(&tmV, v, ldv, Nk, heads, B, &err))
+    return fail(ctx, "sd2_attn_fwd: " + err);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk;
+  p.scale = scale;
+  p.c2 = scale * 1.4426950408889634f;
+  p.o = reinterpret_cast<bf16*>(o);
+  p.ldo = ldo;
+  p.lse = lse;
+  const size_t smem = 6 * AT_TILE + 12 * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_fwd attr: ") + cudaGetErrorString(e));
+    attr = true;
+  }
+  attn_fwd_kernel<<<dim3((Nq + 127) / 128, heads, B), AT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  return check_launch(ctx, "attn_fwd");
+}
+
+long long sd2_attn_bwd_ws_bytes(int B, int heads, int Nq) {
+  return (long long)B * Nq * heads * 64 * 4 + (long long)B * heads * Nq * 4;
+}
+
+int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                 const void* o, long long ldo, const void* d_o, long long lddo, const float* lse, void* dq, long long lddq,
+                 void* dk, long long lddk, void* dv, long long lddv, void* ws, int B, int heads, int Nq, int Nk,
+                 int head_dim, float scale, sd2_stream stream_) {
+  if (!ctx) return 1;
+  if (head_dim != 64) return fail(ctx, "sd2_attn_bwd: head_dim must be 64");
+  if (B < 1 || heads < 1 || Nq < 1 || Nk < 1) return fail(ctx, "sd2_attn_bwd: empty problem");
+  if ((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) % 8) return fail(ctx, "sd2_attn_bwd: row strides must be multiples of 8");
+  if (!ws) return fail(ctx, "sd2_attn_bwd: workspace required (sd2_attn_bwd_ws_bytes)");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int C = heads * 64;
+  float* dq32 = reinterpret_cast<float*>(ws);                      // [B*Nq][C] fp32 accumulation of dQ
+  float* dvec = dq32 + (long long)B * Nq * C;                      // [B*heads][Nq]
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
+  std::string err;
+  if (!head_tmap(&tmQ, q, ldq, Nq, heads, B, &err) || !head_tmap(&tmK, k, ldk, Nk, heads, B, &err) ||
+      !head_tmap(&tmV, v, ldv, Nk, heads, B, &err) || !head_tmap(&tmdO, d_o, lddo, Nq, heads, B, &err))
+    return fail(ctx, "sd2_attn_bwd: " + err);
+  if (!out_tmap(&tmDQ, dq32, true, 32, 64, Nq, C, heads, B, 64, (long long)Nq * C, &err))
+    return fail(ctx, "sd2_attn_bwd dq map: " + err);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk;
+  p.scale = scale;
+  p.c2 = scale * 1.4426950408889634f;
+  p.lse = const_cast<float*>(lse);
+  p.dvec = dvec;
+  p.dk = reinterpret_cast<bf16*>(dk);
+  p.lddk = lddk;
+  p.dv = reinterpret_cast<bf16*>(dv);
+  p.lddv = lddv;
+  const long long nd = (long long)B * Nq * heads * 8;
+  attn_dot_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(o), ldo,
+                                                                    reinterpret_cast<const bf16*>(d_o), lddo, dvec, B, heads, Nq);
+  cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * Nq * C * 4, stream);
+  if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
+  const size_t smem = 10 * AT_TILE + 8 * 4096 + 4 * 128 * 4 + 13 * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd attr: ") + cudaGetErrorString(e));
+    attr = true;
+  }
+  attn_bwd_kernel<<<dim3((Nk + 127) / 128, heads, B), AT_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+  cast2d_f32_bf16_kernel<<<grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(
+      dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
+  return check_launch(ctx, "attn_bwd", 3);
+}
+
+}  // extern "C"

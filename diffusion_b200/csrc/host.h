@@ -34,6 +34,11 @@ bool encode_tmap_4d(CUtensorMap* out, int dtype, int swizzle_bytes, const void* 
                     const uint64_t strides_bytes[3], const uint32_t box[4], std::string* err);
 
 int gemm_out_chunk(int BN);
+// tensor map of a plain (possibly batched) bf16 operand; K-major box = (64, box_rows), MN-major box = (64, 64)
+bool plain_tmap(CUtensorMap* tm, const sd2_operand& o, int box_rows, std::string* err);
+// output map: dims (N, M, nb0, nb1), box (chunk_cols, 32 rows); inner box row 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
+bool out_tmap(CUtensorMap* tm, void* ptr, bool f32, int chunk_cols, int N, int M, long long ldo, long long nb0,
+              long long nb1, long long bs0, long long bs1, std::string* err);
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
                            int BN, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream);
 cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int N, float alpha, const float* bias,

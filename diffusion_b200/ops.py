@@ -380,3 +380,22 @@ def adamw_step(ctx, p, g, m, v, p16, lr, beta1, beta2, eps, weight_decay, step, 
     ctx.check(
         ctx.lib.sd2_adamw_step(ctx.h, _p(p), _p(g), _p(m), _p(v), _p(p16), p.numel(), float(lr), float(beta1), float(beta2),
                                float(eps), float(weight_decay), int(step), float(grad_scale), int(zero_grad), _s()))
+
+
+# ------------------------------------------------------------------------------------------------- fused attention
+def attn_bwd_ws(ctx, B, heads, Nq, device):
+    return torch.empty(ctx.lib.sd2_attn_bwd_ws_bytes(B, heads, Nq), dtype=torch.uint8, device=device)
+
+
+def attn_fwd(ctx, q, k, v, o, lse, B, heads, Nq, Nk, scale):
+    """q/k/v/o: bf16 2-D column-slice views [B*N, heads*64] (any row stride); lse fp32 [B*heads, Nq]."""
+    ctx.check(
+        ctx.lib.sd2_attn_fwd(ctx.h, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(lse), B,
+                             heads, Nq, Nk, 64, float(scale), _s()))
+
+
+def attn_bwd(ctx, q, k, v, o, do, lse, dq, dk, dv, ws, B, heads, Nq, Nk, scale):
+    ctx.check(
+        ctx.lib.sd2_attn_bwd(ctx.h, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(do),
+                             do.stride(0), _p(lse), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(ws), B,
+                             heads, Nq, Nk, 64, float(scale), _s()))

@@ -135,6 +135,20 @@ int sd2_softmax_fwd(sd2_ctx* ctx, const float* S, long long lds, void* P, long l
 int sd2_softmax_bwd(sd2_ctx* ctx, const void* P, long long ldp, const float* dP, long long lddp, void* dS,
                     long long ldds, long long rows, int cols, float scale, sd2_stream stream);
 
+/* ---- fused flash-style attention (scores never leave the SM; replaces xformers / SDPA, reference models.py:109-111).
+ * q/k/v/o/d_o: bf16 column slices of [tokens][channels] activations: token row b*N + i, head h at columns h*64..h*64+63
+ * relative to the given pointer, row stride ld* (elements, multiples of 8).  head_dim must be 64.
+ * lse: fp32 [B*heads][Nq], base-2 log-sum-exp of the scaled scores (written by fwd, read by bwd).
+ * bwd: ws = scratch of sd2_attn_bwd_ws_bytes(B, heads, Nq) bytes (fp32 dQ accumulation + rowsum(dO*O)). */
+int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                 void* o, long long ldo, float* lse, int B, int heads, int Nq, int Nk, int head_dim, float scale,
+                 sd2_stream stream);
+long long sd2_attn_bwd_ws_bytes(int B, int heads, int Nq);
+int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                 const void* o, long long ldo, const void* d_o, long long lddo, const float* lse, void* dq, long long lddq,
+                 void* dk, long long lddk, void* dv, long long lddv, void* ws, int B, int heads, int Nq, int Nk,
+                 int head_dim, float scale, sd2_stream stream);
+
 /* ---- pointwise / layout kernels -------------------------------------------------------------------------------- */
 /* GEGLU: h = [a | g] ([rows][2*C]) -> y = a * gelu_erf(g) ([rows][C]) */
 int sd2_geglu_fwd(sd2_ctx* ctx, const void* h, void* y, long long rows, int C, sd2_stream stream);

@@ -422,3 +422,49 @@ def test_fused_adamw_matches_torch(ctx):
         assert float(gbuf.abs().max()) == 0.0
         close(p, ref.detach(), rtol=1e-5, atol=1e-6, name=f'adamw step {step}')
         assert torch.equal(p16, p.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ fused attention
+ATTN_SHAPES = [(2, 5, 1024, 1024), (2, 10, 256, 77), (1, 4, 64, 64), (2, 2, 16, 77), (1, 2, 300, 200), (1, 1, 2048, 2048),
+               (3, 1, 128, 128), (1, 3, 129, 257)]
+
+
+def _attn_inputs(B, heads, Nq, Nk, self_attn):
+    Cc = heads * 64
+    if self_attn:  # q | k | v are column slices of one fused [B*N, 3C] projection (row stride 3C), as in the engine
+        qkv = bf(B * Nq, 3 * Cc, seed=1)
+        return qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    q = bf(B * Nq, Cc, seed=1)
+    kv = bf(B * Nk, 2 * Cc, seed=2)
+    return q, kv[:, :Cc], kv[:, Cc:]
+
+
+@pytest.mark.parametrize('B,heads,Nq,Nk', ATTN_SHAPES)
+def test_flash_attention_fwd_bwd(ctx, B, heads, Nq, Nk):
+    from diffusion_b200 import ops
+    Cc, d = heads * 64, 64
+    scale = d**-0.5
+    q, k, v = _attn_inputs(B, heads, Nq, Nk, Nq == Nk)
+    o = torch.zeros(B * Nq, Cc, dtype=torch.bfloat16, device='cuda')
+    lse = torch.zeros(B * heads, Nq, dtype=torch.float32, device='cuda')
+    ops.attn_fwd(ctx, q, k, v, o, lse, B, heads, Nq, Nk, scale)
+    qh = q.float().reshape(B, Nq, heads, d).transpose(1, 2).requires_grad_(True)
+    kh = k.float().reshape(B, Nk, heads, d).transpose(1, 2).requires_grad_(True)
+    vh = v.float().reshape(B, Nk, heads, d).transpose(1, 2).requires_grad_(True)
+    S = (qh @ kh.transpose(-1, -2)) * scale
+    o_ref = torch.softmax(S, -1) @ vh
+    close(o, o_ref.transpose(1, 2).reshape(B * Nq, Cc), name='attn fwd')
+    lse_ref = torch.logsumexp(S, -1) / math.log(2.0)
+    close(lse.view(B, heads, Nq), lse_ref, rtol=1e-3, atol=2e-2, name='lse')
+    # backward
+    do = bf(B * Nq, Cc, seed=9)
+    o_ref.backward(do.float().reshape(B, Nq, heads, d).transpose(1, 2))
+    dq_buf = torch.zeros(B * Nq, 3 * Cc, dtype=torch.bfloat16, device='cuda')  # strided outputs, like qkv.grad slices
+    dkv_buf = torch.zeros(B * Nk, 2 * Cc, dtype=torch.bfloat16, device='cuda')
+    dq, dk, dv = dq_buf[:, Cc:2 * Cc], dkv_buf[:, :Cc], dkv_buf[:, Cc:]
+    ws = ops.attn_bwd_ws(ctx, B, heads, Nq, q.device)
+    ops.attn_bwd(ctx, q, k, v, o, do, lse, dq, dk, dv, ws, B, heads, Nq, Nk, scale)
+    close(dq, qh.grad.transpose(1, 2).reshape(B * Nq, Cc), rtol=3e-2, name='attn dq')
+    close(dk, kh.grad.transpose(1, 2).reshape(B * Nk, Cc), rtol=3e-2, name='attn dk')
+    close(dv, vh.grad.transpose(1, 2).reshape(B * Nk, Cc), rtol=3e-2, name='attn dv')
+    assert float(dq_buf[:, :Cc].abs().max()) == 0 and float(dq_buf[:, 2 * Cc:].abs().max()) == 0, 'dq wrote outside its slice'
