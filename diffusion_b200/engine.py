@@ -25,7 +25,7 @@ BF16 = torch.bfloat16
 
 
 _GEMM_FUNCS = (ops.linear_fwd, ops.linear_dgrad, ops.linear_wgrad, ops.conv3x3_fwd, ops.conv3x3_dgrad, ops.conv3x3_wgrad,
-               ops.bmm)
+               ops.bmm, ops.attn_fwd, ops.attn_bwd)
 
 
 class Node:
@@ -148,15 +148,7 @@ class Engine:
         self.gn_ws = ops.groupnorm_ws(self.ctx, B, cmax, dev)
         self.ln_ws = ops.layernorm_ws(self.ctx, B * H * W, max(self.cfg['block_out_channels']), dev)
         self.act_bytes = 0
-        # attention score scratch (S / dP in fp32, dS in bf16), shared by all layers: sized for the largest level
-        smax, hw = 8, H * W
-        for i, t in enumerate(self.cfg['down_block_types']):
-            if t == 'CrossAttnDownBlock2D':
-                smax = max(smax, B * self.cfg['attention_head_dim'][i] * hw * _align(max(hw, L), 8))
-            hw //= 4
-        smax = max(smax, B * self.cfg['attention_head_dim'][-1] * (hw * 4) * _align(max(hw * 4, L), 8))
-        self.S32 = torch.empty(smax, dtype=torch.float32, device=dev)
-        self.dS16 = torch.empty(smax, dtype=BF16, device=dev)
+        self.attn_ws = None  # scratch of the fused attention backward (fp32 dQ accumulation), shared by all layers
         self.gemm_flops = 0  # algorithmic 2*M*N*K of every tensor-core GEMM recorded (fwd + bwd)
         self.fwd_is_gemm, self.bwd_is_gemm = [], []
         # static inputs (written by K1 / the prep kernels)
@@ -407,27 +399,18 @@ class Engine:
         return y
 
     def attention(self, q, k, v, qn, kvn, q_col, k_col, v_col, Nq, Nk, heads, C):
-        """softmax(q k^T / sqrt(d)) v per (image, head).  q/k/v are column slices (offset *_col) of nodes qn / kvn.
-        Materialised-score path: S (fp32 scratch) -> P (bf16, saved) -> O."""
+        """softmax(q k^T / sqrt(d)) v per (image, head), fused flash-style kernel (csrc/attn.cu): scores and
+        probabilities never leave the SM; only the output and the per-row log-sum-exp are saved for backward.
+        q/k/v are column slices (offset *_col) of nodes qn / kvn."""
         B, d = self.B, C // heads
-        ldp = _align(Nk, 8)
         scale = float(d)**-0.5
-        nbh = B * heads
-        P = self.buf(nbh, Nq, ldp)
         out = self.node(B * Nq, C)
-        ldq, ldk = qn.C, kvn.C
-        qd = (d, Nq, ldq, d, Nq * ldq)
-        kd = (d, Nk, ldk, d, Nk * ldk)
-        sd = (ldp, Nq * ldp, heads * Nq * ldp)
-        pd = (Nk, Nq, ldp, Nq * ldp, heads * Nq * ldp)
-        od = (C, d, Nq * C)
-
-        nS = nbh * Nq * ldp
-        S = self.S32[:nS].view(nbh, Nq, ldp)
-        dS = self.dS16[:nS].view(nbh, Nq, ldp)
-        self.f(ops.bmm, q, 0, qd, k, 0, kd, S, sd, Nq, Nk, d, nbh, heads, alpha=scale, out_f32=True)
-        self.f(ops.softmax_fwd, S, P, nbh * Nq, Nk)
-        self.f(ops.bmm, P, 0, pd, v, 1, kd, out.data, od, Nq, d, Nk, nbh, heads)
+        lse = self.buf(B * heads, Nq, dtype=torch.float32)
+        self.f(ops.attn_fwd, q, k, v, out.data, lse, B, heads, Nq, Nk, scale)
+        self.gemm_flops += 4 * B * heads * Nq * Nk * d
+        need = self.ctx.lib.sd2_attn_bwd_ws_bytes(B, heads, Nq)
+        if self.attn_ws is None or self.attn_ws.numel() < need:
+            self.attn_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
 
         def bwd():
             assert out.gw
@@ -439,16 +422,8 @@ class Engine:
             dq = qn.grad[:, q_col:q_col + C]
             dk = kvn.grad[:, k_col:k_col + C]
             dv = kvn.grad[:, v_col:v_col + C]
-            dqd = (ldq, d, Nq * ldq)
-            dkd = (ldk, d, Nk * ldk)
-            dOd = (d, Nq, C, d, Nq * C)
-
-            dP = S  # the score scratch is free again in backward
-            self.b(ops.bmm, dO, 0, dOd, v, 0, kd, dP, sd, Nq, Nk, d, nbh, heads, out_f32=True)
-            self.b(ops.softmax_bwd, P, dP, dS, nbh * Nq, Nk, scale)
-            self.b(ops.bmm, dS, 0, pd, k, 1, kd, dq, dqd, Nq, d, Nk, nbh, heads)
-            self.b(ops.bmm, dS, 1, pd, q, 1, qd, dk, dkd, Nk, d, Nq, nbh, heads)
-            self.b(ops.bmm, P, 1, pd, dO, 1, dOd, dv, dkd, Nk, d, Nq, nbh, heads)
+            self.b(ops.attn_bwd, q, k, v, out.data, dO, lse, dq, dk, dv, self.attn_ws, B, heads, Nq, Nk, scale)
+            self.gemm_flops += 10 * B * heads * Nq * Nk * d
             qn.gw = kvn.gw = True
 
         self._bwd_builders.append(bwd)

@@ -106,7 +106,12 @@ def test_loss_backward_scale_and_metrics():
     out = model(batch)
     model.loss(out, batch).backward()
     n = 'mid_block.resnets.0.conv1.weight'
-    assert torch.allclose(4 * g_q[n], model.unet.get_parameter(n).grad, rtol=3e-2, atol=1e-6)
+    # (the fused attention backward sums dQ over key tiles with fp32 reduce-adds in arrival order, so two runs differ by
+    # bf16 rounding noise: compare direction and magnitude rather than element by element)
+    g1 = model.unet.get_parameter(n).grad.flatten().float()
+    g4 = 4 * g_q[n].flatten().float()
+    assert F.cosine_similarity(g4, g1, dim=0).item() > 0.9995
+    assert abs(g4.norm().item() / g1.norm().item() - 1.0) < 1e-2
     # train metric path: eval_forward returns outputs unchanged, update_metric accumulates the same MSE
     assert model.eval_forward(batch, out) is out
     metric = model.get_metrics(is_train=True)['MeanSquaredError']
