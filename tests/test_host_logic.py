@@ -87,7 +87,7 @@ def test_schedule_builds_and_covers_every_parameter(dry, cfg, B, R):
     eng.run_forward()
     eng.run_backward()
     calls = eng.ctx.lib.calls
-    assert calls['sd2_groupnorm_fwd'] == 61 and calls['sd2_layernorm_fwd'] == 48 and calls['sd2_softmax_fwd'] == 32
+    assert calls['sd2_groupnorm_fwd'] == 61 and calls['sd2_layernorm_fwd'] == 48 and calls['sd2_attn_fwd'] == 32 and calls['sd2_attn_bwd'] == 32
     # buckets tile the arena exactly, in completion order
     lo = sorted(b[0] for b in eng.buckets)
     hi = sorted(b[1] for b in eng.buckets)

@@ -32,8 +32,14 @@ def sig(p):
         s = f'B{a[2]} {a[3]}x{a[4]} w{shp(a[5])}'
         fl = 2 * a[2] * a[3] * a[4] * a[5].shape[1] * a[5].shape[2] * 9
     elif name == 'bmm':
-        s = f'M{a[9]} N{a[10]} K{a[11]} b{a[12]} amn{a[1]} bmn{a[4]}'
-        fl = 2 * a[9] * a[10] * a[11] * a[12]
+        s = f'M{a[8]} N{a[9]} K{a[10]} b{a[11]} amn{a[1]} bmn{a[4]}'
+        fl = 2 * a[8] * a[9] * a[10] * a[11]
+    elif name == 'attn_fwd':  # (q, k, v, o, lse, B, heads, Nq, Nk, scale)
+        s = f'B{a[5]} h{a[6]} Nq{a[7]} Nk{a[8]}'
+        fl = 4 * a[5] * a[6] * a[7] * a[8] * 64
+    elif name == 'attn_bwd':  # (q, k, v, o, do, lse, dq, dk, dv, ws, B, heads, Nq, Nk, scale)
+        s = f'B{a[10]} h{a[11]} Nq{a[12]} Nk{a[13]}'
+        fl = 10 * a[10] * a[11] * a[12] * a[13] * 64
     else:
         s = ' '.join(shp(t) for t in a[:3] if torch.is_tensor(t))
         fl = 0
@@ -57,9 +63,14 @@ def main(B=16, R=32, out=None):
     for phase, lst in (('fwd', eng.fwd), ('bwd', eng.bwd)):
         for p in lst:
             p()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    p()
+            g.replay()
             e0.record()
-            for _ in range(reps):
-                p()
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / reps
@@ -69,7 +80,7 @@ def main(B=16, R=32, out=None):
             agg[k][1] += us
             agg[k][2] += fl
             total += us
-    lines = [f'B={B} latent={R}: sum of isolated op times {total / 1e3:.2f} ms (each op replayed {reps}x back to back: warm L2)', '',
+    lines = [f'B={B} latent={R}: sum of isolated op times {total / 1e3:.2f} ms (each op captured {reps}x in a CUDA graph and replayed: no host launch cost, warm L2)', '',
              '| phase | op | shape | n | total us | share | TFLOP/s |', '|---|---|---|---:|---:|---:|---:|']
     for (phase, name, s), (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         tf = f'{fl / us / 1e6:.0f}' if fl else ''
