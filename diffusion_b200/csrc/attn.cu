@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  pdl_grid_sync();
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 // D[bh][i] = sum_d O[i][d] dO[i][d]; 8 lanes per (row, head): 16-byte loads, shuffle reduce.
 __global__ void attn_dot_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o, long long lddo,
                                 float* __restrict__ dvec, int B, int heads, int Nq) {
+  pdl_grid_sync();
   const long long total = (long long)B * Nq * heads * 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float acc = 0.f;
@@ -301,6 +303,7 @@ __global__ void attn_dot_kernel(const bf16* __restrict__ o, long long ldo, const
 // dst[r][0..cols) bf16 (row stride ldd) = src[r][0..cols) fp32 (dense)
 __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long ldd, long long rows,
                                        int cols) {
+  pdl_grid_sync();
   const int V = cols / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384;
+  pdl_grid_sync();
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -647,7 +651,8 @@ int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_fwd attr: ") + cudaGetErrorString(e));
     attr = true;
   }
-  attn_fwd_kernel<<<dim3((Nq + 127) / 128, heads, B), AT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  cudaError_t le = launch_k(attn_fwd_kernel, dim3((Nq + 127) / 128, heads, B), dim3(AT_THREADS), smem, stream, tmQ, tmK, tmV, p);
+  if (le != cudaSuccess) return fail(ctx, std::string("sd2_attn_fwd launch: ") + cudaGetErrorString(le));
   return check_launch(ctx, "attn_fwd");
 }
 
@@ -687,8 +692,8 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.dv = reinterpret_cast<bf16*>(dv);
   p.lddv = lddv;
   const long long nd = (long long)B * Nq * heads * 8;
-  attn_dot_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(o), ldo,
-                                                                    reinterpret_cast<const bf16*>(d_o), lddo, dvec, B, heads, Nq);
+  launch_k(attn_dot_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(o), ldo,
+           reinterpret_cast<const bf16*>(d_o), lddo, dvec, B, heads, Nq);
   cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * Nq * C * 4, stream);
   if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
   const size_t smem = 10 * AT_TILE + 8 * 4096 + 4 * 128 * 4 + 13 * 8 + 16 + 1024;
@@ -699,8 +704,8 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
     attr = true;
   }
   attn_bwd_kernel<<<dim3((Nk + 127) / 128, heads, B), AT_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
-  cast2d_f32_bf16_kernel<<<grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(
-      dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
+  launch_k(cast2d_f32_bf16_kernel, dim3(grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream,
+           (const float*)dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
   return check_launch(ctx, "attn_bwd", 3);
 }
 

@@ -187,6 +187,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel calls pdl_grid_sync() before it touches global memory written by earlier kernels: it blocks until
+// the preceding grid in the stream has completed and flushed (no-op when launched without the attribute), then lets
+// the NEXT grid start launching, so that its launch latency and prologue (barrier init, TMEM alloc, descriptor
+// prefetch) overlap this grid's execution.  Everything a kernel does before this call must be input-independent.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

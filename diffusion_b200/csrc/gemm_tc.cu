@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // everything above is input-independent and overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -438,6 +439,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
                                        const float* __restrict__ bias, const float* __restrict__ rowbias,
                                        int rows_per_group, long long ld_rowbias, const bf16* __restrict__ residual,
                                        long long ldr, void* __restrict__ out, long long ldo, int out_f32) {
+  pdl_grid_sync();
   const long long nvec = M * (N / 8);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / (N / 8);
@@ -489,8 +491,7 @@ static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, tmO, p, stages);
-  return cudaGetLastError();
+  return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmO, p, stages);
 }
 
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
@@ -517,9 +518,8 @@ cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int
   int blocks = (int)((nvec + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(ws, splits, M, N, alpha, bias, rowbias, rows_per_group, ld_rowbias,
-                                                     residual, ldr, out, ldo, out_f32);
-  return cudaGetLastError();
+  return launch_k(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, ws, splits, M, N, alpha, bias, rowbias,
+                  rows_per_group, ld_rowbias, residual, ldr, out, ldo, out_f32);
 }
 
 }  // namespace sd2

@@ -5,7 +5,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <string>
+#include <utility>
 
 #include "../../include/sd2b200.h"
 
@@ -44,6 +48,32 @@ cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int N, float alpha, const float* bias,
                                    const float* rowbias, int rows_per_group, long long ld_rowbias, const bf16* residual,
                                    long long ldr, void* out, long long ldo, int out_f32, cudaStream_t stream);
+
+// Kernel launch with the programmatic-stream-serialization attribute (see pdl_grid_sync in common.cuh).
+// SD2_NO_PDL=1 in the environment launches plainly (debugging aid).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SD2_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(std::forward<A>(args))...);
+}
 
 inline int fail(sd2_ctx* ctx, const std::string& msg) {
   if (ctx) ctx->err = msg;

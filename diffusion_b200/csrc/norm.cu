@@ -51,6 +51,7 @@ __device__ __forceinline__ void gn_block_reduce(float* sm, const float* a, const
 // grid (P, B). Partial (sum, sumsq) per group over this block's pixel chunk -> ws[b][p][G][2]
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ ws,
                                                               int HW, int C, int G) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // [R][C][2] + [C][2]
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int V = C / 8, R = GN_THREADS / V;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
                                                               bf16* __restrict__ y, long long ldy, float* __restrict__ stats,
                                                               const float* __restrict__ ws, int HW, int C, int G, float eps,
                                                               int silu) {
+  pdl_grid_sync();
   __shared__ float s_mean[64], s_rstd[64];
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int cpg = C / G;
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ stats, float* __restrict__ ws, int HW,
                                                                   int C, int G, int silu) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // [R][C][2] + [C][2]
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int V = C / 8, R = GN_THREADS / V, cpg = C / G;
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ gamma,
                                                             float* __restrict__ gstat, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int B, int P, int C, int G) {
+  pdl_grid_sync();
   extern __shared__ float T[];  // [B][cpg][2]
   const int g = blockIdx.x, cpg = C / G;
   for (int idx = threadIdx.x; idx < B * cpg; idx += blockDim.x) {
@@ -242,6 +246,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __
                                                                   const bf16* __restrict__ dx_add, long long ldadd,
                                                                   bf16* __restrict__ dx, long long lddx, int HW, int C, int G,
                                                                   int silu) {
+  pdl_grid_sync();
   __shared__ float s_ds[64], s_db[64];
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int cpg = C / G;
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __
 // grid (ceil(C/32)), block (32 channels, 8 partial lanes): coalesced float2 reads, smem tree over the 8 lanes.
 __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_grid_sync();
   __shared__ float sm[8][32][2];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -320,32 +326,50 @@ __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __
 // ------------------------------------------------------------------------------------------------ LayerNorm
 static constexpr int LN_MAXV = 5;  // up to 5 x 32 lanes x 8 channels = 1280
 
-// one warp per row
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+// One warp per row, NV = ceil(C / 256) 16-byte vectors per lane (exactly unrolled).  The next row's vectors are
+// fetched (raw bf16, 4 registers each) before the current row's reductions, so HBM latency overlaps the shuffles.
+template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, bf16* __restrict__ y,
                                                      float* __restrict__ stats, long long rows, int C, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int V = C / 8;
+  const float invC = 1.f / (float)C;
+  uint4 nx[NV];
+  if (warp < rows) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (lane + 32 * j < V) nx[j] = *reinterpret_cast<const uint4*>(x + warp * C + (lane + 32 * j) * 8);
+  }
   for (long long row = warp; row < rows; row += nwarps) {
-    float f[LN_MAXV][8];
+    float f[NV][8];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAXV; ++j) {
-      const int v = lane + 32 * j;
-      if (v < V) {
-        load8(x + row * C + v * 8, f[j]);
+    for (int j = 0; j < NV; ++j) {
+      if (lane + 32 * j < V) {
+        unpack8(nx[j], f[j]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += f[j][e];
       }
     }
-    const float mean = warp_sum(s) / (float)C;
+    if (row + nwarps < rows) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (lane + 32 * j < V) nx[j] = *reinterpret_cast<const uint4*>(x + (row + nwarps) * C + (lane + 32 * j) * 8);
+    }
+    const float mean = warp_sum(s) * invC;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAXV; ++j) {
-      const int v = lane + 32 * j;
-      if (v < V) {
+    for (int j = 0; j < NV; ++j) {
+      if (lane + 32 * j < V) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float d = f[j][e] - mean;
@@ -353,18 +377,19 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    if (lane == 0) {
-      stats[row * 2] = mean;
-      stats[row * 2 + 1] = rstd;
-    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
 #pragma unroll
-    for (int j = 0; j < LN_MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
       const int v = lane + 32 * j;
       if (v < V) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (f[j][e] - mean) * rstd * gamma[v * 8 + e] + beta[v * 8 + e];
+        for (int e = 0; e < 8; ++e) o[e] = (f[j][e] - mean) * rstd * gv[e] + bv[e];
         store8(y + row * C + v * 8, o);
       }
     }
@@ -372,37 +397,59 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 }
 
 // one warp per row; per-block partial (dbeta, dgamma) -> ws[block][C][2]
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* __restrict__ stats,
-                                                     const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
-                                                     float* __restrict__ ws, long long rows, int C) {
+template <int NV>
+__global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ stats,
+                                                                        const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
+                                                                        float* __restrict__ ws, long long rows, int C) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // [C][2]
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int V = C / 8;
+  const float invC = 1.f / (float)C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  float ag[LN_MAXV][8], ab[LN_MAXV][8];
+  float ag[NV][8], ab[NV][8];
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j)
+  for (int j = 0; j < NV; ++j)
 #pragma unroll
     for (int e = 0; e < 8; ++e) ag[j][e] = ab[j][e] = 0.f;
+  uint4 nx[NV], nd[NV], na[NV];
+  float2 nst = make_float2(0.f, 0.f);
+  if (warp < rows) {
+    nst = *reinterpret_cast<const float2*>(stats + warp * 2);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V) {
+        nx[j] = *reinterpret_cast<const uint4*>(x + warp * C + v * 8);
+        nd[j] = *reinterpret_cast<const uint4*>(dy + warp * C + v * 8);
+        if (dx_add) na[j] = *reinterpret_cast<const uint4*>(dx_add + warp * C + v * 8);
+      }
+    }
+  }
   for (long long row = warp; row < rows; row += nwarps) {
-    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
-    float xh[LN_MAXV][8], g[LN_MAXV][8];
+    const float mean = nst.x, rstd = nst.y;
+    float xh[NV][8], g[NV][8];
+    uint4 ca[NV];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
       const int v = lane + 32 * j;
       if (v < V) {
         float d[8];
-        load8(x + row * C + v * 8, xh[j]);
-        load8(dy + row * C + v * 8, d);
+        unpack8(nx[j], xh[j]);
+        unpack8(nd[j], d);
+        ca[j] = na[j];
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           xh[j][e] = (xh[j][e] - mean) * rstd;
-          g[j][e] = d[e] * gamma[v * 8 + e];
+          g[j][e] = d[e] * gv[e];
           c1 += g[j][e];
           c2 += g[j][e] * xh[j][e];
           ab[j][e] += d[e];
@@ -410,14 +457,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
         }
       }
     }
-    c1 = warp_sum(c1) / (float)C;
-    c2 = warp_sum(c2) / (float)C;
+    if (row + nwarps < rows) {  // next row's operands: in flight during the reductions below
+      const long long nr = row + nwarps;
+      nst = *reinterpret_cast<const float2*>(stats + nr * 2);
 #pragma unroll
-    for (int j = 0; j < LN_MAXV; ++j) {
+      for (int j = 0; j < NV; ++j) {
+        const int v = lane + 32 * j;
+        if (v < V) {
+          nx[j] = *reinterpret_cast<const uint4*>(x + nr * C + v * 8);
+          nd[j] = *reinterpret_cast<const uint4*>(dy + nr * C + v * 8);
+          if (dx_add) na[j] = *reinterpret_cast<const uint4*>(dx_add + nr * C + v * 8);
+        }
+      }
+    }
+    c1 = warp_sum(c1) * invC;
+    c2 = warp_sum(c2) * invC;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
       const int v = lane + 32 * j;
       if (v < V) {
         float o[8];
-        if (dx_add) load8(dx_add + row * C + v * 8, o);
+        if (dx_add) unpack8(ca[j], o);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float t = rstd * (g[j][e] - c1 - xh[j][e] * c2);
@@ -432,7 +492,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int wturn = 0; wturn < (int)(blockDim.x >> 5); ++wturn) {
     if ((int)(threadIdx.x >> 5) == wturn) {
 #pragma unroll
-      for (int j = 0; j < LN_MAXV; ++j) {
+      for (int j = 0; j < NV; ++j) {
         const int v = lane + 32 * j;
         if (v < V) {
 #pragma unroll
@@ -451,7 +511,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 
 static int ln_blocks(long long rows, int num_sms) {
   long long b = (rows + 7) / 8;
-  const long long cap = (long long)num_sms * 2;
+  const long long cap = (long long)num_sms * 4;  // sd2_layernorm_ws_floats is sized for 4 blocks per SM
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -471,8 +531,8 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const dim3 grid(gn_chunks(HW), B);
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
-  gn_stats_kernel<<<grid, GN_THREADS, red_smem, stream>>>(reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
-  gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, gamma, beta,
+  launch_k(gn_stats_kernel, dim3(grid), dim3(GN_THREADS), red_smem, stream, reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(x), ldx, gamma, beta,
                                                    reinterpret_cast<bf16*>(y), ldy, stats, ws, HW, C, G, eps, silu);
   return check_launch(ctx, "groupnorm_fwd", 2);
 }
@@ -488,10 +548,9 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
   const dim3 grid(P, B);
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
   float* gstat = ws + (long long)B * GN_MAXP * C * 2;
-  gn_bwd_stats_kernel<<<grid, GN_THREADS, red_smem, stream>>>(
-      reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws, HW, C, G, silu);
-  gn_bwd_reduce_kernel<<<G, 256, (size_t)B * (C / G) * 2 * sizeof(float), stream>>>(ws, gamma, gstat, dgamma, dbeta, B, P, C, G);
-  gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy), lddy,
+  launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(GN_THREADS), red_smem, stream, reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws, HW, C, G, silu);
+  launch_k(gn_bwd_reduce_kernel, dim3(G), dim3(256), (size_t)B * (C / G) * 2 * sizeof(float), stream, ws, gamma, gstat, dgamma, dbeta, B, P, C, G);
+  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(dy), lddy,
                                                        reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, gstat,
                                                        reinterpret_cast<const bf16*>(dx_add), ldadd,
                                                        reinterpret_cast<bf16*>(dx), lddx, HW, C, G, silu);
@@ -504,8 +563,12 @@ int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const flo
   if (C % 8 != 0 || C > LN_MAXV * 256) return fail(ctx, "sd2_layernorm_fwd: unsupported C");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int blocks = grid_for(rows * 32, 256, ctx->num_sms, 8);
-  ln_fwd_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), gamma, beta, reinterpret_cast<bf16*>(y), stats,
-                                            rows, C, eps);
+  const int nv = (C / 8 + 31) / 32;
+#define LN_FWD(NV)                                                                                                        \
+  launch_k(ln_fwd_kernel<NV>, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const bf16*>(x), gamma, beta,           \
+           reinterpret_cast<bf16*>(y), stats, rows, C, eps)
+  if (nv == 1) LN_FWD(1); else if (nv == 2) LN_FWD(2); else if (nv == 3) LN_FWD(3); else if (nv == 4) LN_FWD(4); else LN_FWD(5);
+#undef LN_FWD
   return check_launch(ctx, "layernorm_fwd");
 }
 
@@ -518,11 +581,14 @@ int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* 
   if (C % 8 != 0 || C > LN_MAXV * 256) return fail(ctx, "sd2_layernorm_bwd: unsupported C");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int blocks = ln_blocks(rows, ctx->num_sms);
-  ln_bwd_kernel<<<blocks, 256, 2 * C * sizeof(float), stream>>>(reinterpret_cast<const bf16*>(dy),
-                                                                reinterpret_cast<const bf16*>(x), gamma, stats,
-                                                                reinterpret_cast<const bf16*>(dx_add),
-                                                                reinterpret_cast<bf16*>(dx), ws, rows, C);
-  affine_grad_reduce_kernel<<<(C + 31) / 32, 256, 0, stream>>>(ws, blocks, C, dgamma, dbeta);
+  const int nv = (C / 8 + 31) / 32;
+#define LN_BWD(NV)                                                                                                        \
+  launch_k(ln_bwd_kernel<NV>, dim3(blocks), dim3(256), 2 * C * sizeof(float), stream, reinterpret_cast<const bf16*>(dy),   \
+           reinterpret_cast<const bf16*>(x), gamma, stats, reinterpret_cast<const bf16*>(dx_add),                          \
+           reinterpret_cast<bf16*>(dx), ws, rows, C)
+  if (nv == 1) LN_BWD(1); else if (nv == 2) LN_BWD(2); else if (nv == 3) LN_BWD(3); else if (nv == 4) LN_BWD(4); else LN_BWD(5);
+#undef LN_BWD
+  launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, ws, blocks, C, dgamma, dbeta);
   return check_launch(ctx, "layernorm_bwd", 2);
 }
 

@@ -27,6 +27,7 @@ __device__ __forceinline__ void st8(bf16* p, const float* v) {
 // zero-padded GEMM operand.
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long lds, bf16* __restrict__ P,
                                                           long long ldp, long long rows, int cols) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict__ P, long long ldp, const float* __restrict__ dP,
                                                           long long lddp, bf16* __restrict__ dS, long long ldds, long long rows,
                                                           int cols, float scale) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -70,6 +72,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 __global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int C) {
+  pdl_grid_sync();
   const int V = C / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -86,6 +89,7 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ 
 
 __global__ void geglu_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dy, bf16* __restrict__ dh, long long rows,
                                  int C) {
+  pdl_grid_sync();
   const int V = C / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -106,6 +110,7 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ h, const bf16* __restr
 }
 
 __global__ void silu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8) {
+  pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     ld8(x + i * 8, f);
@@ -115,6 +120,7 @@ __global__ void silu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
   }
 }
 __global__ void silu_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx, long long n8) {
+  pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8], d[8];
     ld8(x + i * 8, f);
@@ -129,6 +135,7 @@ __global__ void silu_bwd_kernel(const bf16* __restrict__ x, const bf16* __restri
 }
 __global__ void axpby_kernel(const bf16* __restrict__ a, float alpha, const bf16* __restrict__ b, float beta,
                              bf16* __restrict__ out, long long n8) {
+  pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8], g[8];
     ld8(a + i * 8, f);
@@ -142,6 +149,7 @@ __global__ void axpby_kernel(const bf16* __restrict__ a, float alpha, const bf16
 // ---------------------------------------------------------------------------------------------- layout
 __global__ void copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd,
                               long long rows, int cols, int accumulate) {
+  pdl_grid_sync();
   const int V = cols / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -162,6 +170,7 @@ __global__ void copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16*
 
 // y[b][2h+i][2w+j][c] = x[b][h][w][c]
 __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  pdl_grid_sync();
   const int V = C / 8;
   const long long n = (long long)B * 2 * H * 2 * W * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -177,6 +186,7 @@ __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, bf16* __restri
 }
 // dx[b][h][w][c] = sum_{i,j} dy[b][2h+i][2w+j][c]
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int H, int W, int C) {
+  pdl_grid_sync();
   const int V = C / 8;
   const long long n = (long long)B * H * W * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -201,6 +211,7 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restr
 }
 // planes[(h%2)*2 + (w%2)][b][h/2][w/2][c] <-> x[b][h][w][c]
 __global__ void phase_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int H, int W, int C, int merge) {
+  pdl_grid_sync();
   const int V = C / 8;
   const long long n = (long long)B * H * W * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -224,6 +235,7 @@ __global__ void phase_kernel(const bf16* __restrict__ src, bf16* __restrict__ ds
 // grid (ceil(N/64), groups, row_splits); block 256 = 8 column-vectors(8 ch) x 32 row lanes
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out,
                                                      long long ldo, long long rows_per_group, int N, int use_atomic) {
+  pdl_grid_sync();
   __shared__ float sm[32][65];
   const int cv = threadIdx.x % 8, rl = threadIdx.x / 8;
   const int n0 = blockIdx.x * 64 + cv * 8;
@@ -261,11 +273,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
+  pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------- casts
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_grid_sync();
   const long long n8 = n / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(src + i * 8), b = *reinterpret_cast<const float4*>(src + i * 8 + 4);
@@ -276,6 +290,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
   if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8 * 8)) dst[n8 * 8 + threadIdx.x] = __float2bfloat16_rn(src[n8 * 8 + threadIdx.x]);
 }
 __global__ void pad_cast_rows_kernel(const float* __restrict__ src, int cs, bf16* __restrict__ dst, int cd, long long rows) {
+  pdl_grid_sync();
   const long long n = rows * cd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cd;
@@ -285,6 +300,7 @@ __global__ void pad_cast_rows_kernel(const float* __restrict__ src, int cs, bf16
 }
 __global__ void unpad_accum_rows_kernel(const float* __restrict__ src, int cs, float* __restrict__ dst, int cd, long long rows,
                                         int accumulate) {
+  pdl_grid_sync();
   const long long n = rows * cd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cd;
@@ -317,6 +333,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) mse_head_kernel(const bf16* __restrict__ pred8, const T* __restrict__ noise,
                                                        T* __restrict__ pred_nchw, bf16* __restrict__ dpred8,
                                                        float* __restrict__ loss_acc, float gscale, int B, int HW) {
+  pdl_grid_sync();
   const long long npix = (long long)B * HW;
   const float k = gscale * 2.f / (float)(npix * 4);
   float local = 0.f;
@@ -360,14 +377,14 @@ int sd2_softmax_fwd(sd2_ctx* ctx, const float* S, long long lds, void* P, long l
                     sd2_stream stream_) {
   if (!ctx) return 1;
   SD2_STREAM;
-  softmax_fwd_kernel<<<grid_for(rows * 32, 256, ctx->num_sms, 16), 256, 0, stream>>>(S, lds, SD2_BFW(P), ldp, rows, cols);
+  launch_k(softmax_fwd_kernel, dim3(grid_for(rows * 32, 256, ctx->num_sms, 16)), dim3(256), 0, stream, S, lds, SD2_BFW(P), ldp, rows, cols);
   return check_launch(ctx, "softmax_fwd");
 }
 int sd2_softmax_bwd(sd2_ctx* ctx, const void* P, long long ldp, const float* dP, long long lddp, void* dS,
                     long long ldds, long long rows, int cols, float scale, sd2_stream stream_) {
   if (!ctx) return 1;
   SD2_STREAM;
-  softmax_bwd_kernel<<<grid_for(rows * 32, 256, ctx->num_sms, 16), 256, 0, stream>>>(SD2_BF(P), ldp, dP, lddp, SD2_BFW(dS),
+  launch_k(softmax_bwd_kernel, dim3(grid_for(rows * 32, 256, ctx->num_sms, 16)), dim3(256), 0, stream, SD2_BF(P), ldp, dP, lddp, SD2_BFW(dS),
                                                                                     ldds, rows, cols, scale);
   return check_launch(ctx, "softmax_bwd");
 }
@@ -375,28 +392,28 @@ int sd2_geglu_fwd(sd2_ctx* ctx, const void* h, void* y, long long rows, int C, s
   if (!ctx) return 1;
   if (C % 8) return fail(ctx, "geglu: C % 8");
   SD2_STREAM;
-  geglu_fwd_kernel<<<grid_for(rows * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(h), SD2_BFW(y), rows, C);
+  launch_k(geglu_fwd_kernel, dim3(grid_for(rows * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(h), SD2_BFW(y), rows, C);
   return check_launch(ctx, "geglu_fwd");
 }
 int sd2_geglu_bwd(sd2_ctx* ctx, const void* h, const void* dy, void* dh, long long rows, int C, sd2_stream stream_) {
   if (!ctx) return 1;
   if (C % 8) return fail(ctx, "geglu: C % 8");
   SD2_STREAM;
-  geglu_bwd_kernel<<<grid_for(rows * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(h), SD2_BF(dy), SD2_BFW(dh), rows, C);
+  launch_k(geglu_bwd_kernel, dim3(grid_for(rows * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(h), SD2_BF(dy), SD2_BFW(dh), rows, C);
   return check_launch(ctx, "geglu_bwd");
 }
 int sd2_silu_fwd(sd2_ctx* ctx, const void* x, void* y, long long n, sd2_stream stream_) {
   if (!ctx) return 1;
   if (n % 8) return fail(ctx, "silu: n % 8");
   SD2_STREAM;
-  silu_fwd_kernel<<<grid_for(n / 8, 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(x), SD2_BFW(y), n / 8);
+  launch_k(silu_fwd_kernel, dim3(grid_for(n / 8, 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(x), SD2_BFW(y), n / 8);
   return check_launch(ctx, "silu_fwd");
 }
 int sd2_silu_bwd(sd2_ctx* ctx, const void* x, const void* dy, void* dx, long long n, sd2_stream stream_) {
   if (!ctx) return 1;
   if (n % 8) return fail(ctx, "silu: n % 8");
   SD2_STREAM;
-  silu_bwd_kernel<<<grid_for(n / 8, 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(x), SD2_BF(dy), SD2_BFW(dx), n / 8);
+  launch_k(silu_bwd_kernel, dim3(grid_for(n / 8, 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(x), SD2_BF(dy), SD2_BFW(dx), n / 8);
   return check_launch(ctx, "silu_bwd");
 }
 int sd2_axpby(sd2_ctx* ctx, const void* a, float alpha, const void* b, float beta, void* out, long long n,
@@ -404,7 +421,7 @@ int sd2_axpby(sd2_ctx* ctx, const void* a, float alpha, const void* b, float bet
   if (!ctx) return 1;
   if (n % 8) return fail(ctx, "axpby: n % 8");
   SD2_STREAM;
-  axpby_kernel<<<grid_for(n / 8, 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(a), alpha, SD2_BF(b), beta, SD2_BFW(out), n / 8);
+  launch_k(axpby_kernel, dim3(grid_for(n / 8, 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(a), alpha, SD2_BF(b), beta, SD2_BFW(out), n / 8);
   return check_launch(ctx, "axpby");
 }
 int sd2_copy2d(sd2_ctx* ctx, const void* src, long long lds, void* dst, long long ldd, long long rows, int cols,
@@ -412,7 +429,7 @@ int sd2_copy2d(sd2_ctx* ctx, const void* src, long long lds, void* dst, long lon
   if (!ctx) return 1;
   if (cols % 8 || lds % 8 || ldd % 8) return fail(ctx, "copy2d: cols/ld % 8");
   SD2_STREAM;
-  copy2d_kernel<<<grid_for(rows * (cols / 8), 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(src), lds, SD2_BFW(dst), ldd, rows,
+  launch_k(copy2d_kernel, dim3(grid_for(rows * (cols / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(src), lds, SD2_BFW(dst), ldd, rows,
                                                                                   cols, accumulate);
   return check_launch(ctx, "copy2d");
 }
@@ -420,15 +437,14 @@ int sd2_upsample2x_fwd(sd2_ctx* ctx, const void* x, void* y, int B, int H, int W
   if (!ctx) return 1;
   if (C % 8) return fail(ctx, "upsample: C % 8");
   SD2_STREAM;
-  upsample2x_fwd_kernel<<<grid_for((long long)B * 4 * H * W * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(
-      SD2_BF(x), SD2_BFW(y), B, H, W, C);
+  launch_k(upsample2x_fwd_kernel, dim3(grid_for((long long)B * 4 * H * W * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(x), SD2_BFW(y), B, H, W, C);
   return check_launch(ctx, "upsample2x_fwd");
 }
 int sd2_upsample2x_bwd(sd2_ctx* ctx, const void* dy, void* dx, int B, int H, int W, int C, sd2_stream stream_) {
   if (!ctx) return 1;
   if (C % 8) return fail(ctx, "upsample: C % 8");
   SD2_STREAM;
-  upsample2x_bwd_kernel<<<grid_for((long long)B * H * W * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(dy), SD2_BFW(dx),
+  launch_k(upsample2x_bwd_kernel, dim3(grid_for((long long)B * H * W * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(dy), SD2_BFW(dx),
                                                                                                        B, H, W, C);
   return check_launch(ctx, "upsample2x_bwd");
 }
@@ -436,7 +452,7 @@ int sd2_phase_split(sd2_ctx* ctx, const void* x, void* planes, int B, int H, int
   if (!ctx) return 1;
   if (C % 8 || H % 2 || W % 2) return fail(ctx, "phase_split: C % 8 or odd H/W");
   SD2_STREAM;
-  phase_kernel<<<grid_for((long long)B * H * W * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(x), SD2_BFW(planes), B, H,
+  launch_k(phase_kernel, dim3(grid_for((long long)B * H * W * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(x), SD2_BFW(planes), B, H,
                                                                                               W, C, 0);
   return check_launch(ctx, "phase_split");
 }
@@ -444,7 +460,7 @@ int sd2_phase_merge(sd2_ctx* ctx, const void* planes, void* x, int B, int H, int
   if (!ctx) return 1;
   if (C % 8 || H % 2 || W % 2) return fail(ctx, "phase_merge: C % 8 or odd H/W");
   SD2_STREAM;
-  phase_kernel<<<grid_for((long long)B * H * W * (C / 8), 256, ctx->num_sms), 256, 0, stream>>>(SD2_BF(planes), SD2_BFW(x), B, H,
+  launch_k(phase_kernel, dim3(grid_for((long long)B * H * W * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream, SD2_BF(planes), SD2_BFW(x), B, H,
                                                                                               W, C, 1);
   return check_launch(ctx, "phase_merge");
 }
@@ -462,32 +478,32 @@ int sd2_colsum(sd2_ctx* ctx, const void* x, long long ldx, float* out, long long
   if (!accumulate && splits > 1) {
     // zero the destination rows first so that the split partials can be combined with atomics
     for (int g = 0; g < groups; ++g) {
-      fill_f32_kernel<<<grid_for(N, 256, ctx->num_sms), 256, 0, stream>>>(out + (long long)g * ldo, N, 0.f);
+      launch_k(fill_f32_kernel, dim3(grid_for(N, 256, ctx->num_sms)), dim3(256), 0, stream, out + (long long)g * ldo, N, 0.f);
       ++launches;
     }
   }
   const int use_atomic = (accumulate || splits > 1) ? 1 : 0;
-  colsum_kernel<<<dim3(nblk, groups, (unsigned)splits), 256, 0, stream>>>(SD2_BF(x), ldx, out, ldo, rows_per_group, N, use_atomic);
+  launch_k(colsum_kernel, dim3(dim3(nblk, groups, (unsigned)splits)), dim3(256), 0, stream, SD2_BF(x), ldx, out, ldo, rows_per_group, N, use_atomic);
   return check_launch(ctx, "colsum", launches);
 }
 int sd2_cast_f32_to_bf16(sd2_ctx* ctx, const float* src, void* dst, long long n, sd2_stream stream_) {
   if (!ctx) return 1;
   SD2_STREAM;
-  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256, ctx->num_sms), 256, 0, stream>>>(src, SD2_BFW(dst), n);
+  launch_k(cast_f32_bf16_kernel, dim3(grid_for(n / 8 + 1, 256, ctx->num_sms)), dim3(256), 0, stream, src, SD2_BFW(dst), n);
   return check_launch(ctx, "cast_f32_to_bf16");
 }
 int sd2_pad_cast_rows(sd2_ctx* ctx, const float* src, int cols_src, void* dst, int cols_dst, long long rows,
                       sd2_stream stream_) {
   if (!ctx) return 1;
   SD2_STREAM;
-  pad_cast_rows_kernel<<<grid_for(rows * cols_dst, 256, ctx->num_sms), 256, 0, stream>>>(src, cols_src, SD2_BFW(dst), cols_dst, rows);
+  launch_k(pad_cast_rows_kernel, dim3(grid_for(rows * cols_dst, 256, ctx->num_sms)), dim3(256), 0, stream, src, cols_src, SD2_BFW(dst), cols_dst, rows);
   return check_launch(ctx, "pad_cast_rows");
 }
 int sd2_unpad_accum_rows(sd2_ctx* ctx, const float* src, int cols_src, float* dst, int cols_dst, long long rows,
                          int accumulate, sd2_stream stream_) {
   if (!ctx) return 1;
   SD2_STREAM;
-  unpad_accum_rows_kernel<<<grid_for(rows * cols_dst, 256, ctx->num_sms), 256, 0, stream>>>(src, cols_src, dst, cols_dst, rows,
+  launch_k(unpad_accum_rows_kernel, dim3(grid_for(rows * cols_dst, 256, ctx->num_sms)), dim3(256), 0, stream, src, cols_src, dst, cols_dst, rows,
                                                                                           accumulate);
   return check_launch(ctx, "unpad_accum_rows");
 }
@@ -497,7 +513,7 @@ int sd2_mse_head(sd2_ctx* ctx, const void* pred_nhwc8, const void* noise, int no
   SD2_STREAM;
   const int blocks = grid_for((long long)B * H * W, 256, ctx->num_sms, 4);
 #define MSE_LAUNCH(T)                                                                                                  \
-  mse_head_kernel<T><<<blocks, 256, 0, stream>>>(SD2_BF(pred_nhwc8), reinterpret_cast<const T*>(noise),                 \
+  launch_k(mse_head_kernel<T>, dim3(blocks), dim3(256), 0, stream, SD2_BF(pred_nhwc8), reinterpret_cast<const T*>(noise),                 \
                                                  reinterpret_cast<T*>(pred_nchw), SD2_BFW(dpred_nhwc8), loss_acc, gscale, B, H * W)
   if (noise_dtype == SD2_DT_F32) {
     MSE_LAUNCH(float);
@@ -523,6 +539,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                     float* __restrict__ v, bf16* __restrict__ p16, long long n, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bc1, float rsqrt_bc2,
                                                     float gscale, int zero_grad) {
+  pdl_grid_sync();
   const long long n4 = n / 4;
   const float step_size = lr / bc1, decay = 1.f - lr * wd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -581,8 +598,7 @@ extern "C" int sd2_adamw_step(sd2_ctx* ctx, float* param, float* grad, float* ex
     return fail(ctx, "sd2_adamw_step: buffers must be 16-byte aligned");
   SD2_STREAM;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  adamw_kernel<<<grid_for(n / 4 + 1, 256, ctx->num_sms, 16), 256, 0, stream>>>(
-      param, grad, exp_avg, exp_avg_sq, SD2_BFW(param_bf16), n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+  launch_k(adamw_kernel, dim3(grid_for(n / 4 + 1, 256, ctx->num_sms, 16)), dim3(256), 0, stream, param, grad, exp_avg, exp_avg_sq, SD2_BFW(param_bf16), n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
       (float)(1.0 / sqrt(bc2)), grad_scale, zero_grad);
   return check_launch(ctx, "adamw_step");
 }

@@ -140,9 +140,14 @@ def test_fused_adamw_arena_path_matches_torch_adamw():
     assert any(k.startswith('arena') for k in opt_a.state if isinstance(k, str)), 'arena path was not taken'
     assert arena.grads_bound() and float(arena.g32.abs().max()) == 0.0
     assert torch.equal(arena.p16, arena.p32.to(torch.bfloat16)), 'bf16 shadow is stale'
-    worst = 0.0
+    worst, total, count = 0.0, 0.0, 0
     for (n, pa), (_, pb) in zip(model_a.unet.named_parameters(), model_b.unet.named_parameters()):
-        worst = max(worst, (pa - pb).abs().max().item())
+        d = (pa - pb).abs()
+        worst = max(worst, d.max().item())
+        total += d.sum().item()
+        count += d.numel()
     # both models see bf16-kernel gradients with non-deterministic fp32 reduce-add order: Adam's normalised update
-    # amplifies tiny gradient differences where |g| ~ eps, hence a loose absolute bound of a few learning rates
-    assert worst < 5e-3, worst
+    # turns a sign flip of a near-zero gradient into a +-lr step, so single elements may differ by up to
+    # 2 * steps * lr = 6e-3, while the bulk of the parameters must agree closely
+    assert worst <= 6.5e-3, worst
+    assert total / count < 1e-4, total / count
