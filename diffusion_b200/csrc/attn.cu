@@ -22,7 +22,6 @@
 
 namespace sd2 {
 
-static constexpr int AT_THREADS = 192;
 static constexpr int AT_TILE = 128 * 64 * 2;  // one [128 rows][64 bf16] tile, SWIZZLE_128B: 16 KB
 
 struct AttnParams {
@@ -49,25 +48,54 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ================================================================================================ forward
-__global__ void __launch_bounds__(AT_THREADS, 2)
+static constexpr int AT_FWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
+
+// exp2(S c2 - m c2) of one 32-column chunk -> bf16 -> swizzled smem; returns the fp32 row sum of the chunk
+template <bool MASKED>
+__device__ __forceinline__ float attn_exp_chunk(const uint32_t* rs, float c2, float mc, int col0, int nvalid, uint8_t* prow,
+                                                int c, int r) {
+  float sum = 0.f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float pv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float x = ex2(fmaf(__uint_as_float(rs[g * 8 + e]), c2, -mc));
+      if (MASKED && col0 + g * 8 + e >= nvalid) x = 0.f;
+      pv[e] = x;
+      sum += x;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
+    u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
+    *reinterpret_cast<uint4*>(prow + (((c * 4 + g) ^ (r & 7)) << 4)) = u;
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(AT_FWD_THREADS, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + AT_TILE;      // stage s: K at s*2*AT_TILE, V at s*2*AT_TILE + AT_TILE
-  uint8_t* sP = sKV + 4 * AT_TILE;  // one 64-column half of P: [128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_TILE);
+  uint8_t* sK = sQ + AT_TILE;      // [2] K tiles (ring)
+  uint8_t* sV = sK + 2 * AT_TILE;  // one V tile (consumed late in a step, so a single buffer suffices)
+  uint8_t* sP = sV + AT_TILE;      // [2] the two 64-column halves of P: [128 rows][128 B] each
+  float* xch = reinterpret_cast<float*>(sP + 2 * AT_TILE);  // [2 parities][2 halves][128 rows] row-max / row-sum exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 512);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* p_empty = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint64_t* o_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* s_empty = bars + 8;
+  uint64_t* p_full = bars + 9;    // [2]
+  uint64_t* p_empty = bars + 11;  // [2]
+  uint64_t* o_full = bars + 13;
+  uint64_t* o_empty = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -82,15 +110,17 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&kv_full[s], 1);
-        mbar_init(&kv_empty[s], 1);
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&p_full[s], 4);
+        mbar_init(&p_empty[s], 1);
       }
+      mbar_init(v_full, 1);
+      mbar_init(v_empty, 1);
       mbar_init(s_full, 1);
-      mbar_init(s_empty, 4);
-      mbar_init(p_full, 4);
-      mbar_init(p_empty, 1);
+      mbar_init(s_empty, 8);
       mbar_init(o_full, 1);
-      mbar_init(o_empty, 4);
+      mbar_init(o_empty, 8);
       fence_mbar_init();
     }
     __syncwarp();
@@ -113,11 +143,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     __syncwarp();
     for (int j = 0; j < nkt; ++j) {
       const int s = j & 1;
-      mbar_wait(&kv_empty[s], (uint32_t)((j >> 1) & 1) ^ 1u);
+      mbar_wait(&k_empty[s], (uint32_t)((j >> 1) & 1) ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE);
-        tma_load_4d(sKV + s * 2 * AT_TILE, &tmK, &kv_full[s], 0, j * 128, h, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE + AT_TILE, &tmV, &kv_full[s], 0, j * 128, h, b);
+        mbar_arrive_expect_tx(&k_full[s], AT_TILE);
+        tma_load_4d(sK + s * AT_TILE, &tmK, &k_full[s], 0, j * 128, h, b);
+      }
+      __syncwarp();
+      mbar_wait(v_empty, (uint32_t)(j & 1) ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(v_full, AT_TILE);
+        tma_load_4d(sV, &tmV, v_full, 0, j * 128, h, b);
       }
       __syncwarp();
     }
@@ -127,141 +162,148 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
     const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t dP0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
-    const uint64_t dK0 = umma_desc_sw128(smem_u32(sKV), 16, 1024);                 // stage 0 K, K-major
-    const uint64_t dV0 = umma_desc_sw128(smem_u32(sKV + AT_TILE), 8192, 1024);     // stage 0 V, MN-major
-    constexpr uint64_t STAGE = (2 * AT_TILE) >> 4;
+    const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 16, 1024);   // K-major
+    const uint64_t dV0 = umma_desc_sw128(smem_u32(sV), 8192, 1024); // MN-major
+    constexpr uint64_t TS = AT_TILE >> 4;
     mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
+    mbar_wait(&k_full[0], 0);
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tS, dQ0 + 2 * ks, dK0 + 2 * ks, idesc_s, ks != 0 ? 1u : 0u);
       tc_commit(s_full);
+      tc_commit(&k_empty[0]);
     }
     __syncwarp();
     for (int j = 0; j < nkt; ++j) {
-      const uint64_t dVs = dV0 + (uint64_t)(j & 1) * STAGE;
+      if (j + 1 < nkt) {  // next score tile as soon as S_j has been read: runs under the exp work of tile j
+        mbar_wait(s_empty, (uint32_t)(j & 1));
+        mbar_wait(&k_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dKs = dK0 + (uint64_t)((j + 1) & 1) * TS;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tS, dQ0 + 2 * ks, dKs + 2 * ks, idesc_s, ks != 0 ? 1u : 0u);
+          tc_commit(s_full);
+          tc_commit(&k_empty[(j + 1) & 1]);
+        }
+        __syncwarp();
+      }
+      mbar_wait(v_full, (uint32_t)(j & 1));
       if (j > 0) mbar_wait(o_empty, (uint32_t)((j - 1) & 1));  // softmax warps have read O_{j-1}
 #pragma unroll 1
       for (int hlf = 0; hlf < 2; ++hlf) {
-        mbar_wait(p_full, (uint32_t)hlf);  // completion #(2j + hlf)
+        mbar_wait(&p_full[hlf], (uint32_t)(j & 1));
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            tc_mma_bf16(tO, dP0 + 2 * ks, dVs + (uint64_t)(hlf * 4 + ks) * 128, idesc_o, (hlf | ks) != 0 ? 1u : 0u);
-          tc_commit(p_empty);
+            tc_mma_bf16(tO, dP0 + (uint64_t)hlf * TS + 2 * ks, dV0 + (uint64_t)(hlf * 4 + ks) * 128, idesc_o,
+                        (hlf | ks) != 0 ? 1u : 0u);
+          tc_commit(&p_empty[hlf]);
           if (hlf == 1) {
             tc_commit(o_full);
-            tc_commit(&kv_empty[j & 1]);
+            tc_commit(v_empty);
           }
         }
         __syncwarp();
-        if (hlf == 0 && j + 1 < nkt) {  // next score tile, issued between the two halves of P_j V_j
-          mbar_wait(s_empty, (uint32_t)(j & 1));  // S_j fully read
-          mbar_wait(&kv_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t dKs = dK0 + (uint64_t)((j + 1) & 1) * STAGE;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tS, dQ0 + 2 * ks, dKs + 2 * ks, idesc_s, ks != 0 ? 1u : 0u);
-            tc_commit(s_full);
-          }
-          __syncwarp();
-        }
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax + output (thread = query row)
+    // ---------------------------------------------------------------- softmax + output
+    // Two threads per query row: warp group hh = 0 (warps 2-5) owns S columns 0-63 and O columns 0-31,
+    // hh = 1 (warps 6-9) the other halves; the row maximum (per tile) and the row sum (once) are exchanged via smem.
     const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS_h = tS + lane_off + (uint32_t)(hh * 64);
+    uint8_t* prow = sP + hh * AT_TILE + r * 128;
     float m = -INFINITY, l = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int e = 0; e < 64; ++e) o[e] = 0.f;
+    for (int e = 0; e < 32; ++e) o[e] = 0.f;
     for (int j = 0; j < nkt; ++j) {
       const int nvalid = p.Nk - j * 128;  // columns >= nvalid are padding
+      const bool masked = nvalid < 128;
       mbar_wait(s_full, (uint32_t)(j & 1));
       tc_fence_after();
-      // pass 1: row maximum
+      // pass 1: maximum over this thread's 64 columns
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rs[32];
-        tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)(c * 32), rs);
+        tmem_ld_32x32b_x32(tS_h + (uint32_t)(c * 32), rs);
         tmem_wait_ld();
+        if (!masked) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(rs[e]));
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(rs[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (hh * 64 + c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(rs[e]));
+        }
       }
-      const float m_new = fmaxf(m, mx);
+      float* xb = xch + (j & 1) * 256;
+      xb[hh * 128 + r] = mx;
+      named_bar_sync(1, 256);
+      const float m_new = fmaxf(m, fmaxf(mx, xb[(hh ^ 1) * 128 + r]));
       const float a = ex2((m - m_new) * p.c2);
       const float mc = m_new * p.c2;
       m = m_new;
       float rowsum = 0.f;
-      // pass 2: P = exp2(S c2 - m c2) -> bf16 -> swizzled smem, one 64-column half at a time
+      // pass 2: P = exp2(S c2 - m c2) -> bf16 -> this group's half of the P operand
+      mbar_wait(&p_empty[hh], (uint32_t)(j & 1) ^ 1u);  // half consumed by the previous tile's P V
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        if ((c & 1) == 0) mbar_wait(p_empty, (uint32_t)((c >> 1) & 1) ^ 1u);  // previous half consumed by the MMA
+      for (int c = 0; c < 2; ++c) {
         uint32_t rs[32];
-        tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)(c * 32), rs);
+        tmem_ld_32x32b_x32(tS_h + (uint32_t)(c * 32), rs);
         tmem_wait_ld();
-        if (c == 3) {
+        if (c == 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_empty);
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = c * 32 + g * 8 + e;
-            const float x = col < nvalid ? ex2(fmaf(__uint_as_float(rs[g * 8 + e]), p.c2, -mc)) : 0.f;
-            pv[e] = x;
-            rowsum += x;
-          }
-          uint4 u;
-          u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-          u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-          const int j16 = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(sP + r * 128 + ((j16 ^ (r & 7)) << 4)) = u;
-        }
-        if (c & 1) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(p_full);
-        }
+        if (!masked)
+          rowsum += attn_exp_chunk<false>(rs, p.c2, mc, 0, 0, prow, c, r);
+        else
+          rowsum += attn_exp_chunk<true>(rs, p.c2, mc, hh * 64 + c * 32, nvalid, prow, c, r);
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[hh]);
       l = l * a + rowsum;
-      // O = O a + P_j V_j
+      // O = O a + P_j V_j (this thread's 32 output columns)
       mbar_wait(o_full, (uint32_t)(j & 1));
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t ro[32];
-        tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(c * 32), ro);
+        tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(hh * 32), ro);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[c * 32 + e] = fmaf(o[c * 32 + e], a, __uint_as_float(ro[e]));
+        for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], a, __uint_as_float(ro[e]));
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
     }
+    // total row sum = both halves
+    float* xb = xch + (nkt & 1) * 256;
+    xb[hh * 128 + r] = l;
+    named_bar_sync(1, 256);
+    l += xb[(hh ^ 1) * 128 + r];
     const int row = qt * 128 + r;
     if (row < p.Nq) {
       const float inv = 1.f / l;
-      bf16* dst = p.o + ((long long)b * p.Nq + row) * p.ldo + h * 64;
+      bf16* dst = p.o + ((long long)b * p.Nq + row) * p.ldo + h * 64 + hh * 32;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 u;
         u.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv); u.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
         u.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv); u.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
         *reinterpret_cast<uint4*>(dst + g * 8) = u;
       }
-      p.lse[((long long)b * p.heads + h) * p.Nq + row] = m * p.c2 + __log2f(l);
+      if (hh == 0) p.lse[((long long)b * p.heads + h) * p.Nq + row] = m * p.c2 + __log2f(l);
     }
   }
   tc_fence_before();
@@ -317,7 +359,41 @@ __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __re
   }
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+static constexpr int AT_BWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 compute (two threads per key row)
+
+// P^T = exp2(S^T c2 - lse), dS^T = P^T (dP^T - D) for one 32-column (query) chunk of this thread's key row -> smem.
+// (the 1/sqrt(d) factor of dS is applied when dQ / dK are drained)
+template <bool MASKED>
+__device__ __forceinline__ void attn_bwd_chunk(const uint32_t* rs, const uint32_t* rd, const float* lse_t, const float* d_t,
+                                               float c2, bool key_ok, uint8_t* pt_row, uint8_t* ds_row, int c, int r) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 l0 = *reinterpret_cast<const float4*>(lse_t + g * 8);
+    const float4 l1 = *reinterpret_cast<const float4*>(lse_t + g * 8 + 4);
+    const float4 d0 = *reinterpret_cast<const float4*>(d_t + g * 8);
+    const float4 d1 = *reinterpret_cast<const float4*>(d_t + g * 8 + 4);
+    const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float pv[8], dsv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float pe = ex2(fmaf(__uint_as_float(rs[g * 8 + e]), c2, -ls[e]));
+      if (MASKED && !key_ok) pe = 0.f;
+      pv[e] = pe;
+      dsv[e] = pe * (__uint_as_float(rd[g * 8 + e]) - dd[e]);
+    }
+    uint4 up, ud;
+    up.x = pack_bf16x2(pv[0], pv[1]); up.y = pack_bf16x2(pv[2], pv[3]);
+    up.z = pack_bf16x2(pv[4], pv[5]); up.w = pack_bf16x2(pv[6], pv[7]);
+    ud.x = pack_bf16x2(dsv[0], dsv[1]); ud.y = pack_bf16x2(dsv[2], dsv[3]);
+    ud.z = pack_bf16x2(dsv[4], dsv[5]); ud.w = pack_bf16x2(dsv[6], dsv[7]);
+    const int off = ((c * 4 + g) ^ (r & 7)) << 4;
+    *reinterpret_cast<uint4*>(pt_row + off) = up;
+    *reinterpret_cast<uint4*>(ds_row + off) = ud;
+  }
+}
+
+__global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
@@ -329,7 +405,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
   uint8_t* sdO = sQ + 2 * AT_TILE;   // [2]
   uint8_t* sPT = sdO + 2 * AT_TILE;  // P^T  : 2 query chunks x [128 key rows][128 B]
   uint8_t* sdS = sPT + 2 * AT_TILE;  // dS^T : same layout
-  uint8_t* stg = sdS + 2 * AT_TILE;  // 4 warps x 2 x 4 KB fp32 staging for the dQ reduce-add
+  uint8_t* stg = sdS + 2 * AT_TILE;  // 8 warps x 4 KB fp32 staging for the dQ reduce-add
   float* sLSE = reinterpret_cast<float*>(stg + 8 * 4096);  // [2][128]
   float* sD = sLSE + 256;                                   // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
@@ -364,11 +440,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         mbar_init(&qdo_empty[s], 1);
       }
       mbar_init(sdp_full, 1);
-      mbar_init(sdp_empty, 4);
-      mbar_init(pds_full, 4);
+      mbar_init(sdp_empty, 8);
+      mbar_init(pds_full, 8);
       mbar_init(pds_empty, 1);
       mbar_init(dq_full, 1);
-      mbar_init(dq_empty, 4);
+      mbar_init(dq_empty, 8);
       mbar_init(dkv_full, 1);
       fence_mbar_init();
     }
@@ -427,9 +503,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
     __syncwarp();
     for (int i = 0; i < nqt; ++i) {
       const int s = i & 1;
-      mbar_wait(pds_full, (uint32_t)(i & 1));
-      tc_fence_after();
-      if (i + 1 < nqt) {  // next tile's scores first: the compute warps get their input while dV/dK/dQ run
+      if (i + 1 < nqt) {  // next tile's scores as soon as S^T_i / dP^T_i have been read
         const int s1 = (i + 1) & 1;
         mbar_wait(sdp_empty, (uint32_t)(i & 1));
         mbar_wait(&qdo_full[s1], (uint32_t)(((i + 1) >> 1) & 1));
@@ -444,6 +518,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
         }
         __syncwarp();
       }
+      mbar_wait(pds_full, (uint32_t)(i & 1));
       if (i > 0) mbar_wait(dq_empty, (uint32_t)((i - 1) & 1));
       tc_fence_after();
       if (elect_one()) {
@@ -469,26 +544,33 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       __syncwarp();
     }
   } else {
-    // ---------------------------------------------------------------- compute warps (thread = key row / dQ row)
+    // ---------------------------------------------------------------- compute warps
+    // Two threads per key row: warp group hh owns query columns hh*64 .. hh*64+63 of S^T / dP^T (= query chunk hh of the
+    // P^T / dS^T operands), output columns hh*32 .. +31 of dQ, dV and dK.
     const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int key = kt * 128 + r;
     const bool key_ok = key < p.Nk;
+    const bool masked = (kt + 1) * 128 > p.Nk;  // only the last key tile has padding rows
     const long long bh = (long long)b * p.heads + h;
-    uint8_t* my_stg = stg + (size_t)(warp - 2) * 2 * 4096;
-    int sbuf = 0;
+    uint8_t* my_stg = stg + (size_t)(warp - 2) * 4096;
+    uint8_t* pt_row = sPT + hh * AT_TILE + r * 128;
+    uint8_t* ds_row = sdS + hh * AT_TILE + r * 128;
     float nlse = INFINITY, nD = 0.f;
-    if (r < p.Nq) {
+    if (hh == 0 && r < p.Nq) {
       nlse = p.lse[bh * p.Nq + r];
       nD = p.dvec[bh * p.Nq + r];
     }
     for (int i = 0; i < nqt; ++i) {
       const int buf = i & 1;
-      sLSE[buf * 128 + r] = nlse;
-      sD[buf * 128 + r] = nD;
-      named_bar_sync(1, 128);
-      {  // prefetch the next tile's per-query statistics
+      if (hh == 0) {
+        sLSE[buf * 128 + r] = nlse;
+        sD[buf * 128 + r] = nD;
+      }
+      named_bar_sync(1, 256);
+      if (hh == 0) {  // prefetch the next tile's per-query statistics
         const int qn = (i + 1) * 128 + r;
         nlse = INFINITY;
         nD = 0.f;
@@ -500,102 +582,78 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
       mbar_wait(sdp_full, (uint32_t)(i & 1));
       tc_fence_after();
       mbar_wait(pds_empty, (uint32_t)(i & 1) ^ 1u);  // P^T / dS^T smem consumed by the previous iteration's MMAs
-      const float* lse_t = sLSE + buf * 128;
-      const float* d_t = sD + buf * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(c * 32), rs);
-        tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(c * 32), rd);
-        tmem_wait_ld();
-        if (c == 3) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_empty);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 l0 = *reinterpret_cast<const float4*>(lse_t + c * 32 + g * 8);
-          const float4 l1 = *reinterpret_cast<const float4*>(lse_t + c * 32 + g * 8 + 4);
-          const float4 d0 = *reinterpret_cast<const float4*>(d_t + c * 32 + g * 8);
-          const float4 d1 = *reinterpret_cast<const float4*>(d_t + c * 32 + g * 8 + 4);
-          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-          float pv[8], dsv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float pe = key_ok ? ex2(fmaf(__uint_as_float(rs[g * 8 + e]), p.c2, -ls[e])) : 0.f;
-            pv[e] = pe;
-            dsv[e] = pe * (__uint_as_float(rd[g * 8 + e]) - dd[e]) * p.scale;
-          }
-          uint4 up, ud;
-          up.x = pack_bf16x2(pv[0], pv[1]); up.y = pack_bf16x2(pv[2], pv[3]);
-          up.z = pack_bf16x2(pv[4], pv[5]); up.w = pack_bf16x2(pv[6], pv[7]);
-          ud.x = pack_bf16x2(dsv[0], dsv[1]); ud.y = pack_bf16x2(dsv[2], dsv[3]);
-          ud.z = pack_bf16x2(dsv[4], dsv[5]); ud.w = pack_bf16x2(dsv[6], dsv[7]);
-          const int off = (c >> 1) * AT_TILE + r * 128 + ((((c & 1) * 4 + g) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(sPT + off) = up;
-          *reinterpret_cast<uint4*>(sdS + off) = ud;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      // dQ_i (rows = queries): TMEM -> fp32 staging -> TMA reduce-add into the fp32 accumulation buffer
-      mbar_wait(dq_full, (uint32_t)(i & 1));
-      tc_fence_after();
+      const float* lse_t = sLSE + buf * 128 + hh * 64;
+      const float* d_t = sD + buf * 128 + hh * 64;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        uint32_t rq[32];
-        tmem_ld_32x32b_x32(tdQ + lane_off + (uint32_t)(c * 32), rq);
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64 + c * 32), rs);
+        tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(hh * 64 + c * 32), rd);
         tmem_wait_ld();
         if (c == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(dq_empty);
+          if (lane == 0) mbar_arrive(sdp_empty);
         }
-        if (lane == 0) bulk_wait_read<1>();
+        if (!masked)
+          attn_bwd_chunk<false>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, true, pt_row, ds_row, c, r);
+        else
+          attn_bwd_chunk<true>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, key_ok, pt_row, ds_row, c, r);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // dQ_i (rows = queries): this group's 32 columns: TMEM -> fp32 staging -> TMA reduce-add
+      mbar_wait(dq_full, (uint32_t)(i & 1));
+      tc_fence_after();
+      {
+        uint32_t rq[32];
+        tmem_ld_32x32b_x32(tdQ + lane_off + (uint32_t)(hh * 32), rq);
+        tmem_wait_ld();
+        tc_fence_before();
         __syncwarp();
-        uint8_t* bufp = my_stg + sbuf * 4096 + lane * 128;
+        if (lane == 0) {
+          mbar_arrive(dq_empty);
+          bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
+        }
+        __syncwarp();
+        uint8_t* bufp = my_stg + lane * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<float4*>(bufp + ((g ^ (lane & 7)) << 4)) =
-              make_float4(__uint_as_float(rq[g * 4]), __uint_as_float(rq[g * 4 + 1]), __uint_as_float(rq[g * 4 + 2]),
-                          __uint_as_float(rq[g * 4 + 3]));
+              make_float4(__uint_as_float(rq[g * 4]) * p.scale, __uint_as_float(rq[g * 4 + 1]) * p.scale,
+                          __uint_as_float(rq[g * 4 + 2]) * p.scale, __uint_as_float(rq[g * 4 + 3]) * p.scale);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (i * 128 + q * 32 < p.Nq) tma_reduce_add_4d(&tmDQ, my_stg + sbuf * 4096, c * 32, i * 128 + q * 32, h, b);
+          if (i * 128 + q * 32 < p.Nq) tma_reduce_add_4d(&tmDQ, my_stg, hh * 32, i * 128 + q * 32, h, b);
           bulk_commit();
         }
-        sbuf ^= 1;
       }
     }
-    // dV, dK of this key tile
+    // dV, dK of this key tile (this group's 32 columns of each)
     mbar_wait(dkv_full, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
-      bf16* dst = (t == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (t == 0 ? p.lddv : p.lddk) + h * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32((t == 0 ? tdV : tdK) + lane_off + (uint32_t)(c * 32), rr);
-        tmem_wait_ld();
-        if (key_ok) {
+      bf16* dst = (t == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (t == 0 ? p.lddv : p.lddk) + h * 64 + hh * 32;
+      const float mul = t == 0 ? 1.f : p.scale;
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32((t == 0 ? tdV : tdK) + lane_off + (uint32_t)(hh * 32), rr);
+      tmem_wait_ld();
+      if (key_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(rr[g * 8 + 0]), __uint_as_float(rr[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(rr[g * 8 + 2]), __uint_as_float(rr[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(rr[g * 8 + 4]), __uint_as_float(rr[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(rr[g * 8 + 6]), __uint_as_float(rr[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(rr[g * 8 + 0]) * mul, __uint_as_float(rr[g * 8 + 1]) * mul);
+          u.y = pack_bf16x2(__uint_as_float(rr[g * 8 + 2]) * mul, __uint_as_float(rr[g * 8 + 3]) * mul);
+          u.z = pack_bf16x2(__uint_as_float(rr[g * 8 + 4]) * mul, __uint_as_float(rr[g * 8 + 5]) * mul);
+          u.w = pack_bf16x2(__uint_as_float(rr[g * 8 + 6]) * mul, __uint_as_float(rr[g * 8 + 7]) * mul);
+          *reinterpret_cast<uint4*>(dst + g * 8) = u;
         }
       }
     }
-    if (lane == 0) bulk_wait<0>();
+    if (lane == 0) bulk_wait_read<0>();
     __syncwarp();
   }
   tc_fence_before();
@@ -644,14 +702,14 @@ int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.o = reinterpret_cast<bf16*>(o);
   p.ldo = ldo;
   p.lse = lse;
-  const size_t smem = 6 * AT_TILE + 12 * 8 + 16 + 1024;
+  const size_t smem = 6 * AT_TILE + 512 * 4 + 16 * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_fwd attr: ") + cudaGetErrorString(e));
     attr = true;
   }
-  cudaError_t le = launch_k(attn_fwd_kernel, dim3((Nq + 127) / 128, heads, B), dim3(AT_THREADS), smem, stream, tmQ, tmK, tmV, p);
+  cudaError_t le = launch_k(attn_fwd_kernel, dim3((Nq + 127) / 128, heads, B), dim3(AT_FWD_THREADS), smem, stream, tmQ, tmK, tmV, p);
   if (le != cudaSuccess) return fail(ctx, std::string("sd2_attn_fwd launch: ") + cudaGetErrorString(le));
   return check_launch(ctx, "attn_fwd");
 }
@@ -703,7 +761,7 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd attr: ") + cudaGetErrorString(e));
     attr = true;
   }
-  attn_bwd_kernel<<<dim3((Nk + 127) / 128, heads, B), AT_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+  attn_bwd_kernel<<<dim3((Nk + 127) / 128, heads, B), AT_BWD_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
   launch_k(cast2d_f32_bf16_kernel, dim3(grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream,
            (const float*)dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
   return check_launch(ctx, "attn_bwd", 3);
