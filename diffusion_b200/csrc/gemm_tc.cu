@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (c + 1 < NCH) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
       }
     }
-    if (lane == 0) bulk_wait<0>();  // all stores / reductions of this warp have completed
+    if (lane == 0) bulk_wait_read<0>();  // staging smem no longer read by the copy engine; the writes complete with the grid
     __syncwarp();
   }
   tc_fence_before();
