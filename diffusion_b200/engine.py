@@ -28,6 +28,53 @@ _GEMM_FUNCS = (ops.linear_fwd, ops.linear_dgrad, ops.linear_wgrad, ops.conv3x3_f
                ops.bmm, ops.attn_fwd, ops.attn_bwd)
 
 
+# Output operands of every recorded op: (positional indices after ctx, keyword names).  Every other tensor argument is
+# an input.  The two-stream scheduler derives read / write address ranges from this table.
+_OP_WRITES = {
+    'linear_fwd': ((2,), ('workspace',)), 'linear_dgrad': ((2,), ('workspace',)), 'linear_wgrad': ((2,), ()),
+    'conv3x3_fwd': ((5,), ('workspace',)), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
+    'attn_fwd': ((3, 4), ()), 'attn_bwd': ((6, 7, 8, 9), ()),
+    'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ()),
+    'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ()),
+    'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ()), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
+    'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
+    'phase_split': ((1,), ()), 'phase_merge': ((1,), ()), 'colsum': ((1,), ()), 'cast_f32_to_bf16': ((1,), ()),
+    'pad_cast_rows': ((2,), ()), 'unpad_accum_rows': ((2,), ()), 'fill_f32': ((0,), ()),
+}
+
+
+def _span(t):
+    """Address range [lo, hi) touched by a (possibly strided) tensor view."""
+    if t.numel() == 0:
+        return (t.data_ptr(), t.data_ptr())
+    last = sum((n - 1) * st for n, st in zip(t.shape, t.stride()))
+    return (t.data_ptr(), t.data_ptr() + (last + 1) * t.element_size())
+
+
+def _op_io(op):
+    """(read ranges, write ranges) of a recorded op (functools.partial(fn, ctx, *args, **kwargs))."""
+    name = op.func.__name__
+    pos, kws = _OP_WRITES[name]
+    args = op.args[1:]
+    reads, writes = [], []
+    for i, a in enumerate(args):
+        if torch.is_tensor(a):
+            (writes if i in pos else reads).append(_span(a))
+    for k, a in op.keywords.items():
+        if torch.is_tensor(a):
+            (writes if k in kws else reads).append(_span(a))
+    # accumulating ops also read their destination; treating every output as read+write is always safe
+    return reads + writes, writes
+
+
+def _overlap(xs, ys):
+    for lo, hi in xs:
+        for lo2, hi2 in ys:
+            if lo < hi2 and lo2 < hi:
+                return True
+    return False
+
+
 class Node:
     """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
     __slots__ = ('data', 'grad', 'gw', 'M', 'C')
@@ -151,6 +198,8 @@ class Engine:
         self.attn_ws = None  # scratch of the fused attention backward (fp32 dQ accumulation), shared by all layers
         self.gemm_flops = 0  # algorithmic 2*M*N*K of every tensor-core GEMM recorded (fwd + bwd)
         self.fwd_is_gemm, self.bwd_is_gemm = [], []
+        self.fwd_side, self.bwd_side = [], []
+        self.ws_side = shared.ws_side if shared is not None else torch.empty(64 << 20, dtype=torch.uint8, device=dev)
         # static inputs (written by K1 / the prep kernels)
         c0 = self.cfg['block_out_channels'][0]
         self.in_x8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
@@ -199,15 +248,28 @@ class Engine:
         self._touched.add(name)  # called from backward builders only: records which builder completes this gradient
         return self.arena.storage(self.arena.g32, name)
 
-    def f(self, fn, *a, **k):
+    def f(self, fn, *a, side=False, **k):
+        """Record a forward op.  side=True: the op is off the critical path (it only feeds later ops) and may run on the
+        side stream, concurrently with the main chain; the scheduler inserts the dependencies."""
         self.fwd.append(partial(fn, self.ctx, *a, **k))
         self.fwd_is_gemm.append(fn in _GEMM_FUNCS)
+        self.fwd_side.append(bool(side))
         self._count_flops(fn, a)
 
-    def b(self, fn, *a, **k):
-        self.bwd.append(partial(fn, self.ctx, *a, **k))
+    def b(self, fn, *a, side=None, **k):
+        """Record a backward op.  Weight-gradient GEMMs and bias-gradient column sums write only parameter gradients,
+        which nothing reads before the end of backward: they go to the side stream by default."""
+        op = partial(fn, self.ctx, *a, **k)
+        if side is None:
+            side = fn in (ops.linear_wgrad, ops.conv3x3_wgrad) or (fn is ops.colsum and self._is_param_grad(a[1]))
+        self.bwd.append(op)
         self.bwd_is_gemm.append(fn in _GEMM_FUNCS)
+        self.bwd_side.append(bool(side))
         self._count_flops(fn, a)
+
+    def _is_param_grad(self, t):
+        g = self.arena.g32
+        return g.data_ptr() <= t.data_ptr() < g.data_ptr() + g.numel() * 4
 
     def _count_flops(self, fn, a):
         if fn in (ops.linear_fwd, ops.linear_dgrad):
@@ -238,14 +300,14 @@ class Engine:
             self.b(ops.axpby, node.grad, 1.0, g, 1.0, node.grad)
 
     # ---------------------------------------------------------------------------------------------- records
-    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None, gnames=()):
+    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None, gnames=(), side=False):
         w = self.w16(wname) if w16 is None else w16
         gwv = self.arena.storage(self.arena.g32, wname) if gw is None else gw
         N = w.shape[0]
         out = self.node(x.M, N)
         bias = self.p32(bname) if bname else None
         self.f(ops.linear_fwd, x.data, w, out.data, bias=bias, residual=residual.data if residual else None,
-               workspace=self.ws)
+               workspace=self.ws_side if side else self.ws, side=side)
 
         def bwd():
             g = out.grad
@@ -440,16 +502,16 @@ class Engine:
         # time-embedding projection -> per-image bias (fp32) added in conv1's epilogue
         wt, bt = self.w16(prefix + '.time_emb_proj.weight'), self.p32(prefix + '.time_emb_proj.bias')
         rb = self.buf(B, cout, dtype=torch.float32)
-        self.f(ops.linear_fwd, semb.data, wt, rb, bias=bt, out_f32=True)
+        self.f(ops.linear_fwd, semb.data, wt, rb, bias=bt, out_f32=True, side=True)
         d_tp32 = self.buf(B, cout, dtype=torch.float32)
         d_tp16 = self.buf(B, cout)
 
         def tproj_bwd(g):
             # d(time_emb_proj out)[b] = sum over the image's pixels of d(h1)
-            self.b(ops.colsum, g, d_tp32, B, HW, False)
-            self.b(ops.cast_f32_to_bf16, d_tp32.view(-1), d_tp16.view(-1))
+            self.b(ops.colsum, g, d_tp32, B, HW, False, side=True)
+            self.b(ops.cast_f32_to_bf16, d_tp32.view(-1), d_tp16.view(-1), side=True)
             gs, acc = self._gout(semb)
-            self.b(ops.linear_dgrad, d_tp16, wt, gs, residual=gs if acc else None)
+            self.b(ops.linear_dgrad, d_tp16, wt, gs, residual=gs if acc else None, side=True)
             self.b(ops.linear_wgrad, d_tp16, semb.data, self.g32(prefix + '.time_emb_proj.weight'))
             self.b(ops.colsum, d_tp16, self.g32(prefix + '.time_emb_proj.bias'), 1, B, True)
 
@@ -476,7 +538,7 @@ class Engine:
         q2 = self.linear(l2, tb + '.attn2.to_q.weight')
         names = [tb + '.attn2.to_k.weight', tb + '.attn2.to_v.weight']
         kv = self.linear(self.ctx_node, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names),
-                         gnames=names)
+                         gnames=names, side=True)  # depends only on the text context: off the critical path
         o2 = self.attention(q2.data, kv.data[:, :C], kv.data[:, C:], q2, kv, 0, 0, C, HW, L, heads, C)
         h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1)
         # --- GEGLU feed-forward
@@ -574,6 +636,32 @@ class Engine:
         missing = [n for n in arena.entries if n not in self.grad_ready]
         assert not missing, f'parameters without a gradient-producing op: {missing[:5]}'
         self._make_buckets()
+        self._hoist_forward_side_ops()
+
+    def _hoist_forward_side_ops(self):
+        """Move every forward side op (time-embedding projections, context K/V projections) to the earliest list
+        position its inputs allow, so that the side stream starts them at the beginning of the step instead of right
+        before their consumer."""
+        ios = [_op_io(op) for op in self.fwd]
+        order = list(range(len(self.fwd)))
+        for i in range(len(self.fwd)):
+            if not self.fwd_side[i]:
+                continue
+            pos = order.index(i)
+            j = pos
+            while j > 0:
+                prev = order[j - 1]
+                pr, pw = ios[prev]
+                r, w = ios[i]
+                if _overlap(r, pw) or _overlap(w, pr):  # true dependency (or shared scratch): stop here
+                    break
+                j -= 1
+            if j != pos:
+                order.pop(pos)
+                order.insert(j, i)
+        self.fwd = [self.fwd[i] for i in order]
+        self.fwd_side = [self.fwd_side[i] for i in order]
+        self.fwd_is_gemm = [self.fwd_is_gemm[i] for i in order]
 
     # ---------------------------------------------------------------------------------------------- data parallel (K5)
     def _make_buckets(self, n_buckets=8):
@@ -652,22 +740,60 @@ class Engine:
         if self.comm_stream is not None:
             torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
 
+    def _run_two_streams(self, op_list, side_flags, main, side):
+        """Issue `op_list` on two streams: ops flagged `side` go to `side`, everything else to `main` (the current
+        stream).  Dependencies are derived from the ops' read / write address ranges:
+          * a side op starts after everything issued on main before it (event recorded on main),
+          * a main op that touches data a still-pending side op writes (or overwrites data it reads) first waits for
+            that side op's completion event,
+          * at the end main joins the side stream.
+        Under stream capture the events become graph edges, so the replayed graph runs both chains concurrently."""
+        pending = []  # (read ranges, write ranges, completion event) of side ops main has not synchronised with yet
+        main_dirty = True
+        fork = None
+        for op, is_side in zip(op_list, side_flags):
+            reads, writes = _op_io(op)
+            if is_side:
+                if main_dirty or fork is None:
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    main_dirty = False
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    op()
+                    done = torch.cuda.Event()
+                    done.record(side)
+                pending.append((reads, writes, done))
+            else:
+                last = -1
+                for i, (pr, pw, _) in enumerate(pending):
+                    if _overlap(writes, pr) or _overlap(reads, pw):
+                        last = i
+                if last >= 0:  # the side stream is in order: waiting for entry `last` covers all earlier ones
+                    main.wait_event(pending[last][2])
+                    pending = pending[last + 1:]
+                op()
+                main_dirty = True
+        if pending:
+            main.wait_event(pending[-1][2])
+
     def capture_graphs(self):
-        """Capture the two static schedules as CUDA graphs (call after at least one eager warm-up step)."""
+        """Capture the two static schedules as CUDA graphs (call after at least one eager warm-up step).  Inside the
+        graphs the off-critical-path ops (weight-gradient GEMMs, bias-gradient sums, time-embedding and context K/V
+        projections) run on a second stream, concurrently with the main chain."""
         torch.cuda.synchronize(self.dev)
         s = torch.cuda.Stream(self.dev)
+        s2 = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         gf, gbs = torch.cuda.CUDAGraph(), []
         with torch.cuda.stream(s):
             with torch.cuda.graph(gf, stream=s):
-                for op in self.fwd:
-                    op()
+                self._run_two_streams(self.fwd, self.fwd_side, s, s2)
             start = 0
             for end in self.segments:  # one graph per gradient-bucket segment (all-reduces are issued in between)
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gb, stream=s):
-                    for op in self.bwd[start:end]:
-                        op()
+                    self._run_two_streams(self.bwd[start:end], self.bwd_side[start:end], s, s2)
                 gbs.append(gb)
                 start = end
         torch.cuda.current_stream(self.dev).wait_stream(s)
