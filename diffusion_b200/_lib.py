@@ -182,7 +182,7 @@ class DryLib:
                     raise TypeError(f'{name}: argument {i} ({v!r}) is not a {t}') from e
             self.calls[name] = self.calls.get(name, 0) + 1
             if name == 'sd2_groupnorm_ws_floats':
-                return a[0] * 32 * a[1] * 2 + a[0] * 128
+                return a[0] * 64 * a[1] * 2 + a[0] * 128
             if name == 'sd2_attn_bwd_ws_bytes':
                 return a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * a[2] * 4
             if name == 'sd2_layernorm_ws_floats':

@@ -10,7 +10,7 @@
 namespace sd2 {
 
 static constexpr int GN_THREADS = 512;
-static constexpr int GN_MAXP = 32;  // pixel-chunk partials per image
+static constexpr int GN_MAXP = 64;  // pixel-chunk partials per image
 
 __device__ __forceinline__ void load8(const bf16* p, float* v) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -23,9 +23,14 @@ __device__ __forceinline__ void store8(bf16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-__host__ __device__ inline int gn_chunks(int HW) {
-  int p = HW / 32;
-  return p < 1 ? 1 : (p > GN_MAXP ? GN_MAXP : p);
+// Pixel chunks per image: B * P blocks should fill two waves of (2 resident blocks per SM) without a ragged tail.
+static inline int gn_chunks(int HW, int B, int C, int num_sms) {
+  int p = (4 * num_sms) / (B > 0 ? B : 1);
+  const int R = GN_THREADS / (C / 8);       // row lanes per block
+  const int pmax = HW / (4 * (R > 0 ? R : 1));  // keep >= 4 rows per thread (the row loops are unrolled by 4)
+  if (p > pmax) p = pmax;
+  if (p > GN_MAXP) p = GN_MAXP;
+  return p < 1 ? 1 : p;
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm fwd
@@ -49,7 +54,7 @@ __device__ __forceinline__ void gn_block_reduce(float* sm, const float* a, const
 }
 
 // grid (P, B). Partial (sum, sumsq) per group over this block's pixel chunk -> ws[b][p][G][2]
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ ws,
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ ws,
                                                               int HW, int C, int G) {
   pdl_grid_sync();
   extern __shared__ float sm[];  // [R][C][2] + [C][2]
@@ -62,6 +67,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
   if (r < R) {
     const bf16* base = x + ((long long)b * HW) * ldx + v * 8;
+#pragma unroll 4
     for (int row = row0 + r; row < row1; row += R) {
       float f[8];
       load8(base + (long long)row * ldx, f);
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const bf16* __rest
 }
 
 // grid (P, B): finalize stats from the P partials, then y = [silu](x * scale + shift)
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __restrict__ x, long long ldx,
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const bf16* __restrict__ x, long long ldx,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               bf16* __restrict__ y, long long ldy, float* __restrict__ stats,
                                                               const float* __restrict__ ws, int HW, int C, int G, float eps,
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const bf16* __rest
   const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
   const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
   bf16* yb = y + ((long long)b * HW) * ldy + v * 8;
+#pragma unroll 4
   for (int row = row0 + r; row < row1; row += R) {
     float f[8];
     load8(xb + (long long)row * ldx, f);
@@ -149,7 +156,7 @@ __device__ __forceinline__ float silu_grad(float z) {
 }
 
 // grid (P, B): per-channel partial sums of dyh and dyh * xhat -> ws[b][p][C][2]
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy,
+__global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy,
                                                                   const bf16* __restrict__ x, long long ldx,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ stats, float* __restrict__ ws, int HW,
@@ -175,6 +182,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_stats_kernel(const bf16* __
     }
     const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
     const bf16* db = dy + ((long long)b * HW) * lddy + v * 8;
+#pragma unroll 4
     for (int row = row0 + r; row < row1; row += R) {
       float f[8], d[8];
       load8(xb + (long long)row * ldx, f);
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restr
 }
 
 // grid (P, B): dx = rstd * (gamma*dyh - (db_g + xhat*ds_g)/n) (+ dx_add)
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
+__global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
                                                                   const bf16* __restrict__ x, long long ldx,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ stats, const float* __restrict__ gstat,
@@ -275,6 +283,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const bf16* __
   const bf16* db = dy + ((long long)b * HW) * lddy + v * 8;
   bf16* ob = dx + ((long long)b * HW) * lddx + v * 8;
   const bf16* ab = dx_add ? dx_add + ((long long)b * HW) * ldadd + v * 8 : nullptr;
+#pragma unroll 4
   for (int row = row0 + r; row < row1; row += R) {
     float f[8], d[8], a[8];
     load8(xb + (long long)row * ldx, f);
@@ -529,7 +538,7 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
   if (!ctx) return 1;
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_fwd: unsupported C/G");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const dim3 grid(gn_chunks(HW), B);
+  const dim3 grid(gn_chunks(HW, B, C, ctx->num_sms), B);
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
   launch_k(gn_stats_kernel, dim3(grid), dim3(GN_THREADS), red_smem, stream, reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
   launch_k(gn_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(x), ldx, gamma, beta,
@@ -544,7 +553,7 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
   if (!ctx) return 1;
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_bwd: unsupported C/G");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int P = gn_chunks(HW);
+  const int P = gn_chunks(HW, B, C, ctx->num_sms);
   const dim3 grid(P, B);
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
   float* gstat = ws + (long long)B * GN_MAXP * C * 2;
