@@ -5,7 +5,9 @@
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 4-D boxes, SWIZZLE_128B, mbarrier complete_tx) into a 4..8 stage ring
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32) into one of TWO
 //                 accumulator buffers in tensor memory, so the next tile's main loop overlaps this tile's epilogue
-//   warps 2..5  : epilogue: tcgen05.ld 32x32b -> registers -> alpha / bias / per-image bias / residual -> swizzled smem
+//   warps 2..9  : epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns, so every SM
+//                 sub-partition has two epilogue warps to hide latencies):
+//                 tcgen05.ld 32x32b -> registers -> alpha / bias / per-image bias / residual -> swizzled smem
 //                 staging -> TMA store (bf16 / fp32) or TMA reduce-add (fp32 weight gradients, split-K sums); every
 //                 global write is a full coalesced row segment issued by the copy engine, no per-thread stores or atomics
 // Operands can be K-major (forward, activations x weights) or MN-major (dgrad reads the weights transposed, wgrad
@@ -23,8 +25,9 @@ static constexpr int BK = 64;
 static constexpr int A_BYTES = BM * BK * 2;      // 16 KB
 static constexpr int CHUNK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major box = 8 KB
 static constexpr int STG_BYTES = 4096;           // one epilogue staging buffer: 32 rows x 128 B
-static constexpr int STG_TOTAL = 4 * 2 * STG_BYTES;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quadrant, each owning half of the tile's columns
+static constexpr int STG_TOTAL = EPI_WARPS * STG_BYTES;
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 static constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int BN>
@@ -33,7 +36,7 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int OUT_CH = (BN % 64 == 0) ? 64 : 32;  // bf16 columns per TMA store box
+  static constexpr int OUT_CH = (BN % 128 == 0) ? 64 : 32;  // bf16 columns per TMA store box (64 needs an even chunk split)
 };
 
 int gemm_stages(int BN) {
@@ -41,7 +44,7 @@ int gemm_stages(int BN) {
   int s = (SMEM_LIMIT - 1024 - 256 - STG_TOTAL) / stage_bytes;
   return s < 2 ? 2 : (s > 8 ? 8 : s);
 }
-int gemm_out_chunk(int BN) { return (BN % 64 == 0) ? 64 : 32; }
+int gemm_out_chunk(int BN) { return (BN % 128 == 0) ? 64 : 32; }
 
 struct WorkItem {
   int m_tile, n_tile, split, batch, kb0, nkb;
@@ -68,25 +71,18 @@ struct EpiTile {  // per work item, per thread (thread = one output row of the 3
   float alpha;
   float bv[8];      // bias of tile columns lane*8 .. lane*8+7
 };
-struct EpiPre {  // global operands of one 32-column chunk, fetched one chunk ahead
-  float4 rb[8];
-  uint4 rs[4];
+struct EpiPre {  // residual of one 32-column chunk, fetched one chunk ahead (the per-image bias rows are tiny and
+  uint4 rs[4];    // L1-resident: they are read in place)
 };
 struct EpiState {
-  int sbuf;
+  int c0, c1;  // this warp's range of 32-column chunks
 };
 
 __device__ __forceinline__ void epi_prefetch(const EpiTile& t, int c, EpiPre& pre) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int n = t.n_tile0 + c * 32 + g * 8;
-    if (n < t.N) {
-      if (t.rb != nullptr) {
-        pre.rb[2 * g] = *reinterpret_cast<const float4*>(t.rb + n);
-        pre.rb[2 * g + 1] = *reinterpret_cast<const float4*>(t.rb + n + 4);
-      }
-      if (t.rs != nullptr) pre.rs[g] = *reinterpret_cast<const uint4*>(t.rs + n);
-    }
+    if (n < t.N && t.rs != nullptr) pre.rs[g] = *reinterpret_cast<const uint4*>(t.rs + n);
   }
 }
 
@@ -95,13 +91,12 @@ template <int BN>
 __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c, const EpiPre& cur, EpiPre& nxt,
                                           uint32_t t_addr, uint8_t* stg, int lane, const CUtensorMap* tmO,
                                           uint64_t* tmem_empty) {
-  constexpr int NCH = BN / 32;
-  constexpr int OUT_CH = (BN % 64 == 0) ? 64 : 32;
+  constexpr int OUT_CH = (BN % 128 == 0) ? 64 : 32;
   const bool f32_out = t.out_mode != OUT_BF16;
   uint32_t r[32];
   tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
   tmem_wait_ld();
-  if (c == NCH - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+  if (c == st.c1 - 1) {  // this warp's columns are fully read: its share of handing the TMEM buffer back to the MMA warp
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tmem_empty);
@@ -109,12 +104,10 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
     epi_prefetch(t, c + 1, nxt);
   }
   const int n_base = t.n_tile0 + c * 32;
-  const bool new_buf = f32_out || OUT_CH == 32 || (c & 1) == 0;
-  if (new_buf) {  // the buffer we are about to fill was handed to the copy engine two stores ago
-    if (lane == 0) bulk_wait_read<1>();
-    __syncwarp();
-  }
-  uint8_t* buf = stg + st.sbuf * STG_BYTES;
+  const int cl = c - st.c0;  // chunk index within this warp's column range
+  const bool new_buf = f32_out || OUT_CH == 32 || (cl & 1) == 0;
+  uint8_t* buf = stg;
+  bool waited = false;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int n = n_base + g * 8;
@@ -127,7 +120,7 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
     }
     if (n < t.N) {
       if (t.rb != nullptr) {
-        const float4 b0 = cur.rb[2 * g], b1 = cur.rb[2 * g + 1];
+        const float4 b0 = *reinterpret_cast<const float4*>(t.rb + n), b1 = *reinterpret_cast<const float4*>(t.rb + n + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
@@ -138,6 +131,11 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
         v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
       }
     }
+    if (new_buf && !waited) {  // the staging buffer was handed to the copy engine by the previous store of this warp
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      waited = true;
+    }
     if (f32_out) {  // staging tile: 32 rows x 32 fp32 (128 B rows), SWIZZLE_128B
       uint8_t* rowp = buf + lane * 128;
       *reinterpret_cast<float4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -147,14 +145,14 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
       o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
       o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
       if (OUT_CH == 64) {  // 32 rows x 64 bf16 (128 B rows), SWIZZLE_128B; this ld fills half a row
-        const int j = (c & 1) * 4 + g;
+        const int j = (cl & 1) * 4 + g;
         *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
       } else {  // 32 rows x 32 bf16 (64 B rows), SWIZZLE_64B
         *reinterpret_cast<uint4*>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
       }
     }
   }
-  const bool full = f32_out || OUT_CH == 32 || (c & 1) == 1;
+  const bool full = f32_out || OUT_CH == 32 || (cl & 1) == 1;
   if (full) {
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the async proxy (TMA)
     __syncwarp();
@@ -166,7 +164,6 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
         tma_store_4d(tmO, buf, col0, t.row0, t.o2, t.o3);
     }
     if (lane == 0) bulk_commit();
-    st.sbuf ^= 1;
   }
 }
 
@@ -201,7 +198,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full_bar[a], 1);
-        mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
       }
       fence_mbar_init();
     }
@@ -376,12 +373,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // per lane, broadcast by shuffles), per-image bias and residual of 32-column chunk c+1 are fetched while chunk c
     // is processed, and chunk 0's are issued before the wait on the accumulator.
     const int q = warp & 3;
-    uint8_t* stg = stg_base + (size_t)(warp - 2) * 2 * STG_BYTES;
+    const int hh = (warp - 2) >> 2;
+    uint8_t* stg = stg_base + (size_t)(warp - 2) * STG_BYTES;
+    constexpr int NCH_ALL = BN / 32;
+    constexpr int HALF = (Cfg::OUT_CH == 64) ? NCH_ALL / 2 : (NCH_ALL + 1) / 2;
     EpiState st;
-    st.sbuf = 0;
+    st.c0 = hh * HALF;
+    st.c1 = hh == 0 ? HALF : NCH_ALL;
     int it = 0;
     const bool raw = p.out_mode == OUT_F32_PARTIAL;
-    constexpr int NCH = BN / 32;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const WorkItem w = decode_item(p, item);
       const int acc = it & 1;
@@ -416,14 +416,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         t.bv[4] = b1.x; t.bv[5] = b1.y; t.bv[6] = b1.z; t.bv[7] = b1.w;
       }
       EpiPre pa, pb;
-      epi_prefetch(t, 0, pa);
+      epi_prefetch(t, st.c0, pa);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
 #pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
+      for (int c = st.c0; c < st.c1; c += 2) {
         epi_chunk<BN>(t, st, c, pa, pb, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
-        if (c + 1 < NCH) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
+        if (c + 1 < st.c1) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
       }
     }
     if (lane == 0) bulk_wait_read<0>();  // staging smem no longer read by the copy engine; the writes complete with the grid
