@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t tS_h = tS + lane_off + (uint32_t)(hh * 64);
     uint8_t* prow = sP + hh * AT_TILE + r * 128;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f, a_pend = 0.f;
     float o[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) o[e] = 0.f;
@@ -248,6 +248,18 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
       xb[hh * 128 + r] = mx;
       named_bar_sync(1, 256);
       const float m_new = fmaxf(m, fmaxf(mx, xb[(hh ^ 1) * 128 + r]));
+      if (j > 0) {  // O += P_{j-1} V_{j-1}: deferred to here so that the tensor pipe's latency is hidden behind pass 1
+        mbar_wait(o_full, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        uint32_t ro[32];
+        tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(hh * 32), ro);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], a_pend, __uint_as_float(ro[e]));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
+      }
       const float a = ex2((m - m_new) * p.c2);
       const float mc = m_new * p.c2;
       m = m_new;
@@ -273,19 +285,16 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[hh]);
       l = l * a + rowsum;
-      // O = O a + P_j V_j (this thread's 32 output columns)
-      mbar_wait(o_full, (uint32_t)(j & 1));
+      a_pend = a;
+    }
+    if (nkt > 0) {  // last tile's P V
+      mbar_wait(o_full, (uint32_t)((nkt - 1) & 1));
       tc_fence_after();
-      {
-        uint32_t ro[32];
-        tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(hh * 32), ro);
-        tmem_wait_ld();
+      uint32_t ro[32];
+      tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(hh * 32), ro);
+      tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], a, __uint_as_float(ro[e]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], a_pend, __uint_as_float(ro[e]));
     }
     // total row sum = both halves
     float* xb = xch + (nkt & 1) * 256;
@@ -361,11 +370,11 @@ __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __re
 
 static constexpr int AT_BWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 compute (two threads per key row)
 
-// P^T = exp2(S^T c2 - lse), dS^T = P^T (dP^T - D) for one 32-column (query) chunk of this thread's key row -> smem.
-// (the 1/sqrt(d) factor of dS is applied when dQ / dK are drained)
+// P^T = exp2(S^T c2 - lse), dS^T = P^T (dP^T - D) for one 32-column (query) chunk of this thread's key row, packed to
+// bf16 in registers (the 1/sqrt(d) factor of dS is applied when dQ / dK are drained)
 template <bool MASKED>
 __device__ __forceinline__ void attn_bwd_chunk(const uint32_t* rs, const uint32_t* rd, const float* lse_t, const float* d_t,
-                                               float c2, bool key_ok, uint8_t* pt_row, uint8_t* ds_row, int c, int r) {
+                                               float c2, bool key_ok, uint4* pk_p, uint4* pk_d) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 l0 = *reinterpret_cast<const float4*>(lse_t + g * 8);
@@ -382,14 +391,37 @@ __device__ __forceinline__ void attn_bwd_chunk(const uint32_t* rs, const uint32_
       pv[e] = pe;
       dsv[e] = pe * (__uint_as_float(rd[g * 8 + e]) - dd[e]);
     }
-    uint4 up, ud;
-    up.x = pack_bf16x2(pv[0], pv[1]); up.y = pack_bf16x2(pv[2], pv[3]);
-    up.z = pack_bf16x2(pv[4], pv[5]); up.w = pack_bf16x2(pv[6], pv[7]);
-    ud.x = pack_bf16x2(dsv[0], dsv[1]); ud.y = pack_bf16x2(dsv[2], dsv[3]);
-    ud.z = pack_bf16x2(dsv[4], dsv[5]); ud.w = pack_bf16x2(dsv[6], dsv[7]);
-    const int off = ((c * 4 + g) ^ (r & 7)) << 4;
-    *reinterpret_cast<uint4*>(pt_row + off) = up;
-    *reinterpret_cast<uint4*>(ds_row + off) = ud;
+    pk_p[g].x = pack_bf16x2(pv[0], pv[1]); pk_p[g].y = pack_bf16x2(pv[2], pv[3]);
+    pk_p[g].z = pack_bf16x2(pv[4], pv[5]); pk_p[g].w = pack_bf16x2(pv[6], pv[7]);
+    pk_d[g].x = pack_bf16x2(dsv[0], dsv[1]); pk_d[g].y = pack_bf16x2(dsv[2], dsv[3]);
+    pk_d[g].z = pack_bf16x2(dsv[4], dsv[5]); pk_d[g].w = pack_bf16x2(dsv[6], dsv[7]);
+  }
+}
+
+// dQ tile of one query block: this warp group's 32 columns, TMEM -> fp32 staging -> TMA reduce-add
+__device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint8_t* my_stg, int lane, float scale, uint64_t* dq_empty,
+                                                  const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h, int b) {
+  uint32_t rq[32];
+  tmem_ld_32x32b_x32(taddr, rq);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    mbar_arrive(dq_empty);
+    bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
+  }
+  __syncwarp();
+  uint8_t* bufp = my_stg + lane * 128;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(bufp + ((g ^ (lane & 7)) << 4)) =
+        make_float4(__uint_as_float(rq[g * 4]) * scale, __uint_as_float(rq[g * 4 + 1]) * scale,
+                    __uint_as_float(rq[g * 4 + 2]) * scale, __uint_as_float(rq[g * 4 + 3]) * scale);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (row0 < Nq) tma_reduce_add_4d(tmDQ, my_stg, col0, row0, h, b);
+    bulk_commit();
   }
 }
 
@@ -581,10 +613,12 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
       }
       mbar_wait(sdp_full, (uint32_t)(i & 1));
       tc_fence_after();
-      mbar_wait(pds_empty, (uint32_t)(i & 1) ^ 1u);  // P^T / dS^T smem consumed by the previous iteration's MMAs
       const float* lse_t = sLSE + buf * 128 + hh * 64;
       const float* d_t = sD + buf * 128 + hh * 64;
-#pragma unroll 1
+      // all of this tile's math goes to registers first: the MMAs of the previous tile (which still read the P^T / dS^T
+      // smem and produce dQ_{i-1}) run underneath it
+      uint4 pk_p[8], pk_d[8];
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t rs[32], rd[32];
         tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64 + c * 32), rs);
@@ -596,40 +630,34 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
           if (lane == 0) mbar_arrive(sdp_empty);
         }
         if (!masked)
-          attn_bwd_chunk<false>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, true, pt_row, ds_row, c, r);
+          attn_bwd_chunk<false>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, true, pk_p + c * 4, pk_d + c * 4);
         else
-          attn_bwd_chunk<true>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, key_ok, pt_row, ds_row, c, r);
+          attn_bwd_chunk<true>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, key_ok, pk_p + c * 4, pk_d + c * 4);
       }
+      if (i > 0) {  // dQ_{i-1} (rows = queries): drained now, after its MMAs had a whole tile of math to complete
+        mbar_wait(dq_full, (uint32_t)((i - 1) & 1));
+        tc_fence_after();
+        attn_bwd_drain_dq(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, lane, p.scale, dq_empty, &tmDQ, hh * 32,
+                          (i - 1) * 128 + q * 32, p.Nq, h, b);
+      }
+      mbar_wait(pds_empty, (uint32_t)(i & 1) ^ 1u);  // P^T / dS^T smem consumed by the previous tile's MMAs
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int off = ((c * 4 + g) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(pt_row + off) = pk_p[c * 4 + g];
+          *reinterpret_cast<uint4*>(ds_row + off) = pk_d[c * 4 + g];
+        }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // dQ_i (rows = queries): this group's 32 columns: TMEM -> fp32 staging -> TMA reduce-add
-      mbar_wait(dq_full, (uint32_t)(i & 1));
+    }
+    {  // last tile's dQ
+      mbar_wait(dq_full, (uint32_t)((nqt - 1) & 1));
       tc_fence_after();
-      {
-        uint32_t rq[32];
-        tmem_ld_32x32b_x32(tdQ + lane_off + (uint32_t)(hh * 32), rq);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(dq_empty);
-          bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
-        }
-        __syncwarp();
-        uint8_t* bufp = my_stg + lane * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(bufp + ((g ^ (lane & 7)) << 4)) =
-              make_float4(__uint_as_float(rq[g * 4]) * p.scale, __uint_as_float(rq[g * 4 + 1]) * p.scale,
-                          __uint_as_float(rq[g * 4 + 2]) * p.scale, __uint_as_float(rq[g * 4 + 3]) * p.scale);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (i * 128 + q * 32 < p.Nq) tma_reduce_add_4d(&tmDQ, my_stg, hh * 32, i * 128 + q * 32, h, b);
-          bulk_commit();
-        }
-      }
+      attn_bwd_drain_dq(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, lane, p.scale, dq_empty, &tmDQ, hh * 32,
+                        (nqt - 1) * 128 + q * 32, p.Nq, h, b);
     }
     // dV, dK of this key tile (this group's 32 columns of each)
     mbar_wait(dkv_full, 0);
