@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restr
       a1 += T[(b * cpg + cl) * 2];
       a2 += T[(b * cpg + cl) * 2 + 1];
     }
-    dbeta[g * cpg + cl] += a1;
-    dgamma[g * cpg + cl] += a2;
+    atomicAdd(&dbeta[g * cpg + cl], a1);  // atomics: two half-batch chains may accumulate concurrently (DualEngine)
+    atomicAdd(&dgamma[g * cpg + cl], a2);
   }
 }
 
@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __
       a1 += sm[k][cl][0];
       a2 += sm[k][cl][1];
     }
-    dbeta[c] += a1;
-    dgamma[c] += a2;
+    atomicAdd(&dbeta[c], a1);
+    atomicAdd(&dgamma[c], a2);
   }
 }
 

@@ -306,7 +306,10 @@ __global__ void unpad_accum_rows_kernel(const float* __restrict__ src, int cs, f
     const long long r = i / cd;
     const int c = (int)(i % cd);
     const float v = src[r * cs + c];
-    dst[i] = accumulate ? dst[i] + v : v;
+    if (accumulate)
+      atomicAdd(&dst[i], v);  // concurrent half-batch chains accumulate into the same gradient
+    else
+      dst[i] = v;
   }
 }
 

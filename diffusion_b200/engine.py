@@ -180,7 +180,10 @@ class ParamArena:
 
 class Engine:
 
-    def __init__(self, unet, B, H, W, L, shared=None):
+    def __init__(self, unet, B, H, W, L, shared=None, io=None, own_scratch=False):
+        """io: optional dict of externally owned static buffers (in_x8, in_temb, in_ctx, pred8, dpred8) - used by
+        DualEngine, whose two half-batch engines work on slices of full-batch buffers.  own_scratch: do not share the
+        split-K workspaces with `shared` (engines that run concurrently need private scratch)."""
         dev = unet.conv_in.weight.device
         self.ctx = ops.get_ctx(dev)
         self.dev = dev
@@ -189,7 +192,8 @@ class Engine:
         self.B, self.H, self.W, self.L = B, H, W, L
         self.fwd, self.bwd, self._bwd_builders = [], [], []
         self._touched, self.grad_ready = set(), {}
-        self.ws = shared.ws if shared is not None else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        reuse = shared is not None and not own_scratch and getattr(shared, 'ws', None) is not None
+        self.ws = shared.ws if reuse else torch.empty((128 if own_scratch else 256) << 20, dtype=torch.uint8, device=dev)
         self.G = self.cfg['norm_num_groups']
         cmax = max(self.cfg['block_out_channels']) * 2
         self.gn_ws = ops.groupnorm_ws(self.ctx, B, cmax, dev)
@@ -199,14 +203,15 @@ class Engine:
         self.gemm_flops = 0  # algorithmic 2*M*N*K of every tensor-core GEMM recorded (fwd + bwd)
         self.fwd_is_gemm, self.bwd_is_gemm = [], []
         self.fwd_side, self.bwd_side = [], []
-        self.ws_side = shared.ws_side if shared is not None else torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        self.ws_side = shared.ws_side if reuse else torch.empty(64 << 20, dtype=torch.uint8, device=dev)
         # static inputs (written by K1 / the prep kernels)
         c0 = self.cfg['block_out_channels'][0]
-        self.in_x8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
-        self.in_temb = torch.zeros(B, c0, dtype=BF16, device=dev)
-        self.in_ctx = torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
-        self.pred8 = None
-        self.dpred8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
+        io = io or {}
+        self.in_x8 = io['in_x8'] if 'in_x8' in io else torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
+        self.in_temb = io['in_temb'] if 'in_temb' in io else torch.zeros(B, c0, dtype=BF16, device=dev)
+        self.in_ctx = io['in_ctx'] if 'in_ctx' in io else torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
+        self.pred8 = io.get('pred8')
+        self.dpred8 = io['dpred8'] if 'dpred8' in io else torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
         self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         self._build()
         self.graph_fwd = self.graph_bwd = None
@@ -614,7 +619,8 @@ class Engine:
         # ---- head: GN + SiLU + conv_out (4 output channels padded to 8)
         n = self.groupnorm(x, 'conv_norm_out', cfg['norm_eps'], 1, H * W)
         w_out = self.w16('conv_out.weight')  # [9, 4, C0]
-        self.pred8 = self.buf(M, 8)
+        if self.pred8 is None:
+            self.pred8 = self.buf(M, 8)
         self.f(ops.conv3x3_fwd, n.data, B, H, W, w_out, self.pred8, bias=self.b_out8, workspace=self.ws)
         gb8 = self.buf(8, dtype=torch.float32)
 
@@ -814,6 +820,160 @@ class Engine:
                     if is_gemm:
                         op()
                         n += 1
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        return g, n
+
+
+class DualEngine:
+    """The per-GPU microbatch as TWO concurrent half-batch chains.
+
+    The step time of one chain is ~9 ms of dependent-launch latency plus ~0.74 ms per image (measured): most kernels of
+    the UNet at B=16 cannot fill 148 SMs and each waits for its predecessor.  Two half-batch engines share the weight
+    arenas and work on slices of the full-batch I/O buffers; inside the CUDA graphs each runs on its own (main, side)
+    stream pair, so one chain's kernels fill the other's bubbles.  Gradients of both halves accumulate into the same
+    fp32 arena (TMA reduce-add / atomics).  Samples are independent in this network (GroupNorm is per sample), so the
+    result equals the single-chain result up to fp32 summation order.  Same interface as Engine."""
+
+    def __init__(self, unet, B, H, W, L, shared=None):
+        assert B % 2 == 0
+        dev = unet.conv_in.weight.device
+        self.ctx, self.dev, self.cfg = ops.get_ctx(dev), dev, unet.config
+        self.B, self.H, self.W, self.L = B, H, W, L
+        c0 = self.cfg['block_out_channels'][0]
+        M, Bh = B * H * W, B // 2
+        self.in_x8 = torch.zeros(M, 8, dtype=BF16, device=dev)
+        self.in_temb = torch.zeros(B, c0, dtype=BF16, device=dev)
+        self.in_ctx = torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
+        self.pred8 = torch.zeros(M, 8, dtype=BF16, device=dev)
+        self.dpred8 = torch.zeros(M, 8, dtype=BF16, device=dev)
+        self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.halves = []
+        for h in range(2):
+            rows = slice(h * Bh * H * W, (h + 1) * Bh * H * W)
+            io = dict(in_x8=self.in_x8[rows], in_temb=self.in_temb[h * Bh:(h + 1) * Bh],
+                      in_ctx=self.in_ctx[h * Bh * L:(h + 1) * Bh * L], pred8=self.pred8[rows], dpred8=self.dpred8[rows])
+            prev = self.halves[0] if self.halves else shared
+            self.halves.append(Engine(unet, Bh, H, W, L, shared=prev, io=io, own_scratch=True))
+        self.arena = self.halves[0].arena
+        self.buckets, self.segments = self.halves[0].buckets, self.halves[0].segments
+        self.graph_fwd = self.graph_bwd = None
+        self.ws = None  # no scratch to lend to later engines
+
+    # ---- aggregate views used by tools / tests
+    @property
+    def fwd(self):
+        return self.halves[0].fwd + self.halves[1].fwd
+
+    @property
+    def bwd(self):
+        return self.halves[0].bwd + self.halves[1].bwd
+
+    @property
+    def gemm_flops(self):
+        return sum(e.gemm_flops for e in self.halves)
+
+    @property
+    def act_bytes(self):
+        return sum(e.act_bytes for e in self.halves)
+
+    def params_bound(self):
+        return self.arena.bound()
+
+    prepare_inputs = Engine.prepare_inputs
+    set_context = Engine.set_context
+    enable_grad_sync = Engine.enable_grad_sync
+    _allreduce_bucket = Engine._allreduce_bucket
+
+    # ---- execution
+    def run_forward(self):
+        self.arena.refresh_shadow(self.ctx)
+        if self.graph_fwd is not None:
+            self.graph_fwd.replay()
+        else:
+            for e in self.halves:
+                for op in e.fwd:
+                    op()
+
+    def run_backward(self):
+        sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
+        start = 0
+        for k, end in enumerate(self.segments):
+            if self.graph_bwd is not None:
+                self.graph_bwd[k].replay()
+            else:
+                for e in self.halves:
+                    for op in e.bwd[start:end]:
+                        op()
+            if sync:
+                for lo, hi, ready in self.buckets:
+                    if ready == end:
+                        self._allreduce_bucket(lo, hi)
+            start = end
+        if sync and self.comm_stream is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+
+    def _capture_pair(self, graph, s, streams, lists):
+        """One graph: half 0 on (s, streams[0]), half 1 on (streams[1], streams[2]), forked from / joined to s."""
+        (ops0, side0), (ops1, side1) = lists
+        with torch.cuda.graph(graph, stream=s):
+            fork = torch.cuda.Event()
+            fork.record(s)
+            streams[1].wait_event(fork)
+            with torch.cuda.stream(streams[1]):
+                self.halves[1]._run_two_streams(ops1, side1, streams[1], streams[2])
+                done = torch.cuda.Event()
+                done.record(streams[1])
+            self.halves[0]._run_two_streams(ops0, side0, s, streams[0])
+            s.wait_event(done)
+
+    def capture_graphs(self):
+        torch.cuda.synchronize(self.dev)
+        s = torch.cuda.Stream(self.dev)
+        extra = [torch.cuda.Stream(self.dev) for _ in range(3)]
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        a, b = self.halves
+        gf, gbs = torch.cuda.CUDAGraph(), []
+        with torch.cuda.stream(s):
+            self._capture_pair(gf, s, extra, ((a.fwd, a.fwd_side), (b.fwd, b.fwd_side)))
+            start = 0
+            for end in self.segments:
+                gb = torch.cuda.CUDAGraph()
+                self._capture_pair(gb, s, extra, ((a.bwd[start:end], a.bwd_side[start:end]),
+                                                  (b.bwd[start:end], b.bwd_side[start:end])))
+                gbs.append(gb)
+                start = end
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph_fwd, self.graph_bwd = gf, gbs
+
+    def capture_gemm_only(self):
+        """Tensor-core launches of one step (both halves, concurrently on two streams as in the real step)."""
+        torch.cuda.synchronize(self.dev)
+        s, s1 = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        g = torch.cuda.CUDAGraph()
+        n = 0
+
+        def gemms(e):
+            k = 0
+            for op, is_gemm in list(zip(e.fwd, e.fwd_is_gemm)) + list(zip(e.bwd, e.bwd_is_gemm)):
+                if is_gemm:
+                    op()
+                    k += 1
+            return k
+
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                fork = torch.cuda.Event()
+                fork.record(s)
+                s1.wait_event(fork)
+                with torch.cuda.stream(s1):
+                    n += gemms(self.halves[1])
+                    done = torch.cuda.Event()
+                    done.record(s1)
+                n += gemms(self.halves[0])
+                s.wait_event(done)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         return g, n

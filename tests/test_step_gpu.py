@@ -151,3 +151,47 @@ def test_fused_adamw_arena_path_matches_torch_adamw():
     # 2 * steps * lr = 6e-3, while the bulk of the parameters must agree closely
     assert worst <= 6.5e-3, worst
     assert total / count < 1e-4, total / count
+
+
+def test_dual_chain_engine_matches_oracle_and_single_chain(monkeypatch):
+    """SD2_DUAL_CHAIN=1: B = 8 runs as two concurrent half-batch chains (DualEngine): same loss and gradients as the oracle, and the same
+    gradients as the single-chain engine up to summation order - eagerly and through the 4-stream CUDA graphs."""
+    from diffusion_b200.engine import DualEngine, Engine
+    from oracle.stable_diffusion import train_step
+    from oracle.unet import TINY_UNET_CONFIG
+    monkeypatch.setenv('SD2_DUAL_CHAIN', '1')
+    oracle, model, batch = _pair(TINY_UNET_CONFIG, 8, 16)
+    torch.manual_seed(11)
+    out = model(batch)
+    loss = model.loss(out, batch)
+    loss.backward()
+    eng = model._last_engine
+    assert isinstance(eng, DualEngine)
+    g_dual = {n: p.grad.detach().clone() for n, p in model.unet.named_parameters()}
+    b32 = {k: v.float() for k, v in batch.items()}
+    l32, _ = train_step(oracle, b32, timesteps=out[2], noise=out[1].float())
+    assert abs(loss.item() - l32.item()) <= 1e-2 * abs(l32.item())
+    cos = _cosines(model, oracle)
+    assert min(cos.values()) > 0.99 and sum(cos.values()) / len(cos) > 0.999
+    # graph replay of the dual engine
+    model.unet.zero_grad(set_to_none=True)
+    eng.capture_graphs()
+    torch.manual_seed(11)
+    out2 = model(batch)
+    loss2 = model.loss(out2, batch)
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) <= 1e-3 * abs(loss.item())
+    for n, p in model.unet.named_parameters():
+        c = F.cosine_similarity(p.grad.flatten().float(), g_dual[n].flatten().float(), dim=0).item()
+        assert c > 0.9995, (n, c)
+    # single chain on the same inputs
+    monkeypatch.delenv('SD2_DUAL_CHAIN')
+    _, model_s, _ = _pair(TINY_UNET_CONFIG, 8, 16)
+    torch.manual_seed(11)
+    out_s = model_s(batch)
+    model_s.loss(out_s, batch).backward()
+    assert isinstance(model_s._last_engine, Engine)
+    assert torch.equal(out_s[1], out[1]) and torch.equal(out_s[2], out[2])
+    for n, p in model_s.unet.named_parameters():
+        c = F.cosine_similarity(p.grad.flatten().float(), g_dual[n].flatten().float(), dim=0).item()
+        assert c > 0.999, (n, c)
