@@ -5,7 +5,11 @@
                                                            # on the box's host cores (the reference itself has no
                                                            # installable stack here: diffusers/composer are absent)
 A step = StableDiffusion.forward (K1 + UNet) + loss + backward + gradient all-reduce (N>1) + AdamW step on one
-microbatch of 16 synthetic latents per GPU (SD-2-base-256: 32x32x4 latents, 77x1024 context, bf16, random init).
+microbatch of synthetic latents per GPU (SD-2-base-256: 32x32x4 latents, 77x1024 context, bf16, random init).
+Per-GPU microbatch: the reference recipe trains with a device batch of 256 (global 2048 / 8 GPUs,
+yamls/hydra-yamls/SD-2-base-256.yaml:2,87) cut into microbatches of 16 to fit 40/80 GB parts; microbatching does not
+change the optimizer step (GroupNorm is per sample, the loss is a mean), so on 180 GB B200s the default here is 128
+(two microbatches per device batch; --batch 16 reproduces the yaml's value).  The optimizer still runs every step.
 One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for the roofline arithmetic.
 """
 import argparse
@@ -104,7 +108,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    batch = 1  # bounded sample of the 16-image microbatch so that K steps end within minutes on host cores
+    batch = 1  # bounded sample of the microbatch so that K steps end within minutes on host cores
     val, s_per_step = oracle_cpu_step_rate(args.latent, batch, args.steps, max(1, min(args.warmup, 1)), cores)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
@@ -113,7 +117,7 @@ def run_reference(args):
         'config': {'workload': f'SD-2-base-{args.latent * 8} UNet train step (fwd+loss+bwd), oracle restatement on CPU',
                    'latent': [4, args.latent, args.latent], 'context': [77, 1024]},
         'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{args.steps} steps of batch {batch} (of the 16-image microbatch), fp32, torch {torch.__version__}'},
+                         'sample': f'{args.steps} steps of batch {batch} (of the {args.batch}-image microbatch), fp32, torch {torch.__version__}'},
         'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -225,7 +229,7 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         v, s_per = oracle_cpu_step_rate(R, 2, 2, 1, cores)
         cpu = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': f'2 timed steps of batch 2 (of the 16-image microbatch) after 1 warm-up, fp32 oracle, {s_per:.2f} s/step'}
+               'sample': f'2 timed steps of batch 2 (of the {B}-image microbatch) after 1 warm-up, fp32 oracle, {s_per:.2f} s/step'}
     imgs = B * world * args.steps
     line = {
         'metric': METRIC, 'value': imgs / (ms_dev * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
@@ -235,7 +239,7 @@ def run_ours(args):
                                f'precomputed latents, random init', 'per_gpu_microbatch': B, 'global_batch': B * world,
                    'latent': [4, R, R], 'context': [77, 1024], 'params': 865910724, 'parallelism': f'dp{world}',
                    'cuda_graphs': not args.no_graphs,
-                   'l2': 'no explicit flush: every step streams 3.5 GB of fp32 parameters + optimizer state and >10 GB of '
+                   'l2': 'no explicit flush: every step streams 3.5 GB of fp32 parameters + optimizer state and tens of GB of '
                          'activations, far beyond the 126 MB L2'},
         'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': (lat_h.numel() + ctx_h.numel()) * 2, 'd2h_bytes_per_step': 4},
@@ -254,10 +258,13 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--latent', type=int, default=32, help='latent side: 32 = SD-2-base-256 (default), 64 = SD-2-base-512')
-    ap.add_argument('--batch', type=int, default=16, help='per-GPU microbatch (reference yaml: 16)')
+    ap.add_argument('--batch', type=int, default=None,
+                    help='per-GPU microbatch (default 128 at 256^2, 32 at 512^2; the reference yaml uses 16 on 40/80 GB GPUs)')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 128 if args.latent <= 32 else 32
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -558,7 +558,17 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
   float* gstat = ws + (long long)B * GN_MAXP * C * 2;
   launch_k(gn_bwd_stats_kernel, dim3(grid), dim3(GN_THREADS), red_smem, stream, reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, ws, HW, C, G, silu);
-  launch_k(gn_bwd_reduce_kernel, dim3(G), dim3(256), (size_t)B * (C / G) * 2 * sizeof(float), stream, ws, gamma, gstat, dgamma, dbeta, B, P, C, G);
+  const size_t t_smem = (size_t)B * (C / G) * 2 * sizeof(float);
+  if (t_smem > 48 * 1024) {  // large per-GPU batches: opt in to more than the default 48 KB of dynamic shared memory
+    static size_t opted = 0;
+    if (t_smem > 227 * 1024) return fail(ctx, "sd2_groupnorm_bwd: B * C / G too large for the per-group reduction");
+    if (t_smem > opted) {
+      if (cudaFuncSetAttribute(gn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return fail(ctx, "sd2_groupnorm_bwd: cannot raise the shared-memory limit");
+      opted = 227 * 1024;
+    }
+  }
+  launch_k(gn_bwd_reduce_kernel, dim3(G), dim3(256), t_smem, stream, ws, gamma, gstat, dgamma, dbeta, B, P, C, G);
   launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(dy), lddy,
                                                        reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, gstat,
                                                        reinterpret_cast<const bf16*>(dx_add), ldadd,
