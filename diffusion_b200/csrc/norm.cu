@@ -23,6 +23,13 @@ __device__ __forceinline__ void store8(bf16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// contiguous global -> shared bulk copy (no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // Pixel chunks per image: B * P blocks should fill two waves of (2 resident blocks per SM) without a ragged tail.
 static inline int gn_chunks(int HW, int B, int C, int num_sms) {
   int p = (4 * num_sms) / (B > 0 ? B : 1);
@@ -302,6 +309,376 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_apply_kernel(const bf16*
   }
 }
 
+// ---- single-pass GroupNorm backward: one thread-block CLUSTER per image
+// The two-kernel path above reads x and dy twice from HBM/L2 and evaluates the SiLU derivative twice; at the UNet's
+// shapes it ran at 1.5-2.5 TB/s and was half instruction-issue bound.  Here a cluster of NC CTAs owns one image: each
+// CTA stages its HW/NC pixels of (x, dy) in shared memory with the bulk-copy engine (NSUB sub-tiles, each with its own
+// mbarrier, so the first pass starts while later sub-tiles are still in flight),
+//   pass 1: dyh = dy * silu'(.) (written back over dy in smem as bf16 - the same rounding point as the reference's
+//           silu_backward output), per-channel sums of dyh and dyh*xhat -> block reduce -> ws[b*NC+rank][C][2]
+//           (for dgamma/dbeta) and per-group partials,
+//   cluster barrier + distributed-shared-memory reads: group sums of the whole image,
+//   pass 2: dx = rstd*(gamma*dyh - (db_g + xhat*ds_g)/n) (+dx_add) from the smem copy -> global.
+// x and dy cross HBM exactly once.
+static constexpr int GNC_NSUB = 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(const void* local_smem, uint32_t rank) {
+  uint32_t ra;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// d/dz [z * sigmoid(z)] = s + z*s*(1-s), sigmoid through one MUFU.TANH
+__device__ __forceinline__ float silu_grad_fast(float z) {
+  const float s = fmaf(tanh_approx(0.5f * z), 0.5f, 0.5f);
+  return fmaf(z, fmaf(-s, s, s), s);
+}
+
+struct GnClusterCfg {
+  int NC, PX, RL, threads;
+  size_t smem_bytes;
+  bool ok;
+};
+// smallest cluster whose per-CTA chunk fits: prefer <= 100 KB (two CTAs per SM), else <= 190 KB; NC = 16 needs the
+// non-portable cluster-size opt-in.
+static GnClusterCfg gn_cluster_cfg(int HW, int C, int ntensors_staged) {
+  GnClusterCfg c;
+  c.ok = false;
+  const int V = C / 8;
+  if (V > 512 || V < 1) return c;
+  // pass 0: ~256-thread CTAs with <= 110 KB of shared memory, so that two CTAs (of different images) share an SM and
+  // one's loads overlap the other's second pass; pass 1: one 512-thread CTA per SM with up to 225 KB.
+  for (int pass = 0; pass < 3 && !c.ok; ++pass) {  // pass 2: 16-CTA (non-portable) clusters, the last resort
+    const int target = pass == 0 ? 256 : 512;
+    c.RL = target / V;
+    if (c.RL < 1) c.RL = 1;
+    c.threads = ((V * c.RL + 31) / 32) * 32;
+    if (c.threads > 512) continue;
+    const size_t fixed = (size_t)c.RL * C * 2 * 4 + (size_t)C * 2 * 4 + 64 * 2 * 4 * 2 + GNC_NSUB * 8 + 256;
+    const size_t limit = pass == 0 ? 110 * 1024 : 225 * 1024;
+    for (int nc = (pass == 2 ? 16 : 1); nc <= (pass == 2 ? 16 : 8); nc *= 2) {
+      if (HW % nc != 0) break;
+      const int px = HW / nc;
+      const size_t chunk = (size_t)px * C * 2 * ntensors_staged;
+      if (chunk + fixed <= limit && px % GNC_NSUB == 0) {
+        c.NC = nc;
+        c.PX = px;
+        c.smem_bytes = chunk + fixed;
+        c.ok = true;
+        break;
+      }
+      if (px == 1) break;
+    }
+  }
+  return c;
+}
+
+template <bool SILU, bool HAS_ADD>
+__global__ void __launch_bounds__(512, 1) gn_bwd_cluster_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ stats, const bf16* __restrict__ dx_add,
+                                                                 bf16* __restrict__ dx, float* __restrict__ ws, int HW, int C,
+                                                                 int G, int PX, int RL) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const int NC = gridDim.x, rank = blockIdx.x, b = blockIdx.y;  // cluster = the NC blocks of one image
+  const int V = C / 8, cpg = C / G;
+  const size_t chunk_bytes = (size_t)PX * C * 2;
+  bf16* xs = reinterpret_cast<bf16*>(gsm);
+  bf16* dsm = reinterpret_cast<bf16*>(gsm + chunk_bytes);
+  float* red = reinterpret_cast<float*>(gsm + 2 * chunk_bytes);  // [RL][C][2]
+  float* chan = red + (size_t)RL * C * 2;                        // [C][2]
+  float2* gpart = reinterpret_cast<float2*>(chan + (size_t)C * 2);  // [64] this CTA's per-group partial (read by peers)
+  float2* gtot = gpart + 64;                                     // [64] whole-image (db, ds) / n
+  uint64_t* full = reinterpret_cast<uint64_t*>(gtot + 64);       // [GNC_NSUB]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < GNC_NSUB; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_grid_sync();
+  const long long pix0 = (long long)b * HW + (long long)rank * PX;
+  const int sub_px = PX / GNC_NSUB;
+  const uint32_t sub_bytes = (uint32_t)sub_px * C * 2;
+  if (tid == 0) {
+    for (int i = 0; i < GNC_NSUB; ++i) {
+      mbar_arrive_expect_tx(&full[i], 2 * sub_bytes);
+      bulk_load_1d(reinterpret_cast<uint8_t*>(xs) + (size_t)i * sub_bytes, x + (pix0 + (long long)i * sub_px) * C, sub_bytes, &full[i]);
+      bulk_load_1d(reinterpret_cast<uint8_t*>(dsm) + (size_t)i * sub_bytes, dy + (pix0 + (long long)i * sub_px) * C, sub_bytes, &full[i]);
+    }
+  }
+  const int v = tid % V, rl = tid / V;
+  const bool act = rl < RL;
+  float rs[8], nm[8], ga[8], be[8], s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s1[e] = s2[e] = 0.f;
+    rs[e] = nm[e] = ga[e] = be[e] = 0.f;
+    if (act) {
+      const int c = v * 8 + e, g = c / cpg;
+      const float mean = stats[((long long)b * G + g) * 2];
+      rs[e] = stats[((long long)b * G + g) * 2 + 1];
+      nm[e] = -mean * rs[e];
+      ga[e] = gamma[c];
+      be[e] = beta[c];
+    }
+  }
+  // ---- pass 1
+  for (int i = 0; i < GNC_NSUB; ++i) {
+    mbar_wait(&full[i], 0);
+    if (act) {
+#pragma unroll 2
+      for (int r = i * sub_px + rl; r < (i + 1) * sub_px; r += RL) {
+        float xf[8], df[8];
+        load8(xs + (size_t)r * C + v * 8, xf);
+        load8(dsm + (size_t)r * C + v * 8, df);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = fmaf(xf[e], rs[e], nm[e]);
+          if (SILU) df[e] *= silu_grad_fast(fmaf(xh, ga[e], be[e]));
+          s1[e] += df[e];
+          s2[e] = fmaf(df[e], xh, s2[e]);
+        }
+        if (SILU) store8(dsm + (size_t)r * C + v * 8, df);
+      }
+    }
+  }
+  // ---- block reduce over the RL row lanes -> chan[c] = (sum dyh, sum dyh*xhat)
+  if (act) {
+    float* o = red + ((size_t)rl * C + v * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) *reinterpret_cast<float4*>(o + 2 * e) = make_float4(s1[e], s2[e], s1[e + 1], s2[e + 1]);
+  }
+  __syncthreads();
+  {
+    float* wo = ws + ((long long)b * NC + rank) * C * 2;
+    for (int i = tid; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < RL; ++r) t += red[(size_t)r * 2 * C + i];
+      chan[i] = t;
+      wo[i] = t;
+    }
+  }
+  __syncthreads();
+  if (tid < G) {
+    float dbv = 0.f, dsv = 0.f;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+      const float gm = gamma[c];
+      dbv = fmaf(gm, chan[c * 2], dbv);
+      dsv = fmaf(gm, chan[c * 2 + 1], dsv);
+    }
+    gpart[tid] = make_float2(dbv, dsv);
+  }
+  cluster_sync_all();  // every CTA's gpart is published
+  if (tid < G) {
+    float dbv = 0.f, dsv = 0.f;
+    for (int r = 0; r < NC; ++r) {
+      const float2 t = ld_dsmem_f2(&gpart[tid], (uint32_t)r);
+      dbv += t.x;
+      dsv += t.y;
+    }
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    gtot[tid] = make_float2(dbv * inv_n, dsv * inv_n);
+  }
+  __syncthreads();
+  // ---- pass 2
+  if (act) {
+    float a[8], k1[8], k2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int g = (v * 8 + e) / cpg;
+      const float2 t = gtot[g];
+      a[e] = rs[e] * ga[e];
+      k1[e] = -rs[e] * t.x;
+      k2[e] = -rs[e] * t.y;
+    }
+    const bf16* ab = HAS_ADD ? dx_add + pix0 * C + v * 8 : nullptr;
+    bf16* ob = dx + pix0 * C + v * 8;
+#pragma unroll 4
+    for (int r = rl; r < PX; r += RL) {
+      float xf[8], df[8], o[8];
+      if (HAS_ADD) load8(ab + (size_t)r * C, o);
+      load8(xs + (size_t)r * C + v * 8, xf);
+      load8(dsm + (size_t)r * C + v * 8, df);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = fmaf(xf[e], rs[e], nm[e]);
+        float t = fmaf(df[e], a[e], k1[e]);
+        t = fmaf(xh, k2[e], t);
+        o[e] = HAS_ADD ? o[e] + t : t;
+      }
+      store8(ob + (size_t)r * C, o);
+    }
+  }
+  cluster_sync_all();  // no CTA of the cluster exits while a peer may still read its gpart
+}
+
+// ---- single-pass GroupNorm forward on the same cluster skeleton: x crosses HBM once (staged in smem), statistics are
+// combined over the cluster through distributed shared memory, y = [silu](x*scale + shift) is written from the smem copy.
+template <bool SILU>
+__global__ void __launch_bounds__(512, 1) gn_fwd_cluster_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, bf16* __restrict__ y,
+                                                                 float* __restrict__ stats, int HW, int C, int G, int PX, int RL,
+                                                                 float eps) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const int NC = gridDim.x, rank = blockIdx.x, b = blockIdx.y;
+  const int V = C / 8, cpg = C / G;
+  const size_t chunk_bytes = (size_t)PX * C * 2;
+  bf16* xs = reinterpret_cast<bf16*>(gsm);
+  float* red = reinterpret_cast<float*>(gsm + chunk_bytes);  // [RL][C][2]
+  float* chan = red + (size_t)RL * C * 2;                    // [C][2]
+  float2* gpart = reinterpret_cast<float2*>(chan + (size_t)C * 2);
+  float2* gtot = gpart + 64;                                 // [64] (mean, rstd)
+  uint64_t* full = reinterpret_cast<uint64_t*>(gtot + 64);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < GNC_NSUB; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_grid_sync();
+  const long long pix0 = (long long)b * HW + (long long)rank * PX;
+  const int sub_px = PX / GNC_NSUB;
+  const uint32_t sub_bytes = (uint32_t)sub_px * C * 2;
+  if (tid == 0) {
+    for (int i = 0; i < GNC_NSUB; ++i) {
+      mbar_arrive_expect_tx(&full[i], sub_bytes);
+      bulk_load_1d(reinterpret_cast<uint8_t*>(xs) + (size_t)i * sub_bytes, x + (pix0 + (long long)i * sub_px) * C, sub_bytes, &full[i]);
+    }
+  }
+  const int v = tid % V, rl = tid / V;
+  const bool act = rl < RL;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+  for (int i = 0; i < GNC_NSUB; ++i) {
+    mbar_wait(&full[i], 0);
+    if (act) {
+#pragma unroll 4
+      for (int r = i * sub_px + rl; r < (i + 1) * sub_px; r += RL) {
+        float xf[8];
+        load8(xs + (size_t)r * C + v * 8, xf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s1[e] += xf[e];
+          s2[e] = fmaf(xf[e], xf[e], s2[e]);
+        }
+      }
+    }
+  }
+  if (act) {
+    float* o = red + ((size_t)rl * C + v * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) *reinterpret_cast<float4*>(o + 2 * e) = make_float4(s1[e], s2[e], s1[e + 1], s2[e + 1]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < RL; ++r) t += red[(size_t)r * 2 * C + i];
+    chan[i] = t;
+  }
+  __syncthreads();
+  if (tid < G) {
+    float a = 0.f, q = 0.f;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+      a += chan[c * 2];
+      q += chan[c * 2 + 1];
+    }
+    gpart[tid] = make_float2(a, q);
+  }
+  cluster_sync_all();
+  if (tid < G) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < NC; ++r) {
+      const float2 t = ld_dsmem_f2(&gpart[tid], (uint32_t)r);
+      a += t.x;
+      q += t.y;
+    }
+    const float n = (float)cpg * (float)HW;
+    const float mean = a / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    gtot[tid] = make_float2(mean, rstd);
+    if (rank == 0) *reinterpret_cast<float2*>(stats + ((long long)b * G + tid) * 2) = make_float2(mean, rstd);
+  }
+  __syncthreads();
+  if (act) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      const float2 t = gtot[c / cpg];
+      sc[e] = gamma[c] * t.y;
+      sh[e] = beta[c] - t.x * sc[e];
+    }
+    bf16* ob = y + pix0 * C + v * 8;
+#pragma unroll 4
+    for (int r = rl; r < PX; r += RL) {
+      float xf[8];
+      load8(xs + (size_t)r * C + v * 8, xf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float z = fmaf(xf[e], sc[e], sh[e]);
+        xf[e] = SILU ? silu_f(z) : z;
+      }
+      store8(ob + (size_t)r * C, xf);
+    }
+  }
+  cluster_sync_all();
+}
+
+template <typename... P, typename... A>
+static cudaError_t launch_cluster(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, int cluster_x, cudaStream_t stream,
+                                  A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(std::forward<A>(args))...);
+}
+
+template <bool SILU, bool HAS_ADD>
+static cudaError_t launch_gn_bwd_cluster(const GnClusterCfg& c, int B, cudaStream_t stream, const bf16* dy, const bf16* x,
+                                         const float* gamma, const float* beta, const float* stats, const bf16* dx_add,
+                                         bf16* dx, float* ws, int HW, int C, int G) {
+  auto kern = gn_bwd_cluster_kernel<SILU, HAS_ADD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_cluster(kern, dim3(c.NC, B), dim3(c.threads), c.smem_bytes, c.NC, stream, dy, x, gamma, beta, stats, dx_add, dx,
+                        ws, HW, C, G, c.PX, c.RL);
+}
+
 // dgamma[c] += sum_i ws[i][c][1], dbeta[c] += sum_i ws[i][c][0] over `n_part` partial slabs.
 // grid (ceil(C/32)), block (32 channels, 8 partial lanes): coalesced float2 reads, smem tree over the 8 lanes.
 __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C,
@@ -405,123 +782,193 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
   }
 }
 
-// one warp per row; per-block partial (dbeta, dgamma) -> ws[block][C][2]
-template <int NV>
-__global__ void __launch_bounds__(256, (NV <= 2 ? 2 : 1)) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                                        const float* __restrict__ gamma,
-                                                                        const float* __restrict__ stats,
-                                                                        const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
-                                                                        float* __restrict__ ws, long long rows, int C) {
-  pdl_grid_sync();
-  extern __shared__ float sm[];  // [C][2]
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+// ---- LayerNorm backward: persistent CTAs over row tiles staged in shared memory by the bulk-copy engine
+// A tile is R consecutive rows = one contiguous byte range of x, dy (and dx_add), so each operand of a tile is ONE
+// cp.async.bulk (no tensor map); LN_STAGES tiles are in flight per SM, which is what keeps HBM busy - the previous
+// warp-per-row kernel had one row per warp in flight and ran at 1.6 TB/s.  Per tile:
+//   phase 1 (warp per row)           : c1 = mean(dy*gamma), c2 = mean(dy*gamma*xhat) -> smem
+//   phase 2 (thread per 8 channels)  : dx = rstd*(dy*gamma - c1 - xhat*c2) (+dx_add) -> global; dgamma/dbeta partials in
+//                                      16 registers per thread (each thread owns 8 fixed channels, RL row lanes)
+// then one block-level reduction of the partials -> ws[block][C][2] (summed by affine_grad_reduce_kernel).
+static constexpr int LN_STAGES = 3;
+
+
+struct LnTileCfg {
+  int R, RL, threads, ntens;
+  size_t tile_bytes, stage_bytes, body_bytes, smem_bytes;
+};
+// R = 2 * RL rows per tile: every thread owns 8 channels of exactly two rows, which it keeps unpacked in registers
+// between the two phases.
+static LnTileCfg ln_tile_cfg(int C, bool has_add) {
+  LnTileCfg c;
   const int V = C / 8;
+  c.RL = 512 / V;
+  if (c.RL > 32) c.RL = 32;
+  if (c.RL < 1) c.RL = 1;
+  c.R = 2 * c.RL;
+  c.threads = ((V * c.RL + 31) / 32) * 32;
+  c.ntens = has_add ? 3 : 2;
+  c.tile_bytes = (size_t)c.R * C * 2;
+  c.stage_bytes = c.tile_bytes * c.ntens + (size_t)c.R * 8;
+  const size_t red_bytes = (size_t)c.RL * C * 2 * sizeof(float);
+  c.body_bytes = c.stage_bytes * LN_STAGES;
+  if (c.body_bytes < red_bytes) c.body_bytes = red_bytes;
+  c.body_bytes = (c.body_bytes + 127) & ~(size_t)127;
+  // + part[R][V] float2, rowk[R] float2, barriers
+  c.smem_bytes = c.body_bytes + (size_t)c.R * V * 8 + (size_t)c.R * 8 + 64;
+  return c;
+}
+
+template <bool HAS_ADD>
+__global__ void __launch_bounds__(512, 1) ln_bwd_tile_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                              const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                              const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
+                                                              float* __restrict__ ws, long long rows, int C, int RL,
+                                                              unsigned body_bytes) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  constexpr int NT = HAS_ADD ? 3 : 2;
+  const int V = C / 8, R = 2 * RL;
+  const unsigned tile_bytes = (unsigned)R * C * 2;
+  const unsigned stage_bytes = tile_bytes * NT + (unsigned)R * 8;
+  float2* part = reinterpret_cast<float2*>(ln_smem + body_bytes);        // [R][V] per-thread partial (sum g, sum g*(x-mean))
+  float2* rowk = part + (size_t)R * V;                                   // [R] (rstd*c1, rstd*c2)
+  uint64_t* full = reinterpret_cast<uint64_t*>(rowk + R);                // [LN_STAGES]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const long long tiles = (rows + R - 1) / R;
   const float invC = 1.f / (float)C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+
+  if (tid == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
-  float ag[NV][8], ab[NV][8];
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) ag[j][e] = ab[j][e] = 0.f;
-  uint4 nx[NV], nd[NV], na[NV];
-  float2 nst = make_float2(0.f, 0.f);
-  if (warp < rows) {
-    nst = *reinterpret_cast<const float2*>(stats + warp * 2);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = lane + 32 * j;
-      if (v < V) {
-        nx[j] = *reinterpret_cast<const uint4*>(x + warp * C + v * 8);
-        nd[j] = *reinterpret_cast<const uint4*>(dy + warp * C + v * 8);
-        if (dx_add) na[j] = *reinterpret_cast<const uint4*>(dx_add + warp * C + v * 8);
-      }
+  pdl_grid_sync();
+
+  auto issue = [&](long long tile, int s) {  // thread 0 only
+    const long long row0 = tile * R;
+    const int rt = (int)((rows - row0) < R ? (rows - row0) : R);
+    const uint32_t tb = (uint32_t)rt * C * 2, sb = (uint32_t)((rt & ~1) * 8);
+    uint8_t* st = ln_smem + (size_t)s * stage_bytes;
+    mbar_arrive_expect_tx(&full[s], tb * NT + sb);
+    bulk_load_1d(st, x + row0 * C, tb, &full[s]);
+    bulk_load_1d(st + tile_bytes, dy + row0 * C, tb, &full[s]);
+    if (HAS_ADD) bulk_load_1d(st + 2 * tile_bytes, dx_add + row0 * C, tb, &full[s]);
+    if (sb) bulk_load_1d(st + NT * tile_bytes, stats + row0 * 2, sb, &full[s]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) {
+      const long long t = blockIdx.x + (long long)s * gridDim.x;
+      if (t < tiles) issue(t, s);
     }
   }
-  for (long long row = warp; row < rows; row += nwarps) {
-    const float mean = nst.x, rstd = nst.y;
-    float xh[NV][8], g[NV][8];
-    uint4 ca[NV];
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = lane + 32 * j;
-      if (v < V) {
-        float d[8];
-        unpack8(nx[j], xh[j]);
-        unpack8(nd[j], d);
-        ca[j] = na[j];
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
-        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          xh[j][e] = (xh[j][e] - mean) * rstd;
-          g[j][e] = d[e] * gv[e];
-          c1 += g[j][e];
-          c2 += g[j][e] * xh[j][e];
-          ab[j][e] += d[e];
-          ag[j][e] += d[e] * xh[j][e];
-        }
-      }
+
+  const int v = tid % V, rl = tid / V;
+  const bool p2 = rl < RL;
+  float gv[8], ag[8], ab[8];
+  {
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    if (p2) {
+      g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+      g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
     }
-    if (row + nwarps < rows) {  // next row's operands: in flight during the reductions below
-      const long long nr = row + nwarps;
-      nst = *reinterpret_cast<const float2*>(stats + nr * 2);
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int v = lane + 32 * j;
-        if (v < V) {
-          nx[j] = *reinterpret_cast<const uint4*>(x + nr * C + v * 8);
-          nd[j] = *reinterpret_cast<const uint4*>(dy + nr * C + v * 8);
-          if (dx_add) na[j] = *reinterpret_cast<const uint4*>(dx_add + nr * C + v * 8);
-        }
-      }
-    }
-    c1 = warp_sum(c1) * invC;
-    c2 = warp_sum(c2) * invC;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = lane + 32 * j;
-      if (v < V) {
-        float o[8];
-        if (dx_add) unpack8(ca[j], o);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float t = rstd * (g[j][e] - c1 - xh[j][e] * c2);
-          o[e] = dx_add ? o[e] + t : t;
-        }
-        store8(dx + row * C + v * 8, o);
-      }
-    }
+    gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
   }
-  // block-level sum of the per-warp partials: warps take turns adding into shared memory (each lane owns distinct
-  // channels, so the read-modify-writes are conflict-free and need no atomics)
-  for (int wturn = 0; wturn < (int)(blockDim.x >> 5); ++wturn) {
-    if ((int)(threadIdx.x >> 5) == wturn) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int v = lane + 32 * j;
-        if (v < V) {
+  for (int e = 0; e < 8; ++e) ag[e] = ab[e] = 0.f;
+
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long row0 = tile * R;
+    const int rt = (int)((rows - row0) < R ? (rows - row0) : R);
+    const uint8_t* st = ln_smem + (size_t)s * stage_bytes;
+    const float2* sts = reinterpret_cast<const float2*>(st + NT * tile_bytes);
+    mbar_wait(&full[s], ph);
+    // ---- A: every thread unpacks its 8 channels of its two rows once and publishes the row-sum partials
+    float xf[2][8], df[2][8];
+    float2 mr[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            sm[(v * 8 + e) * 2] += ab[j][e];
-            sm[(v * 8 + e) * 2 + 1] += ag[j][e];
-          }
+    for (int j = 0; j < 2; ++j) {
+      const int r = rl + j * RL;
+      if (p2 && r < rt) {
+        if ((rt & 1) && r == rt - 1) mr[j] = *reinterpret_cast<const float2*>(stats + (row0 + r) * 2);  // odd tail row
+        else mr[j] = sts[r];
+        load8(reinterpret_cast<const bf16*>(st) + (size_t)r * C + v * 8, xf[j]);
+        load8(reinterpret_cast<const bf16*>(st + tile_bytes) + (size_t)r * C + v * 8, df[j]);
+        float p1 = 0.f, pq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float g = df[j][e] * gv[e];
+          p1 += g;
+          pq += g * (xf[j][e] - mr[j].x);
         }
+        part[(size_t)r * V + v] = make_float2(p1, pq);
       }
     }
     __syncthreads();
+    // ---- B: one warp per row sums the V partials
+    for (int r = warp; r < rt; r += nwarps) {
+      float a1 = 0.f, a2 = 0.f;
+      for (int vv = lane; vv < V; vv += 32) {
+        const float2 t = part[(size_t)r * V + vv];
+        a1 += t.x;
+        a2 += t.y;
+      }
+      a1 = warp_sum(a1);
+      a2 = warp_sum(a2);
+      if (lane == 0) {
+        float rstd;
+        if ((rt & 1) && r == rt - 1) rstd = stats[(row0 + r) * 2 + 1];
+        else rstd = sts[r].y;
+        rowk[r] = make_float2(rstd * a1 * invC, rstd * rstd * a2 * invC);
+      }
+    }
+    __syncthreads();
+    // ---- C: dx = rstd*(dy*gamma) - rstd*c1 - xhat*(rstd*c2) (+dx_add); per-channel partial sums
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = rl + j * RL;
+      if (p2 && r < rt) {
+        const float2 k = rowk[r];
+        const float rstd = mr[j].y, nm = -mr[j].x * rstd;
+        float o[8];
+        if (HAS_ADD) load8(reinterpret_cast<const bf16*>(st + 2 * tile_bytes) + (size_t)r * C + v * 8, o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = fmaf(xf[j][e], rstd, nm);
+          float t = fmaf(df[j][e], gv[e] * rstd, -k.x);
+          t = fmaf(xh, -k.y, t);
+          o[e] = HAS_ADD ? o[e] + t : t;
+          ab[e] += df[j][e];
+          ag[e] = fmaf(df[j][e], xh, ag[e]);
+        }
+        store8(dx + (row0 + r) * C + v * 8, o);
+      }
+    }
+    __syncthreads();  // every thread is done with stage s, part and rowk: refill the stage with the tile LN_STAGES ahead
+    if (tid == 0) {
+      const long long nt = tile + (long long)LN_STAGES * gridDim.x;
+      if (nt < tiles) issue(nt, s);
+    }
+    if (++s == LN_STAGES) {
+      s = 0;
+      ph ^= 1u;
+    }
   }
+  // ---- block-level reduction of the partials over the RL row lanes (no copies are in flight any more)
+  float* red = reinterpret_cast<float*>(ln_smem);  // [RL][C][2]
+  if (p2) {
+    float* o = red + ((size_t)rl * C + v * 8) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) *reinterpret_cast<float4*>(o + 2 * e) = make_float4(ab[e], ag[e], ab[e + 1], ag[e + 1]);
+  }
+  __syncthreads();
   float* o = ws + (long long)blockIdx.x * C * 2;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) o[i] = sm[i];
-}
-
-static int ln_blocks(long long rows, int num_sms) {
-  long long b = (rows + 7) / 8;
-  const long long cap = (long long)num_sms * 4;  // sd2_layernorm_ws_floats is sized for 4 blocks per SM
-  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+  for (int i = tid; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < RL; ++r) t += red[(size_t)r * 2 * C + i];
+    o[i] = t;
+  }
 }
 
 }  // namespace sd2
@@ -538,6 +985,29 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
   if (!ctx) return 1;
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_fwd: unsupported C/G");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (ldx == C && ldy == C) {
+    const GnClusterCfg cc = gn_cluster_cfg(HW, C, 1);
+    if (cc.ok) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        if (cudaFuncSetAttribute(gn_fwd_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(gn_fwd_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(gn_fwd_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+            cudaFuncSetAttribute(gn_fwd_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+          return fail(ctx, "sd2_groupnorm_fwd: cannot configure the cluster kernel");
+        attr_set = true;
+      }
+      const cudaError_t e =
+          silu ? launch_cluster(gn_fwd_cluster_kernel<true>, dim3(cc.NC, B), dim3(cc.threads), cc.smem_bytes, cc.NC, stream,
+                                reinterpret_cast<const bf16*>(x), gamma, beta, reinterpret_cast<bf16*>(y), stats, HW, C, G, cc.PX,
+                                cc.RL, eps)
+               : launch_cluster(gn_fwd_cluster_kernel<false>, dim3(cc.NC, B), dim3(cc.threads), cc.smem_bytes, cc.NC, stream,
+                                reinterpret_cast<const bf16*>(x), gamma, beta, reinterpret_cast<bf16*>(y), stats, HW, C, G, cc.PX,
+                                cc.RL, eps);
+      if (e != cudaSuccess) return fail(ctx, std::string("sd2_groupnorm_fwd (cluster): ") + cudaGetErrorString(e));
+      return check_launch(ctx, "groupnorm_fwd", 1);
+    }
+  }
   const dim3 grid(gn_chunks(HW, B, C, ctx->num_sms), B);
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
   launch_k(gn_stats_kernel, dim3(grid), dim3(GN_THREADS), red_smem, stream, reinterpret_cast<const bf16*>(x), ldx, ws, HW, C, G);
@@ -553,6 +1023,23 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
   if (!ctx) return 1;
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_bwd: unsupported C/G");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (ldx == C && lddy == C && lddx == C && (dx_add == nullptr || ldadd == C)) {
+    const GnClusterCfg cc = gn_cluster_cfg(HW, C, 2);
+    if (cc.ok) {  // single-pass cluster kernel + the dgamma/dbeta reduction over the B * NC per-CTA slabs
+      const bf16* dyp = reinterpret_cast<const bf16*>(dy);
+      const bf16* xp = reinterpret_cast<const bf16*>(x);
+      const bf16* ap = reinterpret_cast<const bf16*>(dx_add);
+      bf16* dxp = reinterpret_cast<bf16*>(dx);
+      cudaError_t e;
+      if (silu && ap) e = launch_gn_bwd_cluster<true, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
+      else if (silu) e = launch_gn_bwd_cluster<true, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
+      else if (ap) e = launch_gn_bwd_cluster<false, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
+      else e = launch_gn_bwd_cluster<false, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
+      if (e != cudaSuccess) return fail(ctx, std::string("sd2_groupnorm_bwd (cluster): ") + cudaGetErrorString(e));
+      launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta);
+      return check_launch(ctx, "groupnorm_bwd", 2);
+    }
+  }
   const int P = gn_chunks(HW, B, C, ctx->num_sms);
   const dim3 grid(P, B);
   const size_t red_smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
@@ -591,22 +1078,34 @@ int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const flo
   return check_launch(ctx, "layernorm_fwd");
 }
 
-long long sd2_layernorm_ws_floats(long long rows, int C) { return (long long)148 * 4 * C * 2; }
+long long sd2_layernorm_ws_floats(long long rows, int C) { return (long long)148 * 4 * C * 2; }  // >= one [C][2] slab per CTA
 
 int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* gamma, const float* stats,
                       const void* dx_add, void* dx, float* dgamma, float* dbeta, float* ws, long long rows, int C,
                       sd2_stream stream_) {
   if (!ctx) return 1;
-  if (C % 8 != 0 || C > LN_MAXV * 256) return fail(ctx, "sd2_layernorm_bwd: unsupported C");
+  if (C % 8 != 0 || C < 8) return fail(ctx, "sd2_layernorm_bwd: unsupported C");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int blocks = ln_blocks(rows, ctx->num_sms);
-  const int nv = (C / 8 + 31) / 32;
-#define LN_BWD(NV)                                                                                                        \
-  launch_k(ln_bwd_kernel<NV>, dim3(blocks), dim3(256), 2 * C * sizeof(float), stream, reinterpret_cast<const bf16*>(dy),   \
-           reinterpret_cast<const bf16*>(x), gamma, stats, reinterpret_cast<const bf16*>(dx_add),                          \
-           reinterpret_cast<bf16*>(dx), ws, rows, C)
-  if (nv == 1) LN_BWD(1); else if (nv == 2) LN_BWD(2); else if (nv == 3) LN_BWD(3); else if (nv == 4) LN_BWD(4); else LN_BWD(5);
-#undef LN_BWD
+  if (C / 8 > 512) return fail(ctx, "sd2_layernorm_bwd: C > 4096 unsupported");
+  const LnTileCfg cfg = ln_tile_cfg(C, dx_add != nullptr);
+  if (cfg.smem_bytes > 227 * 1024) return fail(ctx, "sd2_layernorm_bwd: tile does not fit in shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(ln_bwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(ln_bwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail(ctx, "sd2_layernorm_bwd: cannot raise the shared-memory limit");
+    attr_set = true;
+  }
+  const long long tiles = (rows + cfg.R - 1) / cfg.R;
+  const int blocks = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  if (dx_add)
+    launch_k(ln_bwd_tile_kernel<true>, dim3(blocks), dim3(cfg.threads), cfg.smem_bytes, stream,
+             reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,
+             reinterpret_cast<const bf16*>(dx_add), reinterpret_cast<bf16*>(dx), ws, rows, C, cfg.RL, (unsigned)cfg.body_bytes);
+  else
+    launch_k(ln_bwd_tile_kernel<false>, dim3(blocks), dim3(cfg.threads), cfg.smem_bytes, stream,
+             reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,
+             reinterpret_cast<const bf16*>(dx_add), reinterpret_cast<bf16*>(dx), ws, rows, C, cfg.RL, (unsigned)cfg.body_bytes);
   launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, ws, blocks, C, dgamma, dbeta);
   return check_launch(ctx, "layernorm_bwd", 2);
 }

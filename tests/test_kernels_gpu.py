@@ -274,7 +274,8 @@ def test_groupnorm(ctx, B, HW, Cc, silu):
     close(db, beta.grad, rtol=1e-2, atol=1e-2 * beta.grad.abs().max().item(), name='gn dbeta')
 
 
-@pytest.mark.parametrize('rows,Cc', [(16384, 320), (4096, 640), (1024, 1280), (2048, 64), (32, 256)])
+@pytest.mark.parametrize('rows,Cc', [(16384, 320), (4096, 640), (1024, 1280), (2048, 64), (32, 256), (231, 320), (77, 640), (5, 1280),
+                                     (1000, 1280)])
 def test_layernorm(ctx, rows, Cc):
     from diffusion_b200 import ops
     x = (bf(rows, Cc, seed=1).float() * 2 + 0.5).to(torch.bfloat16)

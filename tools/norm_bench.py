@@ -17,7 +17,8 @@ def bf(*shape):
 
 def cases(ctx):
     out = []
-    for B, HW, C in [(16, 1024, 320), (16, 4096, 320), (16, 1024, 640), (16, 256, 1280), (16, 64, 1280), (16, 16, 2560)]:
+    for B, HW, C in [(16, 1024, 320), (64, 1024, 320), (16, 4096, 320), (64, 1024, 640), (64, 256, 640), (64, 64, 1280), (64, 16, 1280),
+                     (64, 256, 1920), (16, 16, 2560)]:
         x, y, dy, dx = bf(B * HW, C), bf(B * HW, C), bf(B * HW, C), bf(B * HW, C)
         gamma, beta = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
         dg, db = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
