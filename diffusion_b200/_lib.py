@@ -81,7 +81,8 @@ class GemmDesc(C.Structure):
                 ('ldo', C.c_longlong), ('out_nb0', C.c_int), ('out_bs0', C.c_longlong), ('out_bs1', C.c_longlong),
                 ('residual', C.c_void_p), ('ldr', C.c_longlong), ('bias', C.c_void_p), ('rowbias', C.c_void_p),
                 ('rows_per_group', C.c_int), ('ld_rowbias', C.c_longlong), ('alpha', C.c_float),
-                ('workspace', C.c_void_p), ('workspace_bytes', C.c_longlong), ('max_splits', C.c_int)]
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_longlong), ('max_splits', C.c_int), ('force_bn', C.c_int),
+                ('force_splits', C.c_int)]
 
 
 GEMM_PLAIN, GEMM_CONV, GEMM_CONV_WGRAD = 0, 1, 2

@@ -233,6 +233,20 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     }
     if (kb < 1 || nbatch < 1) return fail(ctx, "sd2_gemm: empty contraction / batch");
     plan_gemm(ctx, d, p.N, kb, nbatch, bmn, direct_store, &BN, &splits);
+    // measured plan (tools/autotune_gemm.py -> diffusion_b200/gemm_plans.json) overrides the cycle model
+    if (d->force_bn == 256 || d->force_bn == 128 || d->force_bn == 64 || (d->force_bn == 160 && !bmn)) BN = d->force_bn;
+    if (d->force_splits > 0) {
+      long long smax = kb;
+      if (direct_store) {
+        if (nbatch != 1 || d->workspace == nullptr) smax = 1;
+        else {
+          const long long per_split = (long long)d->M * p.N * 4;
+          if (per_split > 0 && d->workspace_bytes / per_split < smax) smax = d->workspace_bytes / per_split;
+        }
+      }
+      if (smax < 1) smax = 1;
+      splits = d->force_splits < smax ? d->force_splits : (int)smax;
+    }
   }
 
   if (d->kind == SD2_GEMM_PLAIN) {
@@ -303,6 +317,20 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   p.nt = (p.N + BN - 1) / BN;
   p.batches = batches;
   p.splits = splits;
+  {
+    // Item order = L2 sharing pattern of the concurrently running CTAs.  Weights always fit in the 126 MB L2, so
+    // forward / dgrad walk n fastest (every activation tile crosses HBM once instead of once per n tile); the conv
+    // weight gradient runs the 9 taps of one K range together (dy and x cross HBM once instead of 9 times).
+    static int forced = -2;
+    if (forced == -2) {
+      const char* e = getenv("SD2_RASTER");
+      forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0) p.raster = forced;
+    else if (d->kind == SD2_GEMM_CONV_WGRAD) p.raster = 2;
+    else if (d->kind == SD2_GEMM_CONV) p.raster = 1;
+    else p.raster = (batches == 1 && !(a_mn && b_mn)) ? 1 : 0;
+  }
 
   CUtensorMap tmO;
   cudaError_t e;

@@ -51,12 +51,27 @@ struct WorkItem {
 };
 __device__ __forceinline__ WorkItem decode_item(const GemmKParams& p, int item) {
   WorkItem w;
-  w.m_tile = item % p.mt;
-  int t = item / p.mt;
-  w.n_tile = t % p.nt;
-  t /= p.nt;
-  w.split = t % p.splits;
-  w.batch = t / p.splits;
+  int t;
+  if (p.raster == 1) {
+    w.n_tile = item % p.nt;
+    t = item / p.nt;
+    w.m_tile = t % p.mt;
+    t /= p.mt;
+    w.split = t % p.splits;
+    w.batch = t / p.splits;
+  } else {
+    w.m_tile = item % p.mt;
+    t = item / p.mt;
+    w.n_tile = t % p.nt;
+    t /= p.nt;
+    if (p.raster == 2) {
+      w.batch = t % p.batches;
+      w.split = t / p.batches;
+    } else {
+      w.split = t % p.splits;
+      w.batch = t / p.splits;
+    }
+  }
   w.kb0 = (int)(((long long)w.split * p.total_kb) / p.splits);
   w.nkb = (int)(((long long)(w.split + 1) * p.total_kb) / p.splits) - w.kb0;
   return w;

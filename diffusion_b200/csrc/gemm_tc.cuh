@@ -21,7 +21,11 @@ struct GemmKParams {
   int M, N;            // output extent (per batch) used for load masking (stores are clipped by the output tensor map)
   int total_kb;        // number of 64-deep K blocks
   int splits;          // split-K factor
-  int mt, nt, batches; // work decomposition: items = mt * nt * splits * batches (m fastest)
+  int mt, nt, batches; // work decomposition: items = mt * nt * splits * batches
+  int raster;          // item order (what the ~148 concurrently running CTAs share through L2):
+                       //   0: m fastest, then n, split, batch      (one B slice shared, A streamed nt times)
+                       //   1: n fastest, then m, split, batch      (each A tile read once by its nt CTAs; B stays in L2)
+                       //   2: m, n, batch fastest, split slowest   (conv wgrad: the 9 taps of a K range run together)
   int kind;
   int a_batched, b_batched;  // plain operands: does the batch index move this operand?
   int a_nb0, b_nb0;          // batch -> (batch % nb0, batch / nb0) = tensor-map coords 2,3

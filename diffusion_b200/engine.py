@@ -256,6 +256,7 @@ class Engine:
     def f(self, fn, *a, side=False, **k):
         """Record a forward op.  side=True: the op is off the critical path (it only feeds later ops) and may run on the
         side stream, concurrently with the main chain; the scheduler inserts the dependencies."""
+        self._attach_plan(fn, a, k)
         self.fwd.append(partial(fn, self.ctx, *a, **k))
         self.fwd_is_gemm.append(fn in _GEMM_FUNCS)
         self.fwd_side.append(bool(side))
@@ -264,6 +265,7 @@ class Engine:
     def b(self, fn, *a, side=None, **k):
         """Record a backward op.  Weight-gradient GEMMs and bias-gradient column sums write only parameter gradients,
         which nothing reads before the end of backward: they go to the side stream by default."""
+        self._attach_plan(fn, a, k)
         op = partial(fn, self.ctx, *a, **k)
         if side is None:
             side = fn in (ops.linear_wgrad, ops.conv3x3_wgrad) or (fn is ops.colsum and self._is_param_grad(a[1]))
@@ -271,6 +273,14 @@ class Engine:
         self.bwd_is_gemm.append(fn in _GEMM_FUNCS)
         self.bwd_side.append(bool(side))
         self._count_flops(fn, a)
+
+    @staticmethod
+    def _attach_plan(fn, a, k):
+        """Measured (tile width, K split) of this GEMM shape, if tools/autotune_gemm.py has one (ops.gemm_plans)."""
+        if fn.__name__ in ops.GEMM_OPS and 'plan' not in k:
+            plan = ops.gemm_plans().get(ops.gemm_key(fn.__name__, a, k))
+            if plan is not None:
+                k['plan'] = plan
 
     def _is_param_grad(self, t):
         g = self.arena.g32

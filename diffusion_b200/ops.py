@@ -137,12 +137,53 @@ def _epilogue(d, out, ldo, out_mode, bias=None, rowbias=None, rows_per_group=1, 
     d.max_splits = 0
 
 
-def run_gemm(ctx, d):
+def run_gemm(ctx, d, plan=None):
+    """plan = (tile width BN, K splits) from the measured plan table, or None for the library's cycle model."""
+    if plan is not None:
+        d.force_bn, d.force_splits = int(plan[0]), int(plan[1])
     ctx.check(ctx.lib.sd2_gemm(ctx.h, C.byref(d), _s()))
 
 
+# ---- measured GEMM plans -----------------------------------------------------------------------------------------
+# tools/autotune_gemm.py times every distinct GEMM / conv of the static schedule under each (tile width, K split) the
+# kernel supports, on a B200, and stores the winners in gemm_plans.json next to this file.  The engine attaches the
+# plan of a recorded op (if its key is in the table) as `plan=`; unknown shapes use the library's cycle model.
+GEMM_OPS = ('linear_fwd', 'linear_dgrad', 'linear_wgrad', 'conv3x3_fwd', 'conv3x3_dgrad', 'conv3x3_wgrad')
+_PLANS = None
+
+
+def gemm_key(name, a, k):
+    """Shape signature of a recorded GEMM op: a = positional arguments after ctx, k = keyword arguments."""
+    r = int(k.get('residual') is not None)
+    if name == 'linear_fwd':
+        return f'linear_fwd|{a[0].shape[0]}|{a[1].shape[0]}|{a[0].shape[1]}|r{r}|f{int(bool(k.get("out_f32")))}'
+    if name == 'linear_dgrad':
+        return f'linear_dgrad|{a[0].shape[0]}|{a[1].shape[1]}|{a[0].shape[1]}|r{r}'
+    if name == 'linear_wgrad':
+        return f'linear_wgrad|{a[0].shape[1]}|{a[1].shape[1]}|{a[0].shape[0]}'
+    nt = len(k.get('taps') or range(9))
+    if name in ('conv3x3_fwd', 'conv3x3_dgrad'):  # (x, B, H, W, w9, out)
+        return f'{name}|{a[1]}|{a[2]}|{a[3]}|{a[4].shape[1]}|{a[4].shape[2]}|{a[0].shape[1]}|t{nt}|r{r}'
+    if name == 'conv3x3_wgrad':  # (dy, x, B, H, W, dw9)
+        return f'conv3x3_wgrad|{a[2]}|{a[3]}|{a[4]}|{a[0].shape[1]}|{a[1].shape[1]}|t{nt}'
+    return None
+
+
+def gemm_plans():
+    global _PLANS
+    if _PLANS is None:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'gemm_plans.json')
+        _PLANS = {}
+        if os.path.exists(path) and os.environ.get('SD2_NO_PLANS') != '1':
+            with open(path) as f:
+                _PLANS = {key: (v[0], v[1]) for key, v in json.load(f).items()}
+    return _PLANS
+
+
 def linear_fwd(ctx, x, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, alpha=1.0, out_f32=False,
-               workspace=None):
+               workspace=None, plan=None):
     """out[M,N] = alpha * x[M,K] @ w[N,K]^T (+bias +rowbias +residual). x, w bf16 with unit inner stride."""
     M, K = x.shape
     N = w.shape[0]
@@ -152,10 +193,10 @@ def linear_fwd(ctx, x, w, out, bias=None, residual=None, rowbias=None, rows_per_
     d.B = _operand(w, 0, K, N, w.stride(0))
     _epilogue(d, out, out.stride(0), L.OUT_F32 if out_f32 else L.OUT_BF16, bias, rowbias, rows_per_group, residual,
               residual.stride(0) if residual is not None else 0, alpha, workspace)
-    run_gemm(ctx, d)
+    run_gemm(ctx, d, plan)
 
 
-def linear_dgrad(ctx, dy, w, dx, residual=None, workspace=None):
+def linear_dgrad(ctx, dy, w, dx, residual=None, workspace=None, plan=None):
     """dx[M,K] = dy[M,N] @ w[N,K]  (w read MN-major: no transposed weight copy) (+residual)."""
     M, N = dy.shape
     K = w.shape[1]
@@ -165,10 +206,10 @@ def linear_dgrad(ctx, dy, w, dx, residual=None, workspace=None):
     d.B = _operand(w, 1, K, N, w.stride(0))
     _epilogue(d, dx, dx.stride(0), L.OUT_BF16, residual=residual, ldr=residual.stride(0) if residual is not None else 0,
               workspace=workspace)
-    run_gemm(ctx, d)
+    run_gemm(ctx, d, plan)
 
 
-def linear_wgrad(ctx, dy, x, dw):
+def linear_wgrad(ctx, dy, x, dw, plan=None):
     """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]; both operands read MN-major (contraction over rows)."""
     M, N = dy.shape
     K = x.shape[1]
@@ -177,7 +218,7 @@ def linear_wgrad(ctx, dy, x, dw):
     d.A = _operand(dy, 1, N, M, dy.stride(0))
     d.B = _operand(x, 1, K, M, x.stride(0))
     _epilogue(d, dw, dw.stride(0), L.OUT_F32_ACCUM)
-    run_gemm(ctx, d)
+    run_gemm(ctx, d, plan)
 
 
 def _conv_geom(x_ptr, n_planes, H, W, Cc, ldc, taps):
@@ -213,7 +254,7 @@ def taps_stride2_dgrad():
 
 
 def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None, taps=None, n_planes=None,
-                workspace=None):
+                workspace=None, plan=None):
     """x: bf16 [n_planes*H*W, Cin] NHWC; w9: bf16 [9, Cout, Cin]; out: bf16 [B*H*W, Cout]."""
     Cin, Cout = x.shape[1], w9.shape[1]
     d = L.GemmDesc()
@@ -222,10 +263,10 @@ def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None
     d.B = _operand(w9, 0, Cin, Cout, w9.stride(1), bs0=w9.stride(0))
     _epilogue(d, out, out.stride(0), L.OUT_BF16, bias, rowbias, H * W, residual,
               residual.stride(0) if residual is not None else 0, 1.0, workspace)
-    run_gemm(ctx, d)
+    run_gemm(ctx, d, plan)
 
 
-def conv3x3_dgrad(ctx, dy, B, H, W, w9, dx, residual=None, taps=None, n_planes=None, workspace=None):
+def conv3x3_dgrad(ctx, dy, B, H, W, w9, dx, residual=None, taps=None, n_planes=None, workspace=None, plan=None):
     """dx[B*H*W, Cin] = sum_taps shift(dy)[.., Cout] @ w9[tap'][Cout][Cin]  (weights read MN-major).
     dy may carry zero-padded channels beyond w9's Cout (conv_out: 4 real of 8)."""
     Cout, Cin = w9.shape[1], w9.shape[2]
@@ -235,10 +276,10 @@ def conv3x3_dgrad(ctx, dy, B, H, W, w9, dx, residual=None, taps=None, n_planes=N
     d.B = _operand(w9, 1, Cin, Cout, w9.stride(1), bs0=w9.stride(0))
     _epilogue(d, dx, dx.stride(0), L.OUT_BF16, residual=residual, ldr=residual.stride(0) if residual is not None else 0,
               workspace=workspace)
-    run_gemm(ctx, d)
+    run_gemm(ctx, d, plan)
 
 
-def conv3x3_wgrad(ctx, dy, x, B, H, W, dw9, taps=None, n_planes=None):
+def conv3x3_wgrad(ctx, dy, x, B, H, W, dw9, taps=None, n_planes=None, plan=None):
     """dw9[tap][Cout][Cin] (fp32) += dy[B*H*W, Cout]^T @ shift_tap(x)[.., Cin]."""
     Cout, Cin = dy.shape[1], x.shape[1]
     M = B * H * W
@@ -248,7 +289,7 @@ def conv3x3_wgrad(ctx, dy, x, B, H, W, dw9, taps=None, n_planes=None):
     d.conv = _conv_geom(x.data_ptr(), n_planes or B, H, W, Cin, x.stride(0), taps or TAPS_FWD)
     _epilogue(d, dw9, dw9.stride(1), L.OUT_F32_ACCUM)
     d.out_nb0, d.out_bs0 = 16, dw9.stride(0)
-    run_gemm(ctx, d)
+    run_gemm(ctx, d, plan)
 
 
 def bmm(ctx, A, a_mn, a_dims, B_, b_mn, b_dims, out, out_dims, M, N, K, batch, nb0, alpha=1.0, out_f32=False):

@@ -103,6 +103,8 @@ typedef struct sd2_gemm_desc {
   void* workspace;      /* split-K scratch (fp32), may be null */
   long long workspace_bytes;
   int max_splits;       /* 0 = auto */
+  int force_bn;         /* 0 = planner decides; else the tile width (256/160/128/64) from a measured plan table */
+  int force_splits;     /* 0 = planner decides; else the K-split count (clamped to what the workspace / K allow) */
 } sd2_gemm_desc;
 
 int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream);
