@@ -6,6 +6,7 @@
 // (reference diffusion/train.py:91-108) and the F.silu that follows every ResnetBlock2D GroupNorm (diffusers).
 #include "common.cuh"
 #include "host.h"
+#include <cstdlib>
 
 namespace sd2 {
 
@@ -362,14 +363,17 @@ static GnClusterCfg gn_cluster_cfg(int HW, int C, int ntensors_staged) {
   if (V > 512 || V < 1) return c;
   // pass 0: ~256-thread CTAs with <= 110 KB of shared memory, so that two CTAs (of different images) share an SM and
   // one's loads overlap the other's second pass; pass 1: one 512-thread CTA per SM with up to 225 KB.
+  // tuning overrides (tools/norm_bench.py sweeps them): SD2_GN_P0_KB = pass-0 shared-memory limit, SD2_GN_P0_THREADS
+  static const int p0_kb = getenv("SD2_GN_P0_KB") ? atoi(getenv("SD2_GN_P0_KB")) : 110;
+  static const int p0_threads = getenv("SD2_GN_P0_THREADS") ? atoi(getenv("SD2_GN_P0_THREADS")) : 256;
   for (int pass = 0; pass < 3 && !c.ok; ++pass) {  // pass 2: 16-CTA (non-portable) clusters, the last resort
-    const int target = pass == 0 ? 256 : 512;
+    const int target = pass == 0 ? p0_threads : 512;
     c.RL = target / V;
     if (c.RL < 1) c.RL = 1;
     c.threads = ((V * c.RL + 31) / 32) * 32;
     if (c.threads > 512) continue;
     const size_t fixed = (size_t)c.RL * C * 2 * 4 + (size_t)C * 2 * 4 + 64 * 2 * 4 * 2 + GNC_NSUB * 8 + 256;
-    const size_t limit = pass == 0 ? 110 * 1024 : 225 * 1024;
+    const size_t limit = pass == 0 ? (size_t)p0_kb * 1024 : 225 * 1024;
     for (int nc = (pass == 2 ? 16 : 1); nc <= (pass == 2 ? 16 : 8); nc *= 2) {
       if (HW % nc != 0) break;
       const int px = HW / nc;
@@ -680,7 +684,12 @@ static cudaError_t launch_gn_bwd_cluster(const GnClusterCfg& c, int B, cudaStrea
 }
 
 // dgamma[c] += sum_i ws[i][c][1], dbeta[c] += sum_i ws[i][c][0] over `n_part` partial slabs.
-// grid (ceil(C/32)), block (32 channels, 8 partial lanes): coalesced float2 reads, smem tree over the 8 lanes.
+// grid (ceil(C/32), slab slices), block (32 channels, 8 partial lanes): coalesced float2 reads, smem tree over the 8
+// lanes, one atomic per (channel, slice).
+static inline int affine_slices(int n_part) {  // ~32 slabs per block: 8 partial lanes x 4 loads in flight
+  const int s = (n_part + 31) / 32;
+  return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
 __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_grid_sync();
@@ -689,7 +698,20 @@ __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __
   const int c = blockIdx.x * 32 + cl;
   float a1 = 0.f, a2 = 0.f;
   if (c < C) {
-    for (int i = pl; i < n_part; i += 8) {
+    // slab i is handled by (grid row i / 8 % gridDim.y, partial lane i % 8); four independent loads in flight per thread
+    const int step = 8 * gridDim.y;
+    int i = blockIdx.y * 8 + pl;
+    for (; i + 3 * step < n_part; i += 4 * step) {
+      float2 t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = *reinterpret_cast<const float2*>(ws + ((long long)(i + j * step) * C + c) * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a1 += t[j].x;
+        a2 += t[j].y;
+      }
+    }
+    for (; i < n_part; i += step) {
       const float2 t = *reinterpret_cast<const float2*>(ws + ((long long)i * C + c) * 2);
       a1 += t.x;
       a2 += t.y;
@@ -1036,7 +1058,7 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
       else if (ap) e = launch_gn_bwd_cluster<false, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
       else e = launch_gn_bwd_cluster<false, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
       if (e != cudaSuccess) return fail(ctx, std::string("sd2_groupnorm_bwd (cluster): ") + cudaGetErrorString(e));
-      launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta);
+      launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(B * cc.NC)), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta);
       return check_launch(ctx, "groupnorm_bwd", 2);
     }
   }
@@ -1106,7 +1128,7 @@ int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* 
     launch_k(ln_bwd_tile_kernel<false>, dim3(blocks), dim3(cfg.threads), cfg.smem_bytes, stream,
              reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,
              reinterpret_cast<const bf16*>(dx_add), reinterpret_cast<bf16*>(dx), ws, rows, C, cfg.RL, (unsigned)cfg.body_bytes);
-  launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, ws, blocks, C, dgamma, dbeta);
+  launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(blocks)), dim3(256), 0, stream, ws, blocks, C, dgamma, dbeta);
   return check_launch(ctx, "layernorm_bwd", 2);
 }
 

@@ -66,43 +66,68 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const bf16* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------- GEGLU / SiLU
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// Exact-GELU pieces from one MUFU.RCP and one MUFU.EX2: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, two orders
+// below the bf16 rounding of the results; libm's erff made both GEGLU kernels instruction-bound at ~55 % of HBM speed).
+//   cdf = Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  pdf = phi(x) = exp(-x^2 / 2) / sqrt(2 pi);  gelu = x cdf, gelu' = cdf + x pdf
+// The negative branch returns the small tail directly (no 1 - (1 - tail) cancellation).
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  const float u = __expf(-0.5f * x * x);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float tail = 0.5f * poly * t * u;
+  cdf = x >= 0.f ? 1.f - tail : tail;
+  pdf = 0.3989422804014327f * u;
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* v) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
-__global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int C) {
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int C) {
   pdl_grid_sync();
   const int V = C / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / V;
     const int v = (int)(i % V);
+    const uint4 ua = ldg_stream16(h + r * 2 * C + v * 8), ug = ldg_stream16(h + r * 2 * C + C + v * 8);
     float a[8], g[8];
-    ld8(h + r * 2 * C + v * 8, a);
-    ld8(h + r * 2 * C + C + v * 8, g);
+    unpack8f(ua, a);
+    unpack8f(ug, g);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] *= gelu_erf(g[e]);
+    for (int e = 0; e < 8; ++e) {
+      float cdf, pdf;
+      gelu_cdf_pdf(g[e], cdf, pdf);
+      a[e] *= g[e] * cdf;
+    }
     st8(y + r * C + v * 8, a);
   }
 }
 
-__global__ void geglu_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dy, bf16* __restrict__ dh, long long rows,
-                                 int C) {
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dy,
+                                                        bf16* __restrict__ dh, long long rows, int C) {
   pdl_grid_sync();
   const int V = C / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / V;
     const int v = (int)(i % V);
+    const uint4 ua = ldg_stream16(h + r * 2 * C + v * 8), ug = ldg_stream16(h + r * 2 * C + C + v * 8);
+    const uint4 ud = ldg_stream16(dy + r * C + v * 8);
     float a[8], g[8], d[8], da[8], dg[8];
-    ld8(h + r * 2 * C + v * 8, a);
-    ld8(h + r * 2 * C + C + v * 8, g);
-    ld8(dy + r * C + v * 8, d);
+    unpack8f(ua, a);
+    unpack8f(ug, g);
+    unpack8f(ud, d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      da[e] = d[e] * gelu_erf(g[e]);
-      dg[e] = d[e] * a[e] * gelu_erf_grad(g[e]);
+      float cdf, pdf;
+      gelu_cdf_pdf(g[e], cdf, pdf);
+      da[e] = d[e] * (g[e] * cdf);
+      dg[e] = d[e] * a[e] * fmaf(g[e], pdf, cdf);
     }
     st8(dh + r * 2 * C + v * 8, da);
     st8(dh + r * 2 * C + C + v * 8, dg);
@@ -247,7 +272,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (n0 < N) {
     const bf16* base = x + ((long long)g * rows_per_group) * ldx + n0;
-    for (long long r = r0 + rl; r < r1; r += 32) {
+    // four independent 16-byte loads in flight per thread (the loop is pure streaming: bytes in flight, not
+    // arithmetic, set its speed)
+    long long r = r0 + rl;
+    for (; r + 96 < r1; r += 128) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = ldg_stream16(base + (r + 32 * j) * ldx);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(u[j].x), b = unpack_bf16x2(u[j].y), c = unpack_bf16x2(u[j].z), d = unpack_bf16x2(u[j].w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+    for (; r < r1; r += 32) {
       float f[8];
       ld8(base + r * ldx, f);
 #pragma unroll
@@ -473,7 +512,7 @@ int sd2_colsum(sd2_ctx* ctx, const void* x, long long ldx, float* out, long long
   if (N % 8 || ldx % 8) return fail(ctx, "colsum: N/ldx % 8");
   SD2_STREAM;
   const int nblk = (N + 63) / 64;
-  long long splits = (2LL * ctx->num_sms) / ((long long)nblk * groups);
+  long long splits = (6LL * ctx->num_sms) / ((long long)nblk * groups);
   const long long max_splits = (rows_per_group + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
