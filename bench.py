@@ -8,8 +8,9 @@ A step = StableDiffusion.forward (K1 + UNet) + loss + backward + gradient all-re
 microbatch of synthetic latents per GPU (SD-2-base-256: 32x32x4 latents, 77x1024 context, bf16, random init).
 Per-GPU microbatch: the reference recipe trains with a device batch of 256 (global 2048 / 8 GPUs,
 yamls/hydra-yamls/SD-2-base-256.yaml:2,87) cut into microbatches of 16 to fit 40/80 GB parts; microbatching does not
-change the optimizer step (GroupNorm is per sample, the loss is a mean), so on 180 GB B200s the default here is 128
-(two microbatches per device batch; --batch 16 reproduces the yaml's value).  The optimizer still runs every step.
+change the optimizer step (GroupNorm is per sample, the loss is a mean), so on 180 GB B200s the default here is the
+whole device batch, 256, in one pass (--batch 16 reproduces the yaml's microbatch; measured on one B200: 630 img/s at
+16, 983 at 64, 1156 at 128, 1199 at 256).  The optimizer runs every step.
 One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for the roofline arithmetic.
 """
 import argparse
@@ -28,6 +29,19 @@ sys.path.insert(0, ROOT)
 # algorithmic training FLOPs per image = 3 (fwd+dgrad+wgrad) * 2 * forward MACs
 TFLOP_PER_IMAGE = {32: 3 * 2 * 90.55e9 / 1e12, 64: 3 * 2 * 402.13e9 / 1e12}
 METRIC = 'sd2_unet_train_images_per_sec'
+
+
+def measured_traffic(batch, latent):
+    """DRAM bytes per step of the tensor-core family from the committed ncu pass of this command
+    (profiles/traffic.json, written by tools/ncu_traffic.py), or None if that configuration was not captured."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        for row in json.load(f):
+            if row.get('per_gpu_microbatch') == batch and row.get('latent') == latent:
+                return row.get('tensor_family_dram_bytes_per_step')
+    return None
 
 
 def read_peaks():
@@ -199,7 +213,7 @@ def run_ours(args):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), float(last)
+        return ms.item(), float(last.detach()) if torch.is_tensor(last) else float(last)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -226,7 +240,7 @@ def run_ours(args):
         gemm_ms = e0.elapsed_time(e1) / reps
         achieved = TFLOP_PER_IMAGE[R] * B / (gemm_ms * 1e-3)
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s', 'frac': achieved / sustained,
-                'traffic': None, 'kernel': 'tensor-core family of one step replayed alone: gemm_tc_kernel<BN,A_MN,B_MN> (every GEMM/conv) + attn_fwd/bwd_kernel',
+                'traffic': measured_traffic(B, R), 'kernel': 'tensor-core family of one step replayed alone: gemm_tc_kernel<BN,A_MN,B_MN> (every GEMM/conv) + attn_fwd/bwd_kernel',
                 'launches_per_step': n_gemm, 'ms_per_step_in_kernel': gemm_ms,
                 'share_of_step': gemm_ms / (ms_dev / args.steps), 'peak_source': f'{how} bf16_tflops_sustained',
                 'plan_tflop_per_step': eng.gemm_flops / 1e12}
@@ -270,14 +284,14 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--latent', type=int, default=32, help='latent side: 32 = SD-2-base-256 (default), 64 = SD-2-base-512')
     ap.add_argument('--batch', type=int, default=None,
-                    help='per-GPU microbatch (default 128 at 256^2, 32 at 512^2; the reference yaml uses 16 on 40/80 GB GPUs)')
+                    help='per-GPU microbatch (default 256 at 256^2, 64 at 512^2; the reference yaml uses 16 on 40/80 GB GPUs)')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-step', action='store_true',
                     help='run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 128 if args.latent <= 32 else 32
+        args.batch = 256 if args.latent <= 32 else 64
     if args.impl == 'reference':
         run_reference(args)
     else:

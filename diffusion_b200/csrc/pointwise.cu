@@ -91,10 +91,15 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const bf16* __restrict__
   pdl_grid_sync();
   const int V = C / 8;
   const long long n = rows * V;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / V;
-    const int v = (int)(i % V);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // two vectors per iteration: four 16-byte loads in flight per thread
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < n;
+    const long long r = i / V, r2 = two ? i2 / V : r;
+    const int v = (int)(i % V), v2 = two ? (int)(i2 % V) : v;
     const uint4 ua = ldg_stream16(h + r * 2 * C + v * 8), ug = ldg_stream16(h + r * 2 * C + C + v * 8);
+    const uint4 ub = ldg_stream16(h + r2 * 2 * C + v2 * 8), uh = ldg_stream16(h + r2 * 2 * C + C + v2 * 8);
     float a[8], g[8];
     unpack8f(ua, a);
     unpack8f(ug, g);
@@ -105,6 +110,17 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const bf16* __restrict__
       a[e] *= g[e] * cdf;
     }
     st8(y + r * C + v * 8, a);
+    if (two) {
+      unpack8f(ub, a);
+      unpack8f(uh, g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float cdf, pdf;
+        gelu_cdf_pdf(g[e], cdf, pdf);
+        a[e] *= g[e] * cdf;
+      }
+      st8(y + r2 * C + v2 * 8, a);
+    }
   }
 }
 

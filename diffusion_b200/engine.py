@@ -230,7 +230,11 @@ class Engine:
         self.set_context(enc)
 
     def set_context(self, enc):
-        self.in_ctx.copy_(enc.reshape(self.B * self.L, -1))
+        """Text conditioning (B, L, D) in its wire dtype (fp16 from the precomputed-latent dataset, bf16, fp32) -> the
+        engine's bf16 context buffer, by the library's cast kernel."""
+        if enc.numel() != self.in_ctx.numel():
+            raise ValueError(f'conditioning has {tuple(enc.shape)}, engine was built for ({self.B}, {self.L}, {self.in_ctx.shape[1]})')
+        ops.cast_to_bf16(self.ctx, enc.contiguous(), self.in_ctx)
 
     # ---------------------------------------------------------------------------------------------- helpers
     def node(self, M, C, dtype=BF16):

@@ -81,6 +81,65 @@ class DDPMScheduler:
         return a * original_samples + s * noise
 
 
+class _StepOutput(dict):
+    """Dict with attribute access, like diffusers' BaseOutput (`scheduler.step(...).prev_sample`, `unet(...).sample`)."""
+    __getattr__ = dict.__getitem__
+
+
+class DDIMScheduler:
+    """Inference scheduler of `generate()`: diffusers' DDIMScheduler as `from_pretrained(SD-2-base scheduler config)`
+    builds it at reference models.py:89 - scaled_linear betas, epsilon prediction, clip_sample False,
+    set_alpha_to_one False, steps_offset 1, 'leading' timestep spacing, eta 0.  Scalars stay fp32 CPU tensors like the
+    original, so `step()` on torch tensors promotes types exactly as the reference loop does; `generate()` itself runs
+    the fused `sd2_cfg_ddim_step` kernel with the same scalars."""
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule='scaled_linear',
+                 prediction_type='epsilon', clip_sample=False, set_alpha_to_one=False, steps_offset=1, **_ignored):
+        if beta_schedule != 'scaled_linear' or prediction_type != 'epsilon' or clip_sample:
+            raise ValueError('only the SD-2-base inference scheduler configuration is implemented')
+        self.num_train_timesteps, self.steps_offset = num_train_timesteps, steps_offset
+        self.betas = torch.linspace(beta_start**0.5, beta_end**0.5, num_train_timesteps, dtype=torch.float32)**2
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_inference_steps = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1, dtype=torch.int64)
+
+    def __len__(self):
+        return self.num_train_timesteps
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        if num_inference_steps > self.num_train_timesteps:
+            raise ValueError(f'`num_inference_steps`: {num_inference_steps} cannot be larger than '
+                             f'`num_train_timesteps`: {self.num_train_timesteps}')
+        self.num_inference_steps = num_inference_steps
+        ratio = self.num_train_timesteps // num_inference_steps
+        ts = (torch.arange(0, num_inference_steps, dtype=torch.int64) * ratio).flip(0) + self.steps_offset
+        self.timesteps = ts.to(device) if device is not None else ts
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def step_scalars(self, timestep):
+        """fp32 (sqrt(1 - a_t), sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev)) of one eta = 0 step."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        t = int(timestep)
+        prev = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        return (1 - a_t)**0.5, a_t**0.5, a_prev**0.5, (1 - a_prev)**0.5
+
+    def step(self, model_output, timestep, sample, eta=0.0, generator=None, **_unused):
+        if eta != 0.0:
+            raise ValueError('only eta = 0 (deterministic DDIM) is implemented')
+        sb, sa, sap, dc = self.step_scalars(timestep)
+        pred_original_sample = (sample - sb * model_output) / sa
+        prev_sample = sap * pred_original_sample + dc * model_output
+        return _StepOutput(prev_sample=prev_sample, pred_original_sample=pred_original_sample)
+
+
 class _FusedMSE(torch.autograd.Function):
     """loss = mean((pred - noise)^2) computed by the fused head kernel from the engine's pred8 buffer; the same
     launch writes dL/dpred so that backward starts without an elementwise pass."""
@@ -212,7 +271,16 @@ class StableDiffusion(ComposerModel):
     def eval_forward(self, batch, outputs=None):
         if outputs is not None:
             return outputs
-        return self.forward(batch)
+        unet_out, noise, timesteps = self.forward(batch)
+        generated_images = {}
+        if self.text_encoder is not None and self.vae is not None and self.text_key in batch and self.image_key in batch:
+            prompts = batch[self.text_key]
+            height, width = batch[self.image_key].shape[-2], batch[self.image_key].shape[-1]
+            for guidance_scale in self.val_guidance_scales:
+                generated_images[guidance_scale] = self.generate(tokenized_prompts=prompts, height=height, width=width,
+                                                                 guidance_scale=guidance_scale, seed=self.val_seed,
+                                                                 progress_bar=False)
+        return unet_out, noise, timesteps, generated_images
 
     def get_metrics(self, is_train: bool = False):
         metrics = self.train_metrics if is_train else self.val_metrics
@@ -230,6 +298,122 @@ class StableDiffusion(ComposerModel):
             metric.update(outputs[0][idx], outputs[1][idx])
         else:
             metric.update(outputs[0], outputs[1])
+
+    # -- reference stable_diffusion.py:259-382 -----------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self,
+                 prompt: Optional[list] = None,
+                 negative_prompt: Optional[list] = None,
+                 tokenized_prompts: Optional[torch.Tensor] = None,
+                 tokenized_negative_prompts: Optional[torch.Tensor] = None,
+                 prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 height: Optional[int] = None,
+                 width: Optional[int] = None,
+                 num_inference_steps: Optional[int] = 50,
+                 guidance_scale: Optional[float] = 3.0,
+                 num_images_per_prompt: Optional[int] = 1,
+                 seed: Optional[int] = None,
+                 progress_bar: Optional[bool] = True,
+                 output_type: str = 'image'):
+        """Backward diffusion from noise: same arguments and defaults as the reference plus `output_type` ('image' decodes
+        with `self.vae` like the reference; 'latent' returns the final fp32 latents, which is all a model built without a
+        VAE can return).  Per step: one timestep-embedding launch, the UNet forward graph on the (2x) batch, and ONE fused
+        launch for classifier-free guidance + the DDIM update + the next UNet input (`sd2_cfg_ddim_step`)."""
+        _check_prompt_given(prompt, tokenized_prompts, prompt_embeds)
+        _check_prompt_lenths(prompt, negative_prompt)
+        _check_prompt_lenths(tokenized_prompts, tokenized_negative_prompts)
+        _check_prompt_lenths(prompt_embeds, negative_prompt_embeds)
+        if output_type not in ('image', 'latent'):
+            raise ValueError("output_type must be 'image' or 'latent'")
+        if output_type == 'image' and self.vae is None:
+            raise ValueError("this model was built without a VAE: call generate(..., output_type='latent')")
+        if self.inference_scheduler is None:
+            raise ValueError('the model has no inference scheduler')
+        device = next(self.unet.parameters()).device
+        vae_scale_factor = 8
+        sample_size = self.unet.config.get('sample_size', 64)
+        height = height or sample_size * vae_scale_factor
+        width = width or sample_size * vae_scale_factor
+        do_cfg = guidance_scale > 1.0
+        text_embeddings = self._prepare_text_embeddings(prompt, tokenized_prompts, prompt_embeds, num_images_per_prompt)
+        batch_size = len(text_embeddings)
+        if do_cfg:
+            if negative_prompt is None and tokenized_negative_prompts is None and negative_prompt_embeds is None:
+                negative_prompt = [''] * (batch_size // num_images_per_prompt)
+            uncond = self._prepare_text_embeddings(negative_prompt, tokenized_negative_prompts, negative_prompt_embeds,
+                                                   num_images_per_prompt)
+            text_embeddings = torch.cat([uncond.to(text_embeddings.dtype), text_embeddings])
+        if device.type != 'cuda':
+            raise RuntimeError('diffusion_b200 needs CUDA (sm_100a) tensors: there is no CPU fallback')
+        rng_generator = torch.Generator(device=device)
+        if seed:
+            rng_generator = rng_generator.manual_seed(seed)
+        h, w = height // vae_scale_factor, width // vae_scale_factor
+        latents = torch.randn((batch_size, self.unet.config['in_channels'], h, w), device=device, generator=rng_generator)
+        self.inference_scheduler.set_timesteps(num_inference_steps)
+        latents = (latents * self.inference_scheduler.init_noise_sigma).contiguous()
+        nb = 2 if do_cfg else 1
+        eng = self.unet.engine(nb * batch_size, h, w, text_embeddings.shape[1])
+        eng.set_context(text_embeddings.to(device))
+        for half in range(nb):  # UNet input of the first step: bf16 NHWC8 copy of the initial latents, per CFG half
+            ops.nchw4_to_nhwc8(eng.ctx, latents, eng.in_x8[half * batch_size * h * w:(half + 1) * batch_size * h * w],
+                               batch_size, h, w)
+        steps = self.inference_scheduler.timesteps
+        if progress_bar:
+            try:
+                from tqdm.auto import tqdm
+                steps = tqdm(steps)
+            except Exception:  # pragma: no cover
+                pass
+        tvec = torch.empty(nb * batch_size, dtype=torch.int64, device=device)
+        for t in steps:
+            tvec.fill_(int(t))
+            ops.timestep_embedding(eng.ctx, tvec, eng.in_temb, torch.float32)
+            eng.run_forward()
+            sb, sa, sap, dc = (float(x) for x in self.inference_scheduler.step_scalars(t))
+            ops.cfg_ddim_step(eng.ctx, eng.pred8, latents, eng.in_x8, batch_size, h, w, do_cfg, guidance_scale, sb, sa, sap, dc)
+        if output_type == 'latent':
+            return latents.detach()
+        latents = 1 / 0.18215 * latents
+        image = self.vae.decode(latents).sample
+        image = (image / 2 + 0.5).clamp(0, 1)
+        return image.detach()
+
+    def _prepare_text_embeddings(self, prompt, tokenized_prompts, prompt_embeds, num_images_per_prompt):
+        """Tokenizes and embeds prompts if needed, then duplicates embeddings per generated image
+        (reference stable_diffusion.py:384-405)."""
+        if prompt_embeds is None:
+            if self.text_encoder is None:
+                raise ValueError('this model was built without a text encoder: pass prompt_embeds / negative_prompt_embeds')
+            device = next(self.text_encoder.parameters()).device
+            if tokenized_prompts is None:
+                if self.tokenizer is None:
+                    raise ValueError('this model was built without a tokenizer: pass tokenized_prompts or prompt_embeds')
+                tokenized_prompts = self.tokenizer(prompt, padding='max_length', max_length=self.tokenizer.model_max_length,
+                                                   truncation=True, return_tensors='pt').input_ids
+            text_embeddings = self.text_encoder(tokenized_prompts.to(device))[0]
+        else:
+            text_embeddings = prompt_embeds
+        bs_embed, seq_len, _ = text_embeddings.shape
+        text_embeddings = text_embeddings.repeat(1, num_images_per_prompt, 1)
+        return text_embeddings.view(bs_embed * num_images_per_prompt, seq_len, -1)
+
+
+def _check_prompt_lenths(prompt, negative_prompt):
+    if prompt is None and negative_prompt is None:
+        return
+    batch_size = 1 if isinstance(prompt, str) else len(prompt)
+    if negative_prompt is not None and len(negative_prompt) > 0:
+        negative_prompt_bs = 1 if isinstance(negative_prompt, str) else len(negative_prompt)
+        if negative_prompt_bs != batch_size:
+            raise ValueError('len(prompts) and len(negative_prompts) must be the same. '
+                             'A negative prompt must be provided for each given prompt.')
+
+
+def _check_prompt_given(prompt, tokenized_prompts, prompt_embeds):
+    if prompt is None and tokenized_prompts is None and prompt_embeds is None:
+        raise ValueError('Must provide one of `prompt`, `tokenized_prompts`, or `prompt_embeds`')
 
 
 def stable_diffusion_2(
@@ -262,7 +446,7 @@ def stable_diffusion_2(
         loss_bins = [(0, 1)]
     unet = UNet2DConditionModel(**(unet_config or SD2_BASE_UNET_CONFIG))
     model = StableDiffusion(unet=unet, vae=None, text_encoder=None, tokenizer=None, noise_scheduler=DDPMScheduler(),
-                            inference_noise_scheduler=None, train_metrics=train_metrics, val_metrics=val_metrics,
+                            inference_noise_scheduler=DDIMScheduler(), train_metrics=train_metrics, val_metrics=val_metrics,
                             val_guidance_scales=val_guidance_scales, val_seed=val_seed, loss_bins=loss_bins,
                             precomputed_latents=precomputed_latents, encode_latents_in_fp16=encode_latents_in_fp16, fsdp=fsdp)
     if torch.cuda.is_available():

@@ -440,3 +440,27 @@ def attn_bwd(ctx, q, k, v, o, do, lse, dq, dk, dv, ws, B, heads, Nq, Nk, scale):
         ctx.lib.sd2_attn_bwd(ctx.h, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(do),
                              do.stride(0), _p(lse), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(ws), B,
                              heads, Nq, Nk, 64, float(scale), _s()))
+
+
+# ------------------------------------------------------------------------------------------------- rows f2-f4
+def cfg_ddim_step(ctx, pred8, latents, next8, B, H, W, guidance, guidance_scale, sqrt_beta_t, sqrt_alpha_t, sqrt_alpha_prev,
+                  dir_coef):
+    """One sampling step: CFG combine of pred8 (bf16 [(2|1)*B*H*W, 8]) + DDIM step (eta=0) on the fp32 NCHW latents (in
+    place) + the next UNet input (bf16 NHWC8, both halves) in next8."""
+    assert latents.dtype == torch.float32 and latents.is_contiguous() and latents.shape == (B, 4, H, W)
+    ctx.check(
+        ctx.lib.sd2_cfg_ddim_step(ctx.h, _p(pred8), _p(latents), _p(next8), B, H, W, int(bool(guidance)), float(guidance_scale),
+                                  float(sqrt_beta_t), float(sqrt_alpha_t), float(sqrt_alpha_prev), float(dir_coef), _s()))
+
+
+def ema_update(ctx, ema, param, smoothing):
+    """ema = ema * smoothing + param * (1 - smoothing) over flat fp32 tensors, in place."""
+    assert ema.dtype == torch.float32 and param.dtype == torch.float32 and ema.numel() == param.numel()
+    assert ema.is_contiguous() and param.is_contiguous()
+    ctx.check(ctx.lib.sd2_ema_update(ctx.h, _p(ema), _p(param), ema.numel(), float(smoothing), float(1. - smoothing), _s()))
+
+
+def cast_to_bf16(ctx, src, dst):
+    """dst (bf16) = src (fp32 / fp16 / bf16), same number of elements, both contiguous."""
+    assert dst.dtype == torch.bfloat16 and src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous()
+    ctx.check(ctx.lib.sd2_cast_to_bf16(ctx.h, _p(src), _DT[src.dtype], _p(dst), src.numel(), _s()))

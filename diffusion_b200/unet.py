@@ -28,6 +28,12 @@ SD2_BASE_UNET_CONFIG = dict(
 )
 
 
+class UNetOutput(dict):
+    """`{'sample': ...}` with attribute access: the reference reads both `unet(...)['sample']`
+    (stable_diffusion.py:183) and `unet(...).sample` (:362)."""
+    __getattr__ = dict.__getitem__
+
+
 def _holder(**children):
     m = nn.Module()
     for k, v in children.items():
@@ -158,4 +164,4 @@ class UNet2DConditionModel(nn.Module):
         """diffusers call signature; returns {'sample': eps_pred} (B,4,h,w) in sample.dtype.  Differentiable with
         respect to the parameters (custom autograd node that replays the static backward schedule)."""
         from diffusion_b200.engine import unet_apply
-        return {'sample': unet_apply(self, sample, timestep, encoder_hidden_states)}
+        return UNetOutput(sample=unet_apply(self, sample, timestep, encoder_hidden_states))

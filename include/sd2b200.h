@@ -193,6 +193,24 @@ int sd2_adamw_step(sd2_ctx* ctx, float* param, float* grad, float* exp_avg, floa
                    long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                    float grad_scale, int zero_grad, sd2_stream stream);
 
+/* ---- rows f2-f4: the callers either side of the training step --------------------------------------------------------
+ * sd2_cfg_ddim_step: one sampling step of StableDiffusion.generate() (reference stable_diffusion.py:353-371): classifier-
+ *   free-guidance combine of the UNet output (pred_nhwc8 bf16 [(guidance ? 2 : 1) * B][H][W][8], unconditional half first),
+ *   DDIMScheduler.step with eta = 0 on the fp32 NCHW latents [B,4,H,W] (updated in place) and the bf16 NHWC8 copy of the
+ *   new latents for BOTH halves of the next UNet call (next_nhwc8).  Scalars: sqrt(1-a_t), sqrt(a_t), sqrt(a_prev),
+ *   sqrt(1-a_prev), computed by the caller in fp32 like the scheduler does. */
+int sd2_cfg_ddim_step(sd2_ctx* ctx, const void* pred_nhwc8, float* latents, void* next_nhwc8, int B, int H, int W,
+                      int guidance, float guidance_scale, float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev,
+                      float dir_coef, sd2_stream stream);
+/* ema[i] = ema[i] * smoothing + param[i] * one_minus_smoothing (reference diffusion/algorithms/ema.py:62-63) */
+int sd2_ema_update(sd2_ctx* ctx, float* ema, const float* param, long long n, float smoothing, float one_minus_smoothing,
+                   sd2_stream stream);
+/* dst bf16[n] = src[n] (src_dtype SD2_DT_F32 / F16 / BF16): the fp16 wire format of precomputed latents
+ * (reference diffusion/datasets/laion/laion.py:103-111) -> the engine's bf16 context buffer */
+int sd2_cast_to_bf16(sd2_ctx* ctx, const void* src, int src_dtype, void* dst, long long n, sd2_stream stream);
+/* host only: gather n sample buffers of bytes_each bytes into one contiguous (pinned) batch buffer; 0 = ok */
+int sd2_wire_gather(const void* const* src, int n, long long bytes_each, void* dst);
+
 #ifdef __cplusplus
 }
 #endif

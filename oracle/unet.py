@@ -312,7 +312,7 @@ class UNet2DConditionModel(nn.Module):
     def forward(self, sample, timestep, encoder_hidden_states):
         if not torch.is_tensor(timestep):
             timestep = torch.tensor([timestep], dtype=torch.long, device=sample.device)
-        timestep = timestep.expand(sample.shape[0])
+        timestep = timestep.reshape(-1).to(sample.device).expand(sample.shape[0])  # 0-dim scheduler timesteps live on the CPU
         t_emb = get_timestep_embedding(timestep, self.block0, self.flip_sin_to_cos, self.freq_shift)
         t_emb = t_emb.to(dtype=sample.dtype)
         emb = self.time_embedding(t_emb)

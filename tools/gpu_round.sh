@@ -53,6 +53,10 @@ if want normsweep; then
   NORM_BENCH_BIG=1 timeout 300 python tools/norm_bench.py l >> gpurun_out/norm_sweep.md 2>&1
   echo "normsweep exit $?" | tee -a gpurun_out/summary.txt; tail -n 12 gpurun_out/norm_sweep.md
 fi
+if want b512big; then
+  timeout 900 python bench.py --latent 64 --batch 64 --steps 5 --no-cpu-baseline > gpurun_out/bench_512_B64.log 2> gpurun_out/bench_512_B64.err
+  echo "bench512 B64 exit $?" | tee -a gpurun_out/summary.txt; tail -n 2 gpurun_out/bench_512_B64.log; tail -n 3 gpurun_out/bench_512_B64.err
+fi
 if want b512; then
   timeout 900 python bench.py --latent 64 --steps 10 --no-cpu-baseline > gpurun_out/bench_512.log 2> gpurun_out/bench_512.err
   echo "bench512 exit $?" | tee -a gpurun_out/summary.txt; tail -n 2 gpurun_out/bench_512.log
