@@ -14,7 +14,7 @@ _CSRC = os.path.join(_HERE, 'csrc')
 _ROOT = os.path.dirname(_HERE)
 _BUILD = os.path.join(_ROOT, 'build')
 LIB_PATH = os.path.join(_HERE, 'libsd2b200.so')
-SOURCES = ['api.cu', 'gemm_tc.cu', 'attn.cu', 'k1_noise_sched.cu', 'norm.cu', 'pointwise.cu', 'sampler.cu']
+SOURCES = ['api.cu', 'gemm_tc.cu', 'attn.cu', 'k1_noise_sched.cu', 'norm.cu', 'pointwise.cu', 'sampler.cu', 'encoders.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
     '-Wno-deprecated-gpu-targets'
@@ -140,6 +140,13 @@ SIGNATURES = {
     'sd2_ema_update': (_i, [_vp, _vp, _vp, _ll, _f, _f, _vp]),
     'sd2_cast_to_bf16': (_i, [_vp, _vp, _i, _vp, _ll, _vp]),
     'sd2_wire_gather': (_i, [_vp, _i, _ll, _vp]),
+    'sd2_nchw_to_nhwc8': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    'sd2_nhwc8_to_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _f, _vp]),
+    'sd2_vae_sample': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'sd2_embed_tokens': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    'sd2_softmax_causal_fwd': (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp]),
+    'sd2_gelu_fwd': (_i, [_vp, _vp, _vp, _ll, _vp]),
+    'sd2_pixel_linear8': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
 }
 
 _lib = None

@@ -91,8 +91,16 @@ bool plain_tmap(CUtensorMap* tm, const sd2_operand& o, int box_rows, std::string
 }
 
 // pixel-box geometry of a shifted NHWC operand: `pixels` (128 for an M tile, 64 for a wgrad k-block) = W * th * nb
-static bool conv_box(const sd2_conv_geom& g, int pixels, int* th, int* nb) {
-  if (g.W <= 0 || g.H <= 0 || pixels % g.W != 0) return false;
+static bool conv_box(const sd2_conv_geom& g, int pixels, int* th, int* nb, int* wseg = nullptr) {
+  if (g.W <= 0 || g.H <= 0) return false;
+  if (wseg) *wseg = g.W;
+  if (wseg && g.W > pixels && g.W % pixels == 0) {  // wide image: the tile is a `pixels`-wide segment of one row
+    *th = 1;
+    *nb = 1;
+    *wseg = pixels;
+    return true;
+  }
+  if (pixels % g.W != 0) return false;
   int rows = pixels / g.W;
   if (rows <= g.H) {
     if (g.H % rows != 0) return false;
@@ -106,10 +114,10 @@ static bool conv_box(const sd2_conv_geom& g, int pixels, int* th, int* nb) {
   return *th <= 256 && *nb <= 256 && g.W <= 256;
 }
 
-static bool conv_tmap(CUtensorMap* tm, const sd2_conv_geom& g, int th, int nb, std::string* err) {
+static bool conv_tmap(CUtensorMap* tm, const sd2_conv_geom& g, int th, int nb, std::string* err, int wseg = 0) {
   const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.n_planes};
   const uint64_t strides[3] = {(uint64_t)g.ldc * 2, (uint64_t)g.ldc * 2 * g.W, (uint64_t)g.ldc * 2 * g.W * g.H};
-  const uint32_t box[4] = {64, (uint32_t)g.W, (uint32_t)th, (uint32_t)nb};
+  const uint32_t box[4] = {64, (uint32_t)(wseg > 0 ? wseg : g.W), (uint32_t)th, (uint32_t)nb};
   return encode_tmap_bf16_4d(tm, g.ptr, dims, strides, box, err);
 }
 
@@ -263,11 +271,13 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     const sd2_conv_geom& g = d->conv;
     a_mn = false;
     b_mn = d->B.mn_major != 0;
-    int th, nb;
-    if (!conv_box(g, 128, &th, &nb)) return fail(ctx, "sd2_gemm conv: unsupported spatial geometry for a 128-pixel tile");
+    int th, nb, wseg;
+    if (!conv_box(g, 128, &th, &nb, &wseg)) return fail(ctx, "sd2_gemm conv: unsupported spatial geometry for a 128-pixel tile");
     p.cH = g.H;
     p.cth = th;
     p.cnb = nb;
+    p.cws = g.W / wseg;
+    p.cwseg = wseg;
     p.cblks = (g.C + 63) / 64;
     p.taps = g.ntaps;
     if (g.ntaps < 1 || g.ntaps > 9) return fail(ctx, "sd2_gemm conv: ntaps out of range");
@@ -278,7 +288,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
       p.tap_w[t] = (signed char)g.wtap[t];
     }
     p.total_kb = g.ntaps * p.cblks;
-    if (!conv_tmap(&tmA, g, th, nb, &err)) return fail(ctx, "sd2_gemm conv A: " + err);
+    if (!conv_tmap(&tmA, g, th, nb, &err, wseg)) return fail(ctx, "sd2_gemm conv A: " + err);
     // weights [tap][rows][cols]: dims (cols, rows, 9, 1)
     sd2_operand w = d->B;
     w.nb0 = 9;
@@ -294,6 +304,8 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     p.cH = g.H;
     p.cth = th;
     p.cnb = nb;
+    p.cws = 1;
+    p.cwseg = g.W;
     p.taps = g.ntaps;
     if (g.ntaps < 1 || g.ntaps > 9) return fail(ctx, "sd2_gemm wgrad: ntaps out of range");
     for (int t = 0; t < g.ntaps; ++t) {

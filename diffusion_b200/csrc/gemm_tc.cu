@@ -234,21 +234,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // advanced incrementally (no division in the loop) so the producer stays far ahead of the tensor pipe.
     int s = 0;
     uint32_t ph = 0;
-    const int bpi = p.cnb == 1 ? p.cH / p.cth : 1;  // pixel blocks (M tiles or wgrad k-blocks) per image
+    const int bpi = p.cnb == 1 ? (p.cH / p.cth) * p.cws : 1;  // pixel blocks (M tiles or wgrad k-blocks) per image
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const WorkItem w = decode_item(p, item);
       const int n_off = w.n_tile * BN, m_off = w.m_tile * BM;
       const int ab0 = p.a_batched ? w.batch % p.a_nb0 : 0, ab1 = p.a_batched ? w.batch / p.a_nb0 : 0;
       const int bb0 = p.b_batched ? w.batch % p.b_nb0 : 0, bb1 = p.b_batched ? w.batch / p.b_nb0 : 0;
       // conv: pixel-block origin of this M tile; (tap, channel block) of the first k-block
-      int cn0 = 0, ch0 = 0, tap = 0, cb = 0;
+      int cn0 = 0, ch0 = 0, cw0 = 0, tap = 0, cb = 0;
       // wgrad: (image, row) origin of the first 64-pixel k-block
       int wn = 0, wh = 0;
       int dh = 0, dw = 0, dn = 0, tw = 0;
       if (p.kind == KIND_CONV) {
         if (p.cnb == 1) {
+          const int t = w.m_tile % bpi;
           cn0 = w.m_tile / bpi;
-          ch0 = (w.m_tile % bpi) * p.cth;
+          ch0 = (t / p.cws) * p.cth;
+          cw0 = (t % p.cws) * p.cwseg;
         } else {
           cn0 = w.m_tile * p.cnb;
         }
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint64_t* fb = &full_bar[s];
           mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
           if (p.kind == KIND_CONV) {
-            tma_load_4d(a_dst, &tmA, fb, cb * 64, dw, ch0 + dh, cn0 + dn);
+            tma_load_4d(a_dst, &tmA, fb, cb * 64, cw0 + dw, ch0 + dh, cn0 + dn);
             if (!B_MN) {
               tma_load_4d(b_dst, &tmB, fb, cb * 64, n_off, tw, 0);
             } else {

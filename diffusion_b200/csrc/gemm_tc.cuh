@@ -30,7 +30,9 @@ struct GemmKParams {
   int a_batched, b_batched;  // plain operands: does the batch index move this operand?
   int a_nb0, b_nb0;          // batch -> (batch % nb0, batch / nb0) = tensor-map coords 2,3
   // conv geometry of the shifted operand: tensor map dims (C, W, H, Nimg), box (64, W, th, nb)
-  int cH, cth, cnb, cblks, taps;
+  // wide images (W > 128, forward conv only): a tile is one 128-pixel segment of a row: box (64, cwseg, 1, 1), cws
+  // segments per row; cws = 1 everywhere else.
+  int cH, cth, cnb, cblks, taps, cws, cwseg;
   // per-tap table: spatial shift (dh, dw), image-index offset (stride-2 phase planes) and weight tap index
   signed char tap_dh[9], tap_dw[9];
   int tap_dn[9];

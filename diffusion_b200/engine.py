@@ -97,9 +97,11 @@ class ParamArena:
         cls._live = [r for r, a in zip(cls._live, out) if a is not None]
         return [a for a in out if a is not None]
 
-    def __init__(self, unet, device):
+    def __init__(self, unet, device, with_grads=True):
+        """with_grads=False: frozen modules (VAE, text encoder) get the fp32 arena and the bf16 shadow only."""
         import weakref
-        ParamArena._live.append(weakref.ref(self))
+        if with_grads:
+            ParamArena._live.append(weakref.ref(self))
         self.shadow_version = None  # parameter-version stamp the bf16 shadow was last refreshed at
         self.entries = {}
         off = 0
@@ -111,7 +113,7 @@ class ParamArena:
             off = _align(off + p.numel())
         self.total = off
         self.p32 = torch.zeros(off, dtype=torch.float32, device=device)
-        self.g32 = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g32 = torch.zeros(off if with_grads else 0, dtype=torch.float32, device=device)
         self.p16 = torch.zeros(off, dtype=BF16, device=device)
         self.params = {}
         with torch.no_grad():

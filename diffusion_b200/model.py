@@ -218,8 +218,8 @@ class StableDiffusion(ComposerModel):
         for frozen in (self.text_encoder, self.vae):
             if frozen is not None:
                 frozen.requires_grad_(False)
-                if self.encode_latents_in_fp16:
-                    frozen.half()
+                if self.encode_latents_in_fp16 and not getattr(frozen, '_sd2_native', False):
+                    frozen.half()  # the native encoders keep fp32 masters and compute from their own bf16 shadow
         if fsdp:
             for m, flag in ((self.text_encoder, False), (self.vae, False), (self.unet, True)):
                 if m is not None:
@@ -236,8 +236,11 @@ class StableDiffusion(ComposerModel):
                                  '(in-loop encoding is SURVEY.md row f1, not part of this hot path)')
             inputs, conditioning = batch[self.image_key], batch[self.text_key]
             conditioning = conditioning.view(-1, conditioning.shape[-1])
-            latents = self.vae.encode(inputs)['latent_dist'].sample().data
-            conditioning = self.text_encoder(conditioning)[0]
+            if self.encode_latents_in_fp16:
+                inputs = inputs.half()
+            with torch.no_grad():
+                latents = self.vae.encode(inputs)['latent_dist'].sample().data
+                conditioning = self.text_encoder(conditioning)[0]
             latents = latents * 0.18215
         if latents.device.type != 'cuda':
             raise RuntimeError('diffusion_b200 needs CUDA (sm_100a) tensors: there is no CPU fallback')
@@ -428,11 +431,16 @@ def stable_diffusion_2(
     encode_latents_in_fp16: bool = True,
     fsdp: bool = True,
     unet_config: Optional[dict] = None,
+    build_encoders: Optional[bool] = None,
+    vae_config: Optional[dict] = None,
+    text_encoder_config: Optional[dict] = None,
 ):
     """Same signature as reference diffusion/models/models.py:28-39 (+ `unet_config` to override the SD-2-base UNet
     config for small test models).  The UNet is random-initialised from the SD-2-base config (`pretrained=False`,
     the yaml default); the HF hub is not reachable here, so `pretrained=True` raises, and VAE / CLIP / tokenizer are
-    only attached when precomputed latents are not used and their weights can be loaded."""
+    attached (native modules of diffusion_b200/encoders.py, random init) when `build_encoders` is true - by default when
+    precomputed latents are not used; the tokenizer needs vocabulary files that are not on disk, so batches must carry
+    token ids (the reference dataset tokenizes in `__getitem__`)."""
     if pretrained:
         raise ValueError('pretrained=True needs the HF hub checkpoint of the UNet; load a state_dict into '
                          'model.unet instead (parameter names follow diffusers)')
@@ -445,7 +453,14 @@ def stable_diffusion_2(
     if loss_bins is None:
         loss_bins = [(0, 1)]
     unet = UNet2DConditionModel(**(unet_config or SD2_BASE_UNET_CONFIG))
-    model = StableDiffusion(unet=unet, vae=None, text_encoder=None, tokenizer=None, noise_scheduler=DDPMScheduler(),
+    vae = text_encoder = None
+    if build_encoders is None:
+        build_encoders = not precomputed_latents
+    if build_encoders:  # random-init native VAE / text tower (diffusers / transformers parameter names: load_state_dict works)
+        from diffusion_b200.encoders import SD2_TEXT_CONFIG, SD2_VAE_CONFIG, AutoencoderKL, CLIPTextModel
+        vae = AutoencoderKL(**(vae_config or SD2_VAE_CONFIG))
+        text_encoder = CLIPTextModel(**(text_encoder_config or SD2_TEXT_CONFIG))
+    model = StableDiffusion(unet=unet, vae=vae, text_encoder=text_encoder, tokenizer=None, noise_scheduler=DDPMScheduler(),
                             inference_noise_scheduler=DDIMScheduler(), train_metrics=train_metrics, val_metrics=val_metrics,
                             val_guidance_scales=val_guidance_scales, val_seed=val_seed, loss_bins=loss_bins,
                             precomputed_latents=precomputed_latents, encode_latents_in_fp16=encode_latents_in_fp16, fsdp=fsdp)

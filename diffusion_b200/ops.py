@@ -464,3 +464,44 @@ def cast_to_bf16(ctx, src, dst):
     """dst (bf16) = src (fp32 / fp16 / bf16), same number of elements, both contiguous."""
     assert dst.dtype == torch.bfloat16 and src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous()
     ctx.check(ctx.lib.sd2_cast_to_bf16(ctx.h, _p(src), _DT[src.dtype], _p(dst), src.numel(), _s()))
+
+
+# ------------------------------------------------------------------------------------------------- row f1 glue
+def nchw_to_nhwc8(ctx, src, dst8, B, Cc, H, W):
+    ctx.check(ctx.lib.sd2_nchw_to_nhwc8(ctx.h, _p(src), _DT[src.dtype], _p(dst8), B, Cc, H, W, _s()))
+
+
+def nhwc8_to_nchw(ctx, src8, dst, B, Cc, H, W, scale=1.0, shift=0.0, lo=-3.0e38, hi=3.0e38):
+    ctx.check(ctx.lib.sd2_nhwc8_to_nchw(ctx.h, _p(src8), _p(dst), _DT[dst.dtype], B, Cc, H, W, float(scale), float(shift),
+                                        float(lo), float(hi), _s()))
+
+
+def vae_sample(ctx, moments8, quant_w, quant_b, noise, latents, mean_out, B, H, W, scale):
+    assert noise.dtype == latents.dtype and noise.is_contiguous() and latents.is_contiguous()
+    ctx.check(ctx.lib.sd2_vae_sample(ctx.h, _p(moments8), _p(quant_w), _p(quant_b), _p(noise), _p(latents), _p(mean_out),
+                                     _DT[latents.dtype], B, H, W, float(scale), _s()))
+
+
+def embed_tokens(ctx, ids, tok, pos, x, L):
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    ctx.check(ctx.lib.sd2_embed_tokens(ctx.h, _p(ids), _p(tok), _p(pos), _p(x), ids.numel(), L, tok.shape[1], tok.shape[0], _s()))
+
+
+def softmax_causal_fwd(ctx, S, P, rows, cols, period):
+    ctx.check(ctx.lib.sd2_softmax_causal_fwd(ctx.h, _p(S), S.stride(-2), _p(P), P.stride(-2), rows, cols, period, _s()))
+
+
+def gelu_fwd(ctx, x, y):
+    ctx.check(ctx.lib.sd2_gelu_fwd(ctx.h, _p(x), _p(y), x.numel(), _s()))
+
+
+def pixel_linear8(ctx, in8, w, b, out8):
+    ctx.check(ctx.lib.sd2_pixel_linear8(ctx.h, _p(in8), _p(w), _p(b), _p(out8), in8.shape[0], w.shape[1], w.shape[0], _s()))
+
+
+def taps_stride2_vae(B):
+    """Forward taps of the VAE's Downsample2D (F.pad(x, (0, 1, 0, 1)) + 3x3 stride-2 pad-0 conv) over the 4 phase planes:
+    input row 2*ho + kh = 2*(ho + dh) + ph with (kh=0: ph=0, dh=0), (kh=1: ph=1, dh=0), (kh=2: ph=0, dh=+1); the bottom /
+    right zero padding is the TMA out-of-bounds fill."""
+    m = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
+    return [(m[kh][1], m[kw][1], (m[kh][0] * 2 + m[kw][0]) * B, kh * 3 + kw) for kh in range(3) for kw in range(3)]

@@ -211,6 +211,32 @@ int sd2_cast_to_bf16(sd2_ctx* ctx, const void* src, int src_dtype, void* dst, lo
 /* host only: gather n sample buffers of bytes_each bytes into one contiguous (pinned) batch buffer; 0 = ok */
 int sd2_wire_gather(const void* const* src, int n, long long bytes_each, void* dst);
 
+/* ---- row f1: glue kernels of the in-loop VAE encoder / CLIP text encoder (reference stable_diffusion.py:160-174); the
+ *      contractions of both networks go through sd2_gemm, the norms through sd2_groupnorm_fwd / sd2_layernorm_fwd ------
+ * images [B,C,H,W] (C <= 8, src_dtype) -> bf16 [B*H*W][8] rows, zero padded; and back with an affine + clamp
+ * (dst = clamp(src * scale + shift, lo, hi): the `(image / 2 + 0.5).clamp(0, 1)` of generate(), :380). */
+int sd2_nchw_to_nhwc8(sd2_ctx* ctx, const void* src, int src_dtype, void* dst_nhwc8, int B, int C, int H, int W,
+                      sd2_stream stream);
+int sd2_nhwc8_to_nchw(sd2_ctx* ctx, const void* src_nhwc8, void* dst, int dst_dtype, int B, int C, int H, int W, float scale,
+                      float shift, float lo, float hi, sd2_stream stream);
+/* quant_conv (1x1, quant_w fp32 [8][8], quant_b fp32 [8]) on the encoder moments (bf16 [B*H*W][8]) +
+ * DiagonalGaussianDistribution.sample() with the caller's noise [B,4,H,W] + `latents *= scale`; latents / mean_out
+ * (optional) are [B,4,H,W] in `dtype`, every tensor op of the reference rounded in that dtype. */
+int sd2_vae_sample(sd2_ctx* ctx, const void* moments_nhwc8, const float* quant_w, const float* quant_b, const void* noise,
+                   void* latents, void* mean_out, int dtype, int B, int H, int W, float scale, sd2_stream stream);
+/* x bf16 [rows][D] = token_embedding[ids[r]] + position_embedding[r % L] (fp32 tables) */
+int sd2_embed_tokens(sd2_ctx* ctx, const int64_t* ids, const float* token_embedding, const float* position_embedding, void* x,
+                     long long rows, int L, int D, int vocab, sd2_stream stream);
+/* P bf16 [rows][ldp] = softmax of S fp32 [rows][lds] over columns <= (row % period) (causal), zeros elsewhere */
+int sd2_softmax_causal_fwd(sd2_ctx* ctx, const float* S, long long lds, void* P, long long ldp, long long rows, int cols,
+                           int period, sd2_stream stream);
+/* 1x1 convolution over <= 8 channels on NHWC8 rows: out[r][o] = b[o] + sum_k w[o][k] in[r][k] (w fp32 [n_out][n_in]);
+ * the VAE decoder's post_quant_conv */
+int sd2_pixel_linear8(sd2_ctx* ctx, const void* in_nhwc8, const float* w, const float* b, void* out_nhwc8, long long n, int n_in,
+                      int n_out, sd2_stream stream);
+/* y = gelu(x) (erf form), bf16, n % 8 == 0 */
+int sd2_gelu_fwd(sd2_ctx* ctx, const void* x, void* y, long long n, sd2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
