@@ -185,26 +185,26 @@ def _device_of(module):
 # ==================================================================================================== VAE
 class DiagonalGaussianDistribution:
     """`latent_dist` of `AutoencoderKL.encode`: sample() draws torch.randn from the default generator (shape / dtype /
-    device of the mean, like diffusers' randn_tensor) and applies it in the fused sampling kernel."""
+    device of the mean, like diffusers' randn_tensor: ONE draw for the whole batch) and applies it in the fused
+    quant_conv + sampling kernel."""
 
-    def __init__(self, vae, eng, B, h, w, dtype):
-        self._vae, self._eng, self._shape, self._dtype = vae, eng, (B, vae.config['latent_channels'], h, w), dtype
+    def __init__(self, eng, moments8, shape, dtype):
+        self._eng, self._moments8, self._shape, self._dtype = eng, moments8, shape, dtype
+
+    def _apply(self, noise, scale, want_mean):
+        eng = self._eng
+        B, _, h, w = self._shape
+        z = torch.empty_like(noise)
+        mean = torch.empty_like(noise) if want_mean else None
+        ops.vae_sample(eng.ctx, self._moments8, eng.p32('quant_conv.weight'), eng.p32('quant_conv.bias'), noise, z, mean, B, h, w, scale)
+        return mean if want_mean else z
 
     def sample(self, generator=None, scale=1.0):
-        eng = self._eng
-        noise = torch.randn(self._shape, generator=generator, device=eng.dev, dtype=self._dtype)
-        z = torch.empty_like(noise)
-        B, _, h, w = self._shape
-        ops.vae_sample(eng.ctx, eng.moments8, eng.p32('quant_conv.weight'), eng.p32('quant_conv.bias'), noise, z, None, B, h, w, scale)
-        return z
+        noise = torch.randn(self._shape, generator=generator, device=self._eng.dev, dtype=self._dtype)
+        return self._apply(noise, scale, False)
 
     def mode(self):
-        eng = self._eng
-        B, _, h, w = self._shape
-        noise = torch.zeros(self._shape, device=eng.dev, dtype=self._dtype)
-        z, mean = torch.empty_like(noise), torch.empty_like(noise)
-        ops.vae_sample(eng.ctx, eng.moments8, eng.p32('quant_conv.weight'), eng.p32('quant_conv.bias'), noise, z, mean, B, h, w, 1.0)
-        return mean
+        return self._apply(torch.zeros(self._shape, device=self._eng.dev, dtype=self._dtype), 1.0, True)
 
 
 class AutoencoderKL(nn.Module):
@@ -247,6 +247,7 @@ class AutoencoderKL(nn.Module):
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
         self.requires_grad_(False)
         self._arena, self._engines = None, {}
+        self.max_chunk = 16  # images per encoder / decoder pass (the reference's microbatch)
 
     @property
     def device(self):
@@ -305,16 +306,31 @@ class AutoencoderKL(nn.Module):
         return e
 
     def encode(self, x, return_dict=True):
-        """x: images (B, C, H, W), any float dtype.  Returns {'latent_dist': DiagonalGaussianDistribution}."""
+        """x: images (B, C, H, W), any float dtype.  Returns {'latent_dist': DiagonalGaussianDistribution}.  Batches larger
+        than `max_chunk` images go through the encoder in chunks (the activations of a 512^2 image are ~1.3 GB); only the
+        8-channel moments of every chunk are kept."""
         B, Cc, H, W = x.shape
         if Cc != self.config['in_channels']:
             raise ValueError(f'expected {self.config["in_channels"]} image channels, got {Cc}')
         if x.device.type != 'cuda':
             raise RuntimeError('diffusion_b200 needs CUDA (sm_100a) tensors: there is no CPU fallback')
-        e = self._encoder_engine(B, H, W)
-        ops.nchw_to_nhwc8(e.ctx, x.contiguous(), e.in_x8, B, Cc, H, W)
-        e.run()
-        return _Out(latent_dist=DiagonalGaussianDistribution(self, e, B, e.out_hw[0], e.out_hw[1], x.dtype))
+        x = x.contiguous()
+        moments, e, b0 = None, None, 0
+        while b0 < B:
+            n = min(self.max_chunk, B - b0)
+            e = self._encoder_engine(n, H, W)
+            ops.nchw_to_nhwc8(e.ctx, x[b0:b0 + n], e.in_x8, n, Cc, H, W)
+            e.run()
+            if n == B:
+                moments = e.moments8
+                break
+            h, w = e.out_hw
+            if moments is None:
+                moments = torch.empty(B * h * w, 8, dtype=BF16, device=x.device)
+            ops.copy2d(e.ctx, e.moments8, moments[b0 * h * w:(b0 + n) * h * w], n * h * w, 8)
+            b0 += n
+        h, w = e.out_hw
+        return _Out(latent_dist=DiagonalGaussianDistribution(e, moments, (B, self.config['latent_channels'], h, w), x.dtype))
 
     # ---- decoder
     def _decoder_engine(self, B, h, w):
@@ -358,11 +374,17 @@ class AutoencoderKL(nn.Module):
             raise ValueError(f'expected {self.config["latent_channels"]} latent channels, got {L}')
         if z.device.type != 'cuda':
             raise RuntimeError('diffusion_b200 needs CUDA (sm_100a) tensors: there is no CPU fallback')
-        e = self._decoder_engine(B, h, w)
-        ops.nchw_to_nhwc8(e.ctx, z.contiguous(), e.in_z8, B, L, h, w)
-        e.run()
-        img = torch.empty(B, self.config['out_channels'], e.out_hw[0], e.out_hw[1], dtype=z.dtype, device=z.device)
-        ops.nhwc8_to_nchw(e.ctx, e.image8, img, B, self.config['out_channels'], e.out_hw[0], e.out_hw[1])
+        z = z.contiguous()
+        img, b0 = None, 0
+        while b0 < B:
+            n = min(self.max_chunk, B - b0)
+            e = self._decoder_engine(n, h, w)
+            ops.nchw_to_nhwc8(e.ctx, z[b0:b0 + n], e.in_z8, n, L, h, w)
+            e.run()
+            if img is None:
+                img = torch.empty(B, self.config['out_channels'], e.out_hw[0], e.out_hw[1], dtype=z.dtype, device=z.device)
+            ops.nhwc8_to_nchw(e.ctx, e.image8, img[b0:b0 + n], n, self.config['out_channels'], e.out_hw[0], e.out_hw[1])
+            b0 += n
         return _Out(sample=img)
 
 
@@ -435,4 +457,4 @@ class CLIPTextModel(nn.Module):
         e = self._engine(B, L)
         e.ids.copy_(input_ids.reshape(-1))
         e.run()
-        return _Out(last_hidden_state=e.out.view(B, L, -1))
+        return _Out(last_hidden_state=e.out.view(B, L, -1).clone())  # the engine's output buffer is reused by the next call

@@ -224,3 +224,60 @@ def test_in_loop_training_step_matches_oracle():
     cos = [F.cosine_similarity(model.unet.get_parameter(n).grad.flatten(), p.grad.float().flatten(), dim=0).item()
            for n, p in oracle.unet.named_parameters()]
     assert min(cos) > 0.98 and sum(cos) / len(cos) > 0.995, (min(cos), sum(cos) / len(cos))
+
+
+def test_vae_chunked_passes_keep_one_noise_draw():
+    """Batches above `max_chunk` run the encoder chunk by chunk but draw the posterior noise once, like the reference."""
+    from oracle.vae import TINY_VAE_CONFIG
+    _, vae = _vae_pair(TINY_VAE_CONFIG)
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.rand(5, 3, 64, 64, device=DEV, generator=g) * 2 - 1
+    torch.manual_seed(3)
+    z_one = vae.encode(x)['latent_dist'].sample()
+    off = torch.cuda.default_generators[0].get_offset()
+    vae.max_chunk = 2  # 2 + 2 + 1
+    torch.manual_seed(3)
+    z_chunks = vae.encode(x)['latent_dist'].sample()
+    assert torch.cuda.default_generators[0].get_offset() == off
+    assert _rel(z_chunks, z_one) < 1e-2 and _cos(z_chunks, z_one) > 0.9999
+    img_chunks = vae.decode(z_one.float()).sample
+    vae.max_chunk = 16
+    img_one = vae.decode(z_one.float()).sample
+    assert img_one.shape == (5, 3, 64, 64) and _rel(img_chunks, img_one) < 1e-2
+
+
+def test_generate_images_end_to_end():
+    """generate(): token ids -> text tower -> DDIM/CFG loop -> VAE decode -> [0, 1] images, against the oracle pipeline."""
+    from transformers import CLIPTextConfig
+    from transformers import CLIPTextModel as HFText
+    from diffusion_b200.encoders import SD2_TEXT_CONFIG
+    from diffusion_b200.model import stable_diffusion_2
+    from oracle.ddim import DDIMSchedulerOracle, generate_latents
+    from oracle.stable_diffusion import StableDiffusionOracle
+    from oracle.unet import TINY_UNET_CONFIG
+    from oracle.vae import TINY_VAE_CONFIG, AutoencoderKLOracle
+    dev = torch.device('cuda', 0)
+    tcfg = dict(SD2_TEXT_CONFIG)
+    tcfg['num_hidden_layers'] = 2
+    torch.manual_seed(17)
+    oracle = StableDiffusionOracle(TINY_UNET_CONFIG).to(dev)
+    ovae = AutoencoderKLOracle(**TINY_VAE_CONFIG).to(dev)
+    hf = HFText(CLIPTextConfig(**tcfg, projection_dim=512)).to(dev).eval()
+    model = stable_diffusion_2(pretrained=False, precomputed_latents=False, fsdp=False, unet_config=TINY_UNET_CONFIG,
+                               vae_config=TINY_VAE_CONFIG, text_encoder_config=tcfg)
+    model.unet.load_state_dict(oracle.unet.state_dict())
+    model.vae.load_state_dict(ovae.state_dict())
+    model.text_encoder.load_state_dict(hf.state_dict(), strict=False)
+    g = torch.Generator(device=dev).manual_seed(1)
+    ids = torch.randint(0, tcfg['vocab_size'], (2, 77), device=dev, generator=g)
+    neg = torch.randint(0, tcfg['vocab_size'], (2, 77), device=dev, generator=g)
+    img = model.generate(tokenized_prompts=ids, tokenized_negative_prompts=neg, height=128, width=128, num_inference_steps=3,
+                         guidance_scale=3.0, seed=7, progress_bar=False)
+    assert img.shape == (2, 3, 128, 128) and img.dtype == torch.float32
+    assert img.min().item() >= 0.0 and img.max().item() <= 1.0
+    with torch.no_grad():
+        lat = generate_latents(oracle.unet, DDIMSchedulerOracle(), hf(ids)[0], hf(neg)[0], 128, 128, 3, 3.0, seed=7)
+        ref = (ovae.decode(1 / 0.18215 * lat) / 2 + 0.5).clamp(0, 1)
+    assert _cos(img, ref) > 0.995 and (img - ref).abs().mean().item() < 2e-2, (_cos(img, ref), (img - ref).abs().mean().item())
+    with pytest.raises(ValueError):  # no tokenizer files offline: string prompts need one
+        model.generate(prompt=['a photo'], height=128, width=128, progress_bar=False)
