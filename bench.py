@@ -152,14 +152,20 @@ def run_ours(args):
     from diffusion_b200.model import stable_diffusion_2
     B, R = args.batch, args.latent
     torch.manual_seed(17)  # identical init on every rank (reference train.py:29) ...
-    model = stable_diffusion_2(pretrained=False, precomputed_latents=True, fsdp=False)
+    model = stable_diffusion_2(pretrained=False, precomputed_latents=not args.in_loop, fsdp=False)
     from diffusion_b200.optim import FusedAdamW
     opt = FusedAdamW(model.parameters(), lr=1.0e-4, weight_decay=0.01)  # reference yaml :55-58 (torch AdamW defaults)
     torch.manual_seed(17 + rank)  # ... then per-rank noise / timestep / data streams (composer reseeds seed + rank)
-    lat_h = torch.randn(B, 4, R, R).to(torch.bfloat16).pin_memory()
-    ctx_h = torch.randn(B, 77, 1024).to(torch.bfloat16).pin_memory()
-    lat_d, ctx_d = lat_h.to(dev), ctx_h.to(dev)
-    batch = {'image_latents': lat_d, 'caption_latents': ctx_d}
+    if args.in_loop:  # BASELINE config 5: VAE encoder + CLIP text encoder inside the step (images ~U(-1,1), random token ids)
+        lat_h = (torch.rand(B, 3, R * 8, R * 8) * 2 - 1).pin_memory()
+        ctx_h = torch.randint(0, 49408, (B, 77)).pin_memory()
+        lat_d, ctx_d = lat_h.to(dev), ctx_h.to(dev)
+        batch = {'image': lat_d, 'captions': ctx_d}
+    else:
+        lat_h = torch.randn(B, 4, R, R).to(torch.bfloat16).pin_memory()
+        ctx_h = torch.randn(B, 77, 1024).to(torch.bfloat16).pin_memory()
+        lat_d, ctx_d = lat_h.to(dev), ctx_h.to(dev)
+        batch = {'image_latents': lat_d, 'caption_latents': ctx_d}
     eng = model.unet.engine(B, R, R, 77)
     if world > 1:
         eng.enable_grad_sync()
@@ -182,6 +188,10 @@ def run_ours(args):
     launches_per_step = eng.ctx.launches - l0
     if not args.no_graphs:
         eng.capture_graphs()
+        if args.in_loop:
+            for m in (model.vae, model.text_encoder):
+                for fe in m._engines.values():
+                    fe.capture()
     for _ in range(args.warmup):
         step(False)
 
@@ -261,13 +271,15 @@ def run_ours(args):
         'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': f'SD-2-base-{R * 8} UNet train step: K1 + UNet fwd + MSE + bwd + grad all-reduce + AdamW, '
-                               f'precomputed latents, random init', 'per_gpu_microbatch': B, 'global_batch': B * world,
+                               + ('in-loop VAE encoder + CLIP text encoder (precomputed_latents=false), ' if args.in_loop else 'precomputed latents, ')
+                               + 'random init', 'per_gpu_microbatch': B, 'global_batch': B * world,
                    'latent': [4, R, R], 'context': [77, 1024], 'params': 865910724, 'parallelism': f'dp{world}',
                    'cuda_graphs': not args.no_graphs,
                    'l2': 'no explicit flush: every step streams 3.5 GB of fp32 parameters + optimizer state and tens of GB of '
                          'activations, far beyond the 126 MB L2'},
         'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': (lat_h.numel() + ctx_h.numel()) * 2, 'd2h_bytes_per_step': 4},
+                'h2d_bytes_per_step': lat_h.numel() * lat_h.element_size() + ctx_h.numel() * ctx_h.element_size(),
+                'd2h_bytes_per_step': 4},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
         'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_e2e,
     }
@@ -285,13 +297,15 @@ def main():
     ap.add_argument('--latent', type=int, default=32, help='latent side: 32 = SD-2-base-256 (default), 64 = SD-2-base-512')
     ap.add_argument('--batch', type=int, default=None,
                     help='per-GPU microbatch (default 256 at 256^2, 64 at 512^2; the reference yaml uses 16 on 40/80 GB GPUs)')
+    ap.add_argument('--in-loop', action='store_true',
+                    help='BASELINE config 5: precomputed_latents=false, VAE encoder + CLIP text encoder run inside the step')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-step', action='store_true',
                     help='run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 256 if args.latent <= 32 else 64
+        args.batch = (256 if args.latent <= 32 else 64) if not args.in_loop else 32
     if args.impl == 'reference':
         run_reference(args)
     else:
