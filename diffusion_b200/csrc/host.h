@@ -86,6 +86,13 @@ inline int check_launch(sd2_ctx* ctx, const char* what, int nlaunch = 1) {
   return 0;
 }
 inline int grid_for(long long work_items, int threads, int num_sms, int max_waves = 8) {
+  static int scale_pct = -1;  // tuning aid: SD2_WAVES_PCT scales the grid cap of every grid-stride kernel (100 = as written)
+  if (scale_pct < 0) {
+    const char* e = getenv("SD2_WAVES_PCT");
+    scale_pct = e ? atoi(e) : 100;
+    if (scale_pct < 1) scale_pct = 100;
+  }
+  max_waves = (int)(((long long)max_waves * scale_pct + 99) / 100);
   long long b = (work_items + threads - 1) / threads;
   long long cap = (long long)num_sms * max_waves;
   if (b > cap) b = cap;

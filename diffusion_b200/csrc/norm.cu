@@ -366,6 +366,7 @@ static GnClusterCfg gn_cluster_cfg(int HW, int C, int ntensors_staged) {
   // tuning overrides (tools/norm_bench.py sweeps them): SD2_GN_P0_KB = pass-0 shared-memory limit, SD2_GN_P0_THREADS
   static const int p0_kb = getenv("SD2_GN_P0_KB") ? atoi(getenv("SD2_GN_P0_KB")) : 110;
   static const int p0_threads = getenv("SD2_GN_P0_THREADS") ? atoi(getenv("SD2_GN_P0_THREADS")) : 256;
+  static const int p0_maxnc = getenv("SD2_GN_P0_MAXNC") ? atoi(getenv("SD2_GN_P0_MAXNC")) : 8;
   for (int pass = 0; pass < 3 && !c.ok; ++pass) {  // pass 2: 16-CTA (non-portable) clusters, the last resort
     const int target = pass == 0 ? p0_threads : 512;
     c.RL = target / V;
@@ -374,7 +375,7 @@ static GnClusterCfg gn_cluster_cfg(int HW, int C, int ntensors_staged) {
     if (c.threads > 512) continue;
     const size_t fixed = (size_t)c.RL * C * 2 * 4 + (size_t)C * 2 * 4 + 64 * 2 * 4 * 2 + GNC_NSUB * 8 + 256;
     const size_t limit = pass == 0 ? (size_t)p0_kb * 1024 : 225 * 1024;
-    for (int nc = (pass == 2 ? 16 : 1); nc <= (pass == 2 ? 16 : 8); nc *= 2) {
+    for (int nc = (pass == 2 ? 16 : 1); nc <= (pass == 2 ? 16 : (pass == 0 ? p0_maxnc : 8)); nc *= 2) {
       if (HW % nc != 0) break;
       const int px = HW / nc;
       const size_t chunk = (size_t)px * C * 2 * ntensors_staged;

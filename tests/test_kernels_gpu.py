@@ -359,7 +359,8 @@ def test_layout_kernels(ctx):
     close(cat[:, Cc:], 2 * x.float(), name='copy2d acc')
 
 
-@pytest.mark.parametrize('groups,rpg,N', [(1, 16384, 320), (16, 1024, 320), (16, 16, 1280), (1, 37, 64)])
+@pytest.mark.parametrize('groups,rpg,N', [(1, 16384, 320), (16, 1024, 320), (16, 16, 1280), (1, 37, 64), (1, 4099, 8), (1, 1025, 2048),
+                                          (1, 515, 2560), (3, 33, 5120), (1, 2048, 10240)])
 def test_colsum(ctx, groups, rpg, N):
     from diffusion_b200 import ops
     x = bf(groups * rpg, N, seed=1)
