@@ -36,7 +36,30 @@ def compute():
     }
 
 
+def compute_next_rows():
+    """tests/golden/next_rows.pt: DDIM scheduler steps (f4) and the tiny VAE oracle (f1) on seeded inputs."""
+    from oracle.ddim import DDIMSchedulerOracle
+    from oracle.vae import TINY_VAE_CONFIG, AutoencoderKLOracle
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(9)
+    x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    sch = DDIMSchedulerOracle()
+    sch.set_timesteps(50)
+    steps = {t: sch.step(e, t, x).clone() for t in (981, 501, 1)}
+    sch.set_timesteps(4)
+    ts4 = sch.timesteps.clone()
+    torch.manual_seed(11)
+    vae = AutoencoderKLOracle(**TINY_VAE_CONFIG)
+    img = torch.rand(1, 3, 32, 32, generator=g) * 2 - 1
+    with torch.no_grad():
+        mom = vae.moments(img)
+        dec = vae.decode(torch.randn(1, 4, 4, 4, generator=g))
+    return {'ddim_prev_981': steps[981], 'ddim_prev_501': steps[501], 'ddim_prev_1': steps[1], 'ddim_timesteps_4': ts4,
+            'vae_moments': mom.clone(), 'vae_decode_slice': dec[0, :, :2, :6].clone(), 'vae_decode_sum': dec.double().sum().float()}
+
+
 if __name__ == '__main__':
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tiny_step.pt')
-    torch.save(compute(), out)
-    print('wrote', out)
+    here = os.path.dirname(os.path.abspath(__file__))
+    torch.save(compute(), os.path.join(here, 'tiny_step.pt'))
+    torch.save(compute_next_rows(), os.path.join(here, 'next_rows.pt'))
+    print('wrote', here)

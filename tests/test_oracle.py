@@ -108,3 +108,47 @@ def test_golden_fixture():
     assert torch.equal(got['randint_seed17_off0_B16'], want['randint_seed17_off0_B16'])
     assert torch.equal(got['randint_seed123_off8_B300'], want['randint_seed123_off8_B300'])
     assert torch.allclose(got['alphas_cumprod_0_499_999'], want['alphas_cumprod_0_499_999'])
+
+
+def test_golden_fixture_next_rows():
+    """DDIM steps and the tiny VAE oracle against tests/golden/next_rows.pt (generator: tests/golden/make_golden.py)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(GOLDEN))
+    from make_golden import compute_next_rows
+    want = torch.load(os.path.join(os.path.dirname(GOLDEN), 'next_rows.pt'))
+    got = compute_next_rows()
+    assert set(got) == set(want)
+    assert torch.equal(got['ddim_timesteps_4'], want['ddim_timesteps_4']) and want['ddim_timesteps_4'].tolist() == [751, 501, 251, 1]
+    for k in ('ddim_prev_981', 'ddim_prev_501', 'ddim_prev_1'):
+        assert torch.allclose(got[k], want[k], rtol=1e-6, atol=1e-6), k
+    assert torch.allclose(got['vae_moments'], want['vae_moments'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(got['vae_decode_slice'], want['vae_decode_slice'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(got['vae_decode_sum'], want['vae_decode_sum'], rtol=1e-4, atol=1e-2)
+
+
+def test_vae_oracle_inventory_and_downsample_semantics():
+    """83,653,863 parameters / 248 tensors for the SD-2 VAE (the published size of AutoencoderKL) with the product
+    skeleton's names; Downsample2D pads bottom / right only."""
+    from diffusion_b200.encoders import AutoencoderKL
+    from oracle.vae import AutoencoderKLOracle
+    o = AutoencoderKLOracle()
+    shapes = {n: tuple(p.shape) for n, p in o.named_parameters()}
+    assert sum(p.numel() for p in o.parameters()) == 83653863 and len(shapes) == 248
+    assert shapes == {n: tuple(p.shape) for n, p in AutoencoderKL().named_parameters()}
+    x = torch.zeros(1, 128, 4, 4)
+    x[0, 0, 3, 3] = 1.0  # bottom-right pixel: seen by the last output position through the (0,1,0,1) padding
+    conv = o.encoder.down_blocks[0].downsamplers[0].conv
+    y = conv(torch.nn.functional.pad(x, (0, 1, 0, 1)))
+    assert y.shape == (1, 128, 2, 2)
+    assert torch.allclose(y[0, :, 1, 1] - conv.bias, conv.weight[:, 0, 1, 1], atol=1e-6)
+
+
+def test_text_skeleton_matches_transformers_names():
+    from transformers import CLIPTextConfig
+    from transformers import CLIPTextModel as HFText
+    from diffusion_b200.encoders import SD2_TEXT_CONFIG, CLIPTextModel
+    cfg = dict(SD2_TEXT_CONFIG)
+    cfg['num_hidden_layers'] = 1
+    a = {n: tuple(p.shape) for n, p in HFText(CLIPTextConfig(**cfg, projection_dim=512)).named_parameters()}
+    b = {n: tuple(p.shape) for n, p in CLIPTextModel(**cfg).named_parameters()}
+    assert a == b
