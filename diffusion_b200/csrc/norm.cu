@@ -356,6 +356,11 @@ struct GnClusterCfg {
 };
 // smallest cluster whose per-CTA chunk fits: prefer <= 100 KB (two CTAs per SM), else <= 190 KB; NC = 16 needs the
 // non-portable cluster-size opt-in.
+// Measured alternatives that LOST at the B=128 shapes (profiles/r01_norm_microbench_B128.md): 16-CTA clusters with 3-4 CTAs
+// per SM (61 -> 65..97 us at 131072 x 320), and a persistent one-CTA-per-SM variant with two chunk buffers that prefetches
+// the next image under the current apply pass (61 -> 72 us: every iteration waits at the cluster barrier for the slowest
+// of its 8 CTAs and no second CTA is resident to fill that wait).  The apply pass with SiLU is MUFU-bound at about the
+// HBM time (2 MUFU per element at 16 / clk / SM), so the remaining lever is GN statistics from the producer's epilogue.
 static GnClusterCfg gn_cluster_cfg(int HW, int C, int ntensors_staged) {
   GnClusterCfg c;
   c.ok = false;

@@ -247,7 +247,10 @@ def test_attention_pieces(ctx, B, heads, Nq, Nk):
 
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize('B,HW,Cc,silu', [(16, 1024, 320, 1), (16, 64, 1920, 1), (2, 1024, 64, 1), (2, 16, 256, 0),
-                                         (4, 4096, 320, 0), (16, 16, 2560, 1), (2, 256, 192, 1)])
+                                         (4, 4096, 320, 0), (16, 16, 2560, 1), (2, 256, 192, 1),
+                                         # batches large enough for the persistent (double-buffered) forward: ragged last round,
+                                         # cluster sizes 8 / 4 / 1
+                                         (45, 1024, 320, 1), (83, 256, 640, 0), (301, 16, 1280, 1)])
 def test_groupnorm(ctx, B, HW, Cc, silu):
     from diffusion_b200 import ops
     G, eps = 32, 1e-5
