@@ -305,7 +305,7 @@ def main():
                     help='run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = (256 if args.latent <= 32 else 64) if not args.in_loop else 32
+        args.batch = 256 if args.latent <= 32 else 64
     if args.impl == 'reference':
         run_reference(args)
     else:

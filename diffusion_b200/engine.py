@@ -182,7 +182,7 @@ class ParamArena:
 
 class Engine:
 
-    def __init__(self, unet, B, H, W, L, shared=None, io=None, own_scratch=False):
+    def __init__(self, unet, B, H, W, L, shared=None, io=None, own_scratch=False, forward_only=False):
         """io: optional dict of externally owned static buffers (in_x8, in_temb, in_ctx, pred8, dpred8) - used by
         DualEngine, whose two half-batch engines work on slices of full-batch buffers.  own_scratch: do not share the
         split-K workspaces with `shared` (engines that run concurrently need private scratch)."""
@@ -215,6 +215,7 @@ class Engine:
         self.pred8 = io.get('pred8')
         self.dpred8 = io['dpred8'] if 'dpred8' in io else torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
         self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.forward_only = forward_only  # sampling / eval: no backward schedule, no gradient buffers
         self._build()
         self.graph_fwd = self.graph_bwd = None
 
@@ -649,6 +650,11 @@ class Engine:
             self.b(ops.unpad_accum_rows, gb8, 8, self.g32('conv_out.bias'), 4, 1, True)
 
         self._bwd_builders.append(head_bwd)
+        if self.forward_only:
+            self._bwd_builders = None
+            self.buckets, self.segments = [], []
+            self._hoist_forward_side_ops()
+            return
         for builder in reversed(self._bwd_builders):
             self._touched = set()
             builder()
@@ -737,6 +743,8 @@ class Engine:
                 op()
 
     def run_backward(self):
+        if self.forward_only:
+            raise RuntimeError('this engine was built forward-only (sampling / eval): it has no backward schedule')
         sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
         if not sync:
             if self.graph_bwd is not None:
@@ -912,6 +920,8 @@ class DualEngine:
                     op()
 
     def run_backward(self):
+        if self.forward_only:
+            raise RuntimeError('this engine was built forward-only (sampling / eval): it has no backward schedule')
         sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
         start = 0
         for k, end in enumerate(self.segments):

@@ -357,7 +357,7 @@ class StableDiffusion(ComposerModel):
         self.inference_scheduler.set_timesteps(num_inference_steps)
         latents = (latents * self.inference_scheduler.init_noise_sigma).contiguous()
         nb = 2 if do_cfg else 1
-        eng = self.unet.engine(nb * batch_size, h, w, text_embeddings.shape[1])
+        eng = self.unet.engine(nb * batch_size, h, w, text_embeddings.shape[1], forward_only=True)
         eng.set_context(text_embeddings.to(device))
         for half in range(nb):  # UNet input of the first step: bf16 NHWC8 copy of the initial latents, per CFG half
             ops.nchw4_to_nhwc8(eng.ctx, latents, eng.in_x8[half * batch_size * h * w:(half + 1) * batch_size * h * w],
@@ -376,6 +376,8 @@ class StableDiffusion(ComposerModel):
             eng.run_forward()
             sb, sa, sap, dc = (float(x) for x in self.inference_scheduler.step_scalars(t))
             ops.cfg_ddim_step(eng.ctx, eng.pred8, latents, eng.in_x8, batch_size, h, w, do_cfg, guidance_scale, sb, sa, sap, dc)
+            if eng.graph_fwd is None and len(steps) > 2:
+                eng.capture_graphs()  # the remaining steps replay the forward schedule as one CUDA graph
         if output_type == 'latent':
             return latents.detach()
         latents = 1 / 0.18215 * latents

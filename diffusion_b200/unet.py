@@ -140,7 +140,7 @@ class UNet2DConditionModel(nn.Module):
         self._engines = {}
 
     # ------------------------------------------------------------------------------------------------------------
-    def engine(self, B, H, W, ctx_len):
+    def engine(self, B, H, W, ctx_len, forward_only=False):
         """Static kernel schedule for one input geometry (built lazily, cached)."""
         import os
         from diffusion_b200.engine import DualEngine, Engine
@@ -148,7 +148,7 @@ class UNet2DConditionModel(nn.Module):
         from diffusion_b200.ops import dry_run
         if dev.type != 'cuda' and not dry_run():
             raise RuntimeError('diffusion_b200 runs on sm_100a GPUs only (no CPU fallback): move the model to CUDA')
-        key = (B, H, W, ctx_len, dev.index)
+        key = (B, H, W, ctx_len, dev.index, bool(forward_only))
         eng = self._engines.get(key)
         if eng is None or not eng.params_bound():
             prev = next(iter(self._engines.values()), None)
@@ -156,7 +156,10 @@ class UNet2DConditionModel(nn.Module):
             # 27.5 ms vs 25.3 ms single-chain - persistent one-CTA-per-SM GEMM kernels of two streams do not share the
             # SMs well - so the single chain stays the default.
             dual = B >= 8 and B % 2 == 0 and os.environ.get('SD2_DUAL_CHAIN') == '1'
-            eng = (DualEngine if dual else Engine)(self, B, H, W, ctx_len, shared=prev)
+            if forward_only:
+                eng = Engine(self, B, H, W, ctx_len, shared=prev, forward_only=True)
+            else:
+                eng = (DualEngine if dual else Engine)(self, B, H, W, ctx_len, shared=prev)
             self._engines[key] = eng
         return eng
 

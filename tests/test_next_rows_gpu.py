@@ -71,6 +71,10 @@ def test_generate_latents_match_oracle_loop(gs):
     trace = []
     want = generate_latents(oracle.unet, DDIMSchedulerOracle(), emb, neg, 256, 256, steps, gs, seed=1138, trace=trace)
     assert got.shape == want.shape == (2, 4, 32, 32) and got.dtype == torch.float32
+    sampler = [e for k, e in model.unet._engines.items() if k[-1]]
+    assert sampler and all(e.forward_only and len(e.bwd) == 0 and e.graph_fwd is not None for e in sampler)
+    with pytest.raises(RuntimeError):
+        sampler[0].run_backward()
     assert torch.isfinite(got).all()
     cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item()
     rel = ((got - want).norm() / want.norm()).item()
