@@ -533,7 +533,7 @@ cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int
                                    long long ldr, void* out, long long ldo, int out_f32, cudaStream_t stream) {
   const long long nvec = M * (N / 8);
   int blocks = (int)((nvec + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 24) blocks = 148 * 24;
   if (blocks < 1) blocks = 1;
   return launch_k(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, ws, splits, M, N, alpha, bias, rowbias,
                   rows_per_group, ld_rowbias, residual, ldr, out, ldo, out_f32);

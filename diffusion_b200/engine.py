@@ -882,6 +882,7 @@ class DualEngine:
         self.arena = self.halves[0].arena
         self.buckets, self.segments = self.halves[0].buckets, self.halves[0].segments
         self.graph_fwd = self.graph_bwd = None
+        self.forward_only = False
         self.ws = None  # no scratch to lend to later engines
 
     # ---- aggregate views used by tools / tests
