@@ -331,6 +331,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Split second barrier of the cluster kernels: a CTA may exit only after every peer has read its gpart.  Peers read it right
+// after the first barrier, so each CTA ARRIVES (relaxed: no memory to publish) as soon as its own remote reads are done and
+// WAITS only at the very end - by then everybody has long arrived, and the arrive no longer fences the apply pass's global
+// stores (ncu: `membar` + `barrier` were the top stall reasons of both kernels with the full barrier at the end).
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ float2 ld_dsmem_f2(const void* local_smem, uint32_t rank) {
   uint32_t ra;
   float2 v;
@@ -505,6 +511,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_cluster_kernel(const bf16* __re
     gtot[tid] = make_float2(dbv * inv_n, dsv * inv_n);
   }
   __syncthreads();
+  cluster_arrive_relaxed();  // this CTA's remote reads are done (see cluster_wait at the end)
   // ---- pass 2
   if (act) {
     float a[8], k1[8], k2[8];
@@ -534,7 +541,7 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_cluster_kernel(const bf16* __re
       store8(ob + (size_t)r * C, o);
     }
   }
-  cluster_sync_all();  // no CTA of the cluster exits while a peer may still read its gpart
+  cluster_wait();  // no CTA of the cluster exits while a peer may still read its gpart
 }
 
 // ---- single-pass GroupNorm forward on the same cluster skeleton: x crosses HBM once (staged in smem), statistics are
@@ -626,6 +633,7 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_cluster_kernel(const bf16* __re
     if (rank == 0) *reinterpret_cast<float2*>(stats + ((long long)b * G + tid) * 2) = make_float2(mean, rstd);
   }
   __syncthreads();
+  cluster_arrive_relaxed();
   if (act) {
     float sc[8], sh[8];
 #pragma unroll
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(512, 1) gn_fwd_cluster_kernel(const bf16* __re
       store8(ob + (size_t)r * C, xf);
     }
   }
-  cluster_sync_all();
+  cluster_wait();
 }
 
 template <typename... P, typename... A>
