@@ -262,9 +262,10 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, s_per = oracle_cpu_step_rate(R, 2, 2, 1, cores)
+        n_cpu = 8 if R <= 32 else 2  # ~10-20 s of host work
+        v, s_per = oracle_cpu_step_rate(R, 2, n_cpu, 1, cores)
         cpu = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': f'2 timed steps of batch 2 (of the {B}-image microbatch) after 1 warm-up, fp32 oracle, {s_per:.2f} s/step'}
+               'sample': f'{n_cpu} timed steps of batch 2 (of the {B}-image microbatch) after 1 warm-up, fp32 oracle, {s_per:.2f} s/step'}
     imgs = B * world * args.steps
     line = {
         'metric': METRIC, 'value': imgs / (ms_dev * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
