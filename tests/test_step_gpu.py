@@ -195,3 +195,37 @@ def test_dual_chain_engine_matches_oracle_and_single_chain(monkeypatch):
     for n, p in model_s.unet.named_parameters():
         c = F.cosine_similarity(p.grad.flatten().float(), g_dual[n].flatten().float(), dim=0).item()
         assert c > 0.999, (n, c)
+
+
+@pytest.mark.parametrize('B,H,W,L', [(2, 16, 32, 77), (1, 32, 16, 50), (5, 8, 8, 77)])
+def test_non_square_latents_and_other_context_lengths(B, H, W, L):
+    """Geometries the reference accepts but its recipes do not use: non-square latents, odd batch, shorter text context."""
+    from diffusion_b200.model import stable_diffusion_2
+    from oracle.stable_diffusion import StableDiffusionOracle, train_step
+    from oracle.unet import TINY_UNET_CONFIG
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(17)
+    oracle = StableDiffusionOracle(TINY_UNET_CONFIG).to(dev)
+    model = stable_diffusion_2(pretrained=False, precomputed_latents=True, unet_config=TINY_UNET_CONFIG, fsdp=False)
+    model.unet.load_state_dict(oracle.unet.state_dict())
+    g = torch.Generator(device=dev).manual_seed(B * 100 + H)
+    batch = {'image_latents': torch.randn(B, 4, H, W, device=dev, generator=g).to(torch.bfloat16),
+             'caption_latents': torch.randn(B, L, 1024, device=dev, generator=g).to(torch.bfloat16)}
+    torch.manual_seed(321)
+    out = model(batch)
+    loss = model.loss(out, batch)
+    loss.backward()
+    torch.manual_seed(321)
+    lo, oo = train_step(oracle, batch, autocast_dtype=torch.bfloat16)
+    assert torch.equal(out[2], oo[2]) and torch.equal(out[1].view(torch.int16), oo[1].view(torch.int16))
+    assert out[0].shape == (B, 4, H, W)
+    assert abs(loss.item() - lo.item()) <= 1e-2 * abs(lo.item()), (loss.item(), lo.item())
+    cos = _cosines(model, oracle)
+    # 8x8 latents put the mid block at 1x1: self-attention over a single token has exactly zero q / k gradients, for which a
+    # cosine is meaningless - there the product's gradient must vanish as well
+    dead = [n for n, p in oracle.unet.named_parameters() if p.grad.float().norm().item() < 1e-9]
+    for n in dead:
+        assert model.unet.get_parameter(n).grad.float().norm().item() < 1e-6, n
+        cos.pop(n)
+    assert len(dead) == (2 if H * W == 64 else 0), dead
+    assert min(cos.values()) > 0.98 and sum(cos.values()) / len(cos) > 0.998, sorted(cos.items(), key=lambda kv: kv[1])[:4]
