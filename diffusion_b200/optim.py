@@ -14,13 +14,19 @@ from diffusion_b200 import ops
 
 class FusedAdamW(torch.optim.Optimizer):
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, **_ignored):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False,
+                 keep_grads_bound=True, **_ignored):
         if amsgrad:
             raise ValueError('FusedAdamW: amsgrad is not implemented')
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError('FusedAdamW: invalid hyper-parameter')
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._grads_cleared = False
+        # True (default): zero_grad() leaves `.grad` viewing the cleared gradient arena, the next backward accumulates in place
+        # and hands autograd no gradient tensors.  A torch DistributedDataParallel wrapper (Composer's default for world > 1)
+        # needs its per-parameter hooks to fire: pass keep_grads_bound=False there (or skip the wrapper and use
+        # Engine.enable_grad_sync(), which overlaps the bucket all-reduces with backward itself).
+        self.keep_grads_bound = keep_grads_bound
 
     def _arena_of(self, group):
         """The engine arena holding every parameter (and gradient) of this group, if there is one."""
@@ -41,15 +47,23 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         cleared = True
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             lr, (b1, b2), eps, wd = group['lr'], group['betas'], group['eps'], group['weight_decay']
             arena = self._arena_of(group)
             if arena is not None:
-                st = self.state.setdefault('arena%d' % id(arena), {})
+                # keyed by the parameter-group index: stable across processes, so `state_dict()` / `load_state_dict()`
+                # (Composer checkpoints, reference train.py resume) carry the flat moments
+                st = self.state.setdefault('arena_group%d' % gi, {})
                 if not st:
                     st['step'] = 0
                     st['exp_avg'] = torch.zeros_like(arena.p32)
                     st['exp_avg_sq'] = torch.zeros_like(arena.p32)
+                if st['exp_avg'].numel() != arena.p32.numel():
+                    raise RuntimeError('FusedAdamW: the loaded optimizer state does not match this model\'s parameter arena')
+                for k in ('exp_avg', 'exp_avg_sq'):  # a checkpoint loaded with map_location='cpu'
+                    if st[k].device != arena.p32.device or st[k].dtype != torch.float32:
+                        st[k] = st[k].to(device=arena.p32.device, dtype=torch.float32).contiguous()
+                st['step'] = int(st['step'])
                 st['step'] += 1
                 ctx = ops.get_ctx(arena.p32.device)
                 ops.adamw_step(ctx, arena.p32, arena.g32, st['exp_avg'], st['exp_avg_sq'], arena.p16, lr, b1, b2, eps, wd,
@@ -76,7 +90,8 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=True):
         """The arena path has already cleared the gradients inside step(); keep the `.grad` views bound so that the
         next backward accumulates in place (no memset, no 686 gradient hand-offs through autograd)."""
-        if self._grads_cleared:
+        if self._grads_cleared and self.keep_grads_bound:
             self._grads_cleared = False
             return
+        self._grads_cleared = False
         super().zero_grad(set_to_none=set_to_none)

@@ -151,6 +151,23 @@ def test_fused_adamw_arena_path_matches_torch_adamw():
     # 2 * steps * lr = 6e-3, while the bulk of the parameters must agree closely
     assert worst <= 6.5e-3, worst
     assert total / count < 1e-4, total / count
+    # checkpoint / resume: optimizer + model state dicts into a fresh model and optimizer, one more identical step
+    import copy
+    sd_opt, sd_model = copy.deepcopy(opt_a.state_dict()), copy.deepcopy(model_a.state_dict())
+    _, model_c, _ = _pair(TINY_UNET_CONFIG, 2, 32, seed=99)
+    model_c.load_state_dict(sd_model)
+    opt_c = FusedAdamW(model_c.parameters(), lr=1e-3, weight_decay=0.01)
+    opt_c.load_state_dict(sd_opt)
+    for model, opt in ((model_a, opt_a), (model_c, opt_c)):
+        torch.manual_seed(500)
+        model.loss(model(batch), batch).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    assert opt_c.state['arena_group0']['step'] == 4
+    diff = max((pa - pc).abs().max().item() for pa, pc in zip(model_a.unet.parameters(), model_c.unet.parameters()))
+    assert diff <= 2.5e-3, diff  # one Adam step of lr 1e-3 apart at most (reduce-add order), not a restart of the moments
+    m_a, m_c = opt_a.state['arena_group0']['exp_avg'], opt_c.state['arena_group0']['exp_avg']
+    assert torch.nn.functional.cosine_similarity(m_a, m_c, dim=0).item() > 0.9999
 
 
 def test_dual_chain_engine_matches_oracle_and_single_chain(monkeypatch):
