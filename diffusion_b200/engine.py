@@ -190,7 +190,12 @@ class Engine:
         self.ctx = ops.get_ctx(dev)
         self.dev = dev
         self.cfg = unet.config
-        self.arena = shared.arena if (shared is not None and shared.arena.bound()) else ParamArena(unet, dev)
+        if shared is not None and shared.arena.bound():
+            self.arena = shared.arena
+        elif hasattr(unet, 'bind_arena'):
+            self.arena = unet.bind_arena()  # the module's own arena (bound early by the factory, see UNet2DConditionModel.bind_arena)
+        else:
+            self.arena = ParamArena(unet, dev)
         self.B, self.H, self.W, self.L = B, H, W, L
         self.fwd, self.bwd, self._bwd_builders = [], [], []
         self._touched, self.grad_ready = set(), {}

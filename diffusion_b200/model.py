@@ -468,4 +468,5 @@ def stable_diffusion_2(
                             precomputed_latents=precomputed_latents, encode_latents_in_fp16=encode_latents_in_fp16, fsdp=fsdp)
     if torch.cuda.is_available():
         model = model.to(torch.device('cuda', torch.cuda.current_device()))
+        model.unet.bind_arena()  # final parameter storage before any wrapper (DDP) looks at the parameters
     return model

@@ -138,8 +138,21 @@ class UNet2DConditionModel(nn.Module):
         self.conv_norm_out = nn.GroupNorm(g, boc[0], eps=eps)
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
         self._engines = {}
+        self._arena = None
 
     # ------------------------------------------------------------------------------------------------------------
+    def bind_arena(self):
+        """Move the parameters into the flat fp32 arena NOW (otherwise the first forward does it).  The factory calls this
+        right after the model reaches the GPU: wrappers that record parameter strides at construction time (torch
+        DistributedDataParallel) must see the final, arena-backed parameters - rebinding afterwards silently corrupts the
+        gradients DDP hands back (reproduced with a plain permuted-view parameter on CPU / gloo)."""
+        from diffusion_b200.engine import ParamArena
+        dev = self.conv_in.weight.device
+        arena = getattr(self, '_arena', None)
+        if arena is None or not arena.bound():
+            self._arena = ParamArena(self, dev)
+        return self._arena
+
     def engine(self, B, H, W, ctx_len, forward_only=False):
         """Static kernel schedule for one input geometry (built lazily, cached)."""
         import os
