@@ -1045,6 +1045,11 @@ class _UNetFn(torch.autograd.Function):
             arena.g32.zero_()
         eng.run_backward()
         if accumulate:  # gradients were accumulated in place into the arena that param.grad already views
+            if getattr(eng, 'ddp_compat', False):
+                # a DistributedDataParallel wrapper reduces `param.grad` from per-parameter autograd hooks, which only fire
+                # if autograd receives a gradient: hand it zero-stride zeros (`grad += 0`), the real gradient is in place
+                z = torch.zeros((), dtype=torch.float32, device=eng.dev)
+                return (None, None, None, None, None) + tuple(z.expand(p.shape) for _, p in plist)
             return (None,) * (5 + ctx_.nparams)
         grads = tuple(arena.grad_view(n) for n, _ in plist)
         return (None, None, None, None, None) + grads

@@ -139,6 +139,10 @@ class UNet2DConditionModel(nn.Module):
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
         self._engines = {}
         self._arena = None
+        # True under a torch DistributedDataParallel wrapper (or SD2_DDP_COMPAT=1): every backward hands autograd a gradient
+        # for every parameter so that the wrapper's reduction hooks fire, also when the gradients are accumulated in place
+        import os
+        self.ddp_compat = os.environ.get('SD2_DDP_COMPAT') == '1'
 
     # ------------------------------------------------------------------------------------------------------------
     def bind_arena(self):
@@ -174,6 +178,7 @@ class UNet2DConditionModel(nn.Module):
             else:
                 eng = (DualEngine if dual else Engine)(self, B, H, W, ctx_len, shared=prev)
             self._engines[key] = eng
+        eng.ddp_compat = self.ddp_compat
         return eng
 
     def forward(self, sample, timestep, encoder_hidden_states, **_unused):

@@ -68,8 +68,45 @@ def main():
     m_c = make()
     ddp_c = torch.nn.parallel.DistributedDataParallel(m_c, device_ids=[local])
     gc = grads_after(m_c, ddp_c, FusedAdamW(m_c.parameters(), lr=1e-3, keep_grads_bound=False))
+    # (c) Composer-style microbatching under the wrapper: two microbatches per step, no_sync() on all but the last, FusedAdamW
+    #     with bound gradients (in-place accumulation) -> needs unet.ddp_compat so the last microbatch fires the hooks
+    def accumulate_two(model, wrapped, sync_ctx):
+        model.zero_grad(set_to_none=True)
+        for mb in range(2):
+            torch.manual_seed(2000 + mb)
+            b = {k: v.roll(mb, 0) for k, v in batch.items()}
+            ctx = sync_ctx() if mb == 0 else contextlib.nullcontext()
+            with ctx:
+                (model.loss(wrapped(b), b) / 2).backward()
+        torch.cuda.synchronize()
+        return torch.cat([p.grad.float().flatten() for p in model.unet.parameters()])
+
+    import contextlib
+    m_d = make()
+    g_local = accumulate_two(m_d, m_d, contextlib.nullcontext)
+    g_want = g_local.clone()
+    dist.all_reduce(g_want)
+    g_want /= dist.get_world_size()
+    m_e = make()
+    m_e.unet.ddp_compat = True
+    ddp_e = torch.nn.parallel.DistributedDataParallel(m_e, device_ids=[local])
+    opt_e = FusedAdamW(m_e.parameters(), lr=0.0)  # lr 0: a first step only binds the gradients (zero_grad keeps them bound)
+    (m_e.loss(ddp_e(batch), batch)).backward()
+    opt_e.step()
+    opt_e.zero_grad()
+    assert m_e._last_engine.arena.grads_bound()
+    # accumulate on the bound, cleared arena (zero_grad(set_to_none=True) would unbind the gradients)
+    for mb in range(2):
+        torch.manual_seed(2000 + mb)
+        b = {k: v.roll(mb, 0) for k, v in batch.items()}
+        ctx = ddp_e.no_sync() if mb == 0 else contextlib.nullcontext()
+        with ctx:
+            (m_e.loss(ddp_e(b), b) / 2).backward()
+    torch.cuda.synchronize()
+    g_ddp = torch.cat([p.grad.float().flatten() for p in m_e.unet.parameters()])
+    cos_mb = torch.nn.functional.cosine_similarity(g_ddp, g_want, dim=0).item()
     res = {}
-    for name, gx in (('engine', ga), ('ddp+AdamW', gb), ('ddp+FusedAdamW', gc)):
+    for name, gx in (('engine', ga), ('ddp+AdamW', gb), ('ddp+FusedAdamW', gc), ('ddp+microbatches', g_ddp)):
         other = gx.clone()
         dist.broadcast(other, src=0)
         res[name] = (gx - other).abs().max().item()  # ranks agree?
@@ -78,7 +115,8 @@ def main():
     if rank == 1:
         print('max |grad(rank1) - grad(rank0)| per route:', res)
         print('cosine engine vs ddp+AdamW: %.6f, engine vs ddp+FusedAdamW: %.6f' % (cos_ab, cos_ac))
-        ok = all(v < 1e-6 for v in res.values()) and cos_ab > 0.995 and cos_ac > 0.995
+        print('microbatch accumulation under DDP no_sync + ddp_compat: cosine vs explicit average %.6f' % cos_mb)
+        ok = all(v < 1e-6 for v in res.values()) and cos_ab > 0.995 and cos_ac > 0.995 and cos_mb > 0.9999
         print('DDP ROUTES OK' if ok else 'DDP ROUTES MISMATCH')
     dist.destroy_process_group()
 
