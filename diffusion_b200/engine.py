@@ -725,6 +725,22 @@ class Engine:
         self.comm_stream = torch.cuda.Stream(self.dev) if self.dev.type == 'cuda' else None
         self.sync_grads = True
 
+    def no_sync(self):
+        """Context manager: backward passes inside accumulate locally (the analogue of DistributedDataParallel.no_sync for
+        all but the last microbatch of an optimizer step)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            prev = getattr(self, 'sync_grads', False)
+            self.sync_grads = False
+            try:
+                yield
+            finally:
+                self.sync_grads = prev
+
+        return cm()
+
     def _allreduce_bucket(self, lo, hi):
         import torch.distributed as dist
         flat = self.arena.g32[lo:hi]

@@ -26,11 +26,13 @@ def _worker(rank, world, port, q):
     eng.run_backward()  # dry kernels; the bucket all-reduces are real
     other = torch.randn(eng.arena.total, generator=torch.Generator().manual_seed(100 + (1 - rank)))
     ok = torch.allclose(eng.arena.g32, (mine + other) / 2, atol=1e-6)
-    # no_sync: gradients stay local
-    eng.sync_grads = False
-    eng.arena.g32.copy_(mine)
+    # no_sync: gradients stay local, synchronisation resumes afterwards
+    with eng.no_sync():
+        eng.arena.g32.copy_(mine)
+        eng.run_backward()
+        ok = ok and torch.equal(eng.arena.g32, mine)
     eng.run_backward()
-    ok = ok and torch.equal(eng.arena.g32, mine)
+    ok = ok and torch.allclose(eng.arena.g32, (mine + other) / 2, atol=1e-6)
     q.put((rank, bool(ok), len(eng.buckets)))
     dist.destroy_process_group()
 
