@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from diffusion_b200 import ops
 from diffusion_b200.engine import ParamArena
+from diffusion_b200.unet import NormParams
 
 BF16 = torch.bfloat16
 
@@ -51,13 +52,13 @@ def _holder(**children):
 
 
 def _resnet(cin, cout, groups):
-    return _holder(norm1=nn.GroupNorm(groups, cin, eps=1e-6), conv1=nn.Conv2d(cin, cout, 3, padding=1),
-                   norm2=nn.GroupNorm(groups, cout, eps=1e-6), conv2=nn.Conv2d(cout, cout, 3, padding=1),
+    return _holder(norm1=NormParams(cin, 1e-6, groups), conv1=nn.Conv2d(cin, cout, 3, padding=1),
+                   norm2=NormParams(cout, 1e-6, groups), conv2=nn.Conv2d(cout, cout, 3, padding=1),
                    conv_shortcut=nn.Conv2d(cin, cout, 1) if cin != cout else None)
 
 
 def _vae_attention(ch, groups):
-    return _holder(group_norm=nn.GroupNorm(groups, ch, eps=1e-6), to_q=nn.Linear(ch, ch), to_k=nn.Linear(ch, ch),
+    return _holder(group_norm=NormParams(ch, 1e-6, groups), to_q=nn.Linear(ch, ch), to_k=nn.Linear(ch, ch),
                    to_v=nn.Linear(ch, ch), to_out=nn.ModuleList([nn.Linear(ch, ch), nn.Dropout(0.0)]))
 
 
@@ -228,7 +229,7 @@ class AutoencoderKL(nn.Module):
                 if i != len(boc) - 1 else None))
             ch = out_ch
         enc.mid_block = _mid(boc[-1], g)
-        enc.conv_norm_out = nn.GroupNorm(g, boc[-1], eps=1e-6)
+        enc.conv_norm_out = NormParams(boc[-1], 1e-6, g)
         enc.conv_out = nn.Conv2d(boc[-1], 2 * latent_channels, 3, padding=1)
         self.encoder = enc
         dec = _holder(conv_in=nn.Conv2d(latent_channels, boc[-1], 3, padding=1), mid_block=_mid(boc[-1], g),
@@ -240,7 +241,7 @@ class AutoencoderKL(nn.Module):
                 resnets=nn.ModuleList([_resnet(ch if j == 0 else out_ch, out_ch, g) for j in range(layers_per_block + 1)]),
                 upsamplers=nn.ModuleList([_holder(conv=nn.Conv2d(out_ch, out_ch, 3, padding=1))]) if i != len(boc) - 1 else None))
             ch = out_ch
-        dec.conv_norm_out = nn.GroupNorm(g, boc[0], eps=1e-6)
+        dec.conv_norm_out = NormParams(boc[0], 1e-6, g)
         dec.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
         self.decoder = dec
         self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
@@ -405,15 +406,15 @@ class CLIPTextModel(nn.Module):
         def layer():
             return _holder(self_attn=_holder(k_proj=nn.Linear(D, D), v_proj=nn.Linear(D, D), q_proj=nn.Linear(D, D),
                                              out_proj=nn.Linear(D, D)),
-                           layer_norm1=nn.LayerNorm(D, eps=layer_norm_eps),
+                           layer_norm1=NormParams(D, layer_norm_eps),
                            mlp=_holder(fc1=nn.Linear(D, intermediate_size), fc2=nn.Linear(intermediate_size, D)),
-                           layer_norm2=nn.LayerNorm(D, eps=layer_norm_eps))
+                           layer_norm2=NormParams(D, layer_norm_eps))
 
         self.text_model = _holder(
             embeddings=_holder(token_embedding=nn.Embedding(vocab_size, D),
                                position_embedding=nn.Embedding(max_position_embeddings, D)),
             encoder=_holder(layers=nn.ModuleList([layer() for _ in range(num_hidden_layers)])),
-            final_layer_norm=nn.LayerNorm(D, eps=layer_norm_eps))
+            final_layer_norm=NormParams(D, layer_norm_eps))
         self.requires_grad_(False)
         self._arena, self._engines = None, {}
 

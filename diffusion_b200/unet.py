@@ -34,6 +34,23 @@ class UNetOutput(dict):
     __getattr__ = dict.__getitem__
 
 
+class NormParams(nn.Module):
+    """weight / bias holder with nn.GroupNorm's / nn.LayerNorm's parameter names, shapes and initialisation (ones, zeros).
+    Deliberately NOT a subclass of those classes: composer's low-precision-norm surgery (reference train.py:91-108,
+    `apply_low_precision_groupnorm/layernorm`) replaces every instance of them by a new module with NEW parameters, which
+    would orphan the arena-backed ones and silently stop the norm weights from training.  With this holder the surgery
+    finds nothing to replace, and the kernels already implement its semantics (bf16 I/O, fp32 statistics)."""
+
+    def __init__(self, channels, eps=1e-5, num_groups=None):
+        super().__init__()
+        self.num_channels, self.eps, self.num_groups = channels, eps, num_groups
+        self.weight = nn.Parameter(torch.ones(channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+
+    def extra_repr(self):
+        return f'{self.num_channels}, eps={self.eps}' + (f', groups={self.num_groups}' if self.num_groups else '')
+
+
 def _holder(**children):
     m = nn.Module()
     for k, v in children.items():
@@ -43,10 +60,10 @@ def _holder(**children):
 
 
 def _resnet(cin, cout, temb, groups, eps):
-    return _holder(norm1=nn.GroupNorm(groups, cin, eps=eps),
+    return _holder(norm1=NormParams(cin, eps, groups),
                    conv1=nn.Conv2d(cin, cout, 3, padding=1),
                    time_emb_proj=nn.Linear(temb, cout),
-                   norm2=nn.GroupNorm(groups, cout, eps=eps),
+                   norm2=NormParams(cout, eps, groups),
                    conv2=nn.Conv2d(cout, cout, 3, padding=1),
                    conv_shortcut=nn.Conv2d(cin, cout, 1) if cin != cout else None)
 
@@ -59,15 +76,15 @@ def _attention(dim, cross_dim):
 
 
 def _transformer(ch, cross_dim, groups):
-    block = _holder(norm1=nn.LayerNorm(ch),
+    block = _holder(norm1=NormParams(ch),
                     attn1=_attention(ch, None),
-                    norm2=nn.LayerNorm(ch),
+                    norm2=NormParams(ch),
                     attn2=_attention(ch, cross_dim),
-                    norm3=nn.LayerNorm(ch),
+                    norm3=NormParams(ch),
                     ff=_holder(net=nn.ModuleList([_holder(proj=nn.Linear(ch, ch * 8)),
                                                   nn.Dropout(0.0),
                                                   nn.Linear(ch * 4, ch)])))
-    return _holder(norm=nn.GroupNorm(groups, ch, eps=1e-6),
+    return _holder(norm=NormParams(ch, 1e-6, groups),
                    proj_in=nn.Linear(ch, ch),
                    transformer_blocks=nn.ModuleList([block]),
                    proj_out=nn.Linear(ch, ch))
@@ -135,7 +152,7 @@ class UNet2DConditionModel(nn.Module):
                           upsamplers=nn.ModuleList([_holder(conv=nn.Conv2d(out_ch, out_ch, 3, padding=1))])
                           if i != len(boc) - 1 else None)
             self.up_blocks.append(blk)
-        self.conv_norm_out = nn.GroupNorm(g, boc[0], eps=eps)
+        self.conv_norm_out = NormParams(boc[0], eps, g)
         self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
         self._engines = {}
         self._arena = None

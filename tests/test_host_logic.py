@@ -96,3 +96,21 @@ def test_schedule_builds_and_covers_every_parameter(dry, cfg, B, R):
     if cfg is SD2_BASE_UNET_CONFIG:
         per_image = eng.gemm_flops / B / 1e12
         assert 0.50 < per_image < 0.56  # 0.543 TFLOP/image fwd+bwd at 32x32
+
+
+def test_low_precision_norm_surgery_finds_nothing_to_replace():
+    """reference train.py:91-108 runs composer's module surgery over `model.unet`, replacing every nn.GroupNorm / nn.LayerNorm
+    instance by a new module with new parameters; the product's norm holders must not be such instances (their parameters
+    live in the arena), while keeping the diffusers parameter names."""
+    import torch
+    from diffusion_b200.encoders import AutoencoderKL, CLIPTextModel
+    from diffusion_b200.unet import NormParams, UNet2DConditionModel
+    u = UNet2DConditionModel(**TINY_UNET_CONFIG)
+    mods = [u, AutoencoderKL(block_out_channels=(64, 64, 64, 64), layers_per_block=1),
+            CLIPTextModel(num_hidden_layers=1, vocab_size=64)]
+    for m in mods:
+        assert not any(isinstance(x, (torch.nn.GroupNorm, torch.nn.LayerNorm)) for x in m.modules())
+    norms = [x for x in u.modules() if isinstance(x, NormParams)]
+    assert len(norms) == 61 + 48  # 61 GroupNorms (resnets, transformers, conv_norm_out) + 3 LayerNorms in each of 16 blocks
+    assert all(torch.equal(n.weight, torch.ones_like(n.weight)) and not n.bias.any() for n in norms)
+    assert 'down_blocks.0.resnets.0.norm1.weight' in dict(u.named_parameters())
