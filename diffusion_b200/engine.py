@@ -929,6 +929,7 @@ class DualEngine:
     prepare_inputs = Engine.prepare_inputs
     set_context = Engine.set_context
     enable_grad_sync = Engine.enable_grad_sync
+    no_sync = Engine.no_sync
     _allreduce_bucket = Engine._allreduce_bucket
 
     # ---- execution

@@ -221,9 +221,13 @@ class StableDiffusion(ComposerModel):
                 if self.encode_latents_in_fp16 and not getattr(frozen, '_sd2_native', False):
                     frozen.half()  # the native encoders keep fp32 masters and compute from their own bf16 shadow
         if fsdp:
-            for m, flag in ((self.text_encoder, False), (self.vae, False), (self.unet, True)):
+            # reference :90-97 marks the UNet for FSDP wrapping (SHARD_GRAD_OP).  Here the parameters are replicated (15.6 GB of
+            # state on a 180 GB part) and live in the engine's flat arenas, which an FSDP FlatParameter would replace - so every
+            # sub-module is marked "do not wrap" (Composer's prepare_fsdp_module skips children with _fsdp_wrap == False) and
+            # the engine averages the gradients itself whenever torch.distributed has more than one rank.
+            for m in (self.text_encoder, self.vae, self.unet):
                 if m is not None:
-                    m._fsdp_wrap = flag
+                    m._fsdp_wrap = False
         self._last_engine = None
 
     # -- reference stable_diffusion.py:154-183 -----------------------------------------------------------------

@@ -195,6 +195,13 @@ class UNet2DConditionModel(nn.Module):
             else:
                 eng = (DualEngine if dual else Engine)(self, B, H, W, ctx_len, shared=prev)
             self._engines[key] = eng
+            # data parallel by default: with torch.distributed initialised on more than one rank the engine averages its
+            # gradient buckets itself (idempotent under an additional DDP wrapper; SD2_NO_AUTO_SYNC=1 or eng.sync_grads = False
+            # turn it off)
+            if not forward_only and not dry_run() and os.environ.get('SD2_NO_AUTO_SYNC') != '1':
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not getattr(eng, 'sync_grads', False):
+                    eng.enable_grad_sync()
         eng.ddp_compat = self.ddp_compat
         return eng
 

@@ -21,7 +21,7 @@ def main():
 
     def make():
         torch.manual_seed(17)
-        return stable_diffusion_2(pretrained=False, precomputed_latents=True, unet_config=TINY_UNET_CONFIG, fsdp=False)
+        return stable_diffusion_2(pretrained=False, precomputed_latents=True, unet_config=TINY_UNET_CONFIG, fsdp=True)
 
     g = torch.Generator(device=dev).manual_seed(100 + rank)  # different data per rank
     batch = {'image_latents': torch.randn(2, 4, 16, 16, device=dev, generator=g).to(torch.bfloat16),
@@ -40,15 +40,20 @@ def main():
         return torch.cat([p.grad.float().flatten() for p in model.unet.parameters()])
 
     # reference for ONE step: local gradients without any synchronisation, averaged explicitly
+    os.environ['SD2_NO_AUTO_SYNC'] = '1'
     m_r = make()
     g_loc = grads_after(m_r, m_r, None, steps=1)
+    del os.environ['SD2_NO_AUTO_SYNC']
     g_ref = g_loc.clone()
     dist.all_reduce(g_ref)
     g_ref /= dist.get_world_size()
-    for name, mk in (('engine', 'a'), ('ddp', 'b')):
+    for name, mk in (('engine', 'a'), ('engine (automatic: torch.distributed world > 1, no wrapper, yaml unchanged)', 'auto'), ('ddp', 'b')):
         m1 = make()
         if mk == 'a':
             m1.unet.engine(2, 16, 16, 77).enable_grad_sync()
+            g1 = grads_after(m1, m1, None, steps=1)
+        elif mk == 'auto':
+            assert m1.unet._fsdp_wrap is False
             g1 = grads_after(m1, m1, None, steps=1)
         else:
             g1 = grads_after(m1, torch.nn.parallel.DistributedDataParallel(m1, device_ids=[local]), None, steps=1)
@@ -82,8 +87,10 @@ def main():
         return torch.cat([p.grad.float().flatten() for p in model.unet.parameters()])
 
     import contextlib
+    os.environ['SD2_NO_AUTO_SYNC'] = '1'
     m_d = make()
     g_local = accumulate_two(m_d, m_d, contextlib.nullcontext)
+    del os.environ['SD2_NO_AUTO_SYNC']
     g_want = g_local.clone()
     dist.all_reduce(g_want)
     g_want /= dist.get_world_size()
