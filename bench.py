@@ -142,8 +142,6 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'  # keeps NCCL's version banner off stdout: rank 0 prints exactly one (JSON) line
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py needs a B200: the product path has no CPU fallback')
     torch.cuda.set_device(local_rank)
