@@ -121,7 +121,7 @@ SIGNATURES = {
     'sd2_attn_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i,
                           _i, _i, _i, _f, _vp]),
     'sd2_geglu_fwd': (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
-    'sd2_geglu_bwd': (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    'sd2_geglu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     'sd2_silu_fwd': (_i, [_vp, _vp, _vp, _ll, _vp]),
     'sd2_silu_bwd': (_i, [_vp, _vp, _vp, _vp, _ll, _vp]),
     'sd2_axpby': (_i, [_vp, _vp, _f, _vp, _f, _vp, _ll, _vp]),

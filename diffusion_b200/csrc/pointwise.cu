@@ -151,6 +151,77 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__
   }
 }
 
+// GEGLU backward that also produces the bias gradient of the projection in front of it (dbias[2C] += column sums of dh),
+// so the separate column-sum pass over dh - 46 % of all bias-gradient traffic of the step - disappears.  Layout: block =
+// 32 column vectors x 8 row lanes over a chunk of rows (a warp still reads 512 contiguous bytes per operand), every thread
+// keeps its 16 column sums in registers, the 8 row lanes meet in shared memory, one atomicAdd per column and block.
+__global__ void __launch_bounds__(256) geglu_bwd_bias_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dy,
+                                                             bf16* __restrict__ dh, float* __restrict__ dbias, long long rows,
+                                                             int C, long long rows_per_chunk) {
+  pdl_grid_sync();
+  __shared__ float sm[8][32][17];
+  const int vx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int V = C / 8, v = blockIdx.x * 32 + vx;
+  const bool act = v < V;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  float sa[8], sg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sa[e] = sg[e] = 0.f;
+  if (act) {
+    for (long long r = r0 + ry; r < r1; r += 16) {
+      const long long r2 = r + 8;
+      const bool two = r2 < r1;
+      const uint4 ua = ldg_stream16(h + r * 2 * C + v * 8), ug = ldg_stream16(h + r * 2 * C + C + v * 8);
+      const uint4 ud = ldg_stream16(dy + r * C + v * 8);
+      uint4 ua2 = ua, ug2 = ug, ud2 = ud;
+      if (two) {
+        ua2 = ldg_stream16(h + r2 * 2 * C + v * 8);
+        ug2 = ldg_stream16(h + r2 * 2 * C + C + v * 8);
+        ud2 = ldg_stream16(dy + r2 * C + v * 8);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j == 1 && !two) break;
+        float a[8], g[8], d[8], da[8], dg[8];
+        unpack8f(j ? ua2 : ua, a);
+        unpack8f(j ? ug2 : ug, g);
+        unpack8f(j ? ud2 : ud, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float cdf, pdf;
+          gelu_cdf_pdf(g[e], cdf, pdf);
+          da[e] = d[e] * (g[e] * cdf);
+          dg[e] = d[e] * a[e] * fmaf(g[e], pdf, cdf);
+          sa[e] += da[e];
+          sg[e] += dg[e];
+        }
+        const long long rr = j ? r2 : r;
+        st8(dh + rr * 2 * C + v * 8, da);
+        st8(dh + rr * 2 * C + C + v * 8, dg);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sm[ry][vx][e] = sa[e];
+    sm[ry][vx][8 + e] = sg[e];
+  }
+  __syncthreads();
+  // 512 column sums per block: thread t -> (vector t / 8 ... ) two passes of 256
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int vv = i >> 4, e = i & 15;
+    const int col_v = blockIdx.x * 32 + vv;
+    if (col_v < V) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += sm[r][vv][e];
+      atomicAdd(dbias + (e < 8 ? 0 : C) + col_v * 8 + (e & 7), t);
+    }
+  }
+}
+
 __global__ void silu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8) {
   pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -456,11 +527,23 @@ int sd2_geglu_fwd(sd2_ctx* ctx, const void* h, void* y, long long rows, int C, s
   launch_k(geglu_fwd_kernel, dim3(grid_for(rows * (C / 8), 256, ctx->num_sms, 32)), dim3(256), 0, stream, SD2_BF(h), SD2_BFW(y), rows, C);
   return check_launch(ctx, "geglu_fwd");
 }
-int sd2_geglu_bwd(sd2_ctx* ctx, const void* h, const void* dy, void* dh, long long rows, int C, sd2_stream stream_) {
+int sd2_geglu_bwd(sd2_ctx* ctx, const void* h, const void* dy, void* dh, float* dbias, long long rows, int C, sd2_stream stream_) {
   if (!ctx) return 1;
   if (C % 8) return fail(ctx, "geglu: C % 8");
   SD2_STREAM;
-  launch_k(geglu_bwd_kernel, dim3(grid_for(rows * (C / 8), 256, ctx->num_sms, 32)), dim3(256), 0, stream, SD2_BF(h), SD2_BF(dy), SD2_BFW(dh), rows, C);
+  if (dbias == nullptr) {
+    launch_k(geglu_bwd_kernel, dim3(grid_for(rows * (C / 8), 256, ctx->num_sms, 32)), dim3(256), 0, stream, SD2_BF(h), SD2_BF(dy), SD2_BFW(dh), rows, C);
+    return check_launch(ctx, "geglu_bwd");
+  }
+  const int ncb = (C / 8 + 31) / 32;
+  long long nrc = (24LL * ctx->num_sms + ncb - 1) / ncb;  // ~24 blocks per SM like the plain kernel's measured optimum
+  const long long max_rc = (rows + 31) / 32;              // at least 32 rows (two unrolled iterations of the 8 lanes) per chunk
+  if (nrc > max_rc) nrc = max_rc;
+  if (nrc < 1) nrc = 1;
+  if (nrc > 65535) nrc = 65535;
+  const long long rpc = ((rows + nrc - 1) / nrc + 7) / 8 * 8;
+  nrc = (rows + rpc - 1) / rpc;
+  launch_k(geglu_bwd_bias_kernel, dim3(ncb, (unsigned)nrc), dim3(256), 0, stream, SD2_BF(h), SD2_BF(dy), SD2_BFW(dh), dbias, rows, C, rpc);
   return check_launch(ctx, "geglu_bwd");
 }
 int sd2_silu_fwd(sd2_ctx* ctx, const void* x, void* y, long long n, sd2_stream stream_) {
@@ -546,9 +629,14 @@ int sd2_colsum(sd2_ctx* ctx, const void* x, long long ldx, float* out, long long
   int launches = 1;
   if (!accumulate && splits > 1) {
     // zero the destination rows first so that the split partials can be combined with atomics
-    for (int g = 0; g < groups; ++g) {
-      launch_k(fill_f32_kernel, dim3(grid_for(N, 256, ctx->num_sms)), dim3(256), 0, stream, out + (long long)g * ldo, N, 0.f);
+    if (ldo == N || groups == 1) {  // contiguous destination rows: one launch for all groups
+      launch_k(fill_f32_kernel, dim3(grid_for((long long)groups * N, 256, ctx->num_sms)), dim3(256), 0, stream, out, (long long)groups * N, 0.f);
       ++launches;
+    } else {
+      for (int g = 0; g < groups; ++g) {
+        launch_k(fill_f32_kernel, dim3(grid_for(N, 256, ctx->num_sms)), dim3(256), 0, stream, out + (long long)g * ldo, N, 0.f);
+        ++launches;
+      }
     }
   }
   const int use_atomic = (accumulate || splits > 1) ? 1 : 0;

@@ -36,7 +36,7 @@ _OP_WRITES = {
     'attn_fwd': ((3, 4), ()), 'attn_bwd': ((6, 7, 8, 9), ()),
     'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ()),
     'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ()),
-    'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ()), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
+    'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ('dbias',)), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
     'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
     'phase_split': ((1,), ()), 'phase_merge': ((1,), ()), 'colsum': ((1,), ()), 'cast_f32_to_bf16': ((1,), ()),
     'pad_cast_rows': ((2,), ()), 'unpad_accum_rows': ((2,), ()), 'fill_f32': ((0,), ()),
@@ -327,7 +327,7 @@ class Engine:
             self.b(ops.axpby, node.grad, 1.0, g, 1.0, node.grad)
 
     # ---------------------------------------------------------------------------------------------- records
-    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None, gnames=(), side=False):
+    def linear(self, x, wname, bname=None, residual=None, w16=None, gw=None, gnames=(), side=False, bias_grad_elsewhere=False):
         w = self.w16(wname) if w16 is None else w16
         gwv = self.arena.storage(self.arena.g32, wname) if gw is None else gw
         N = w.shape[0]
@@ -346,7 +346,7 @@ class Engine:
                 self.b(ops.linear_dgrad, g, w, gx, residual=gx if acc else None, workspace=self.ws)
             self._touched.update(gnames or (wname,))
             self.b(ops.linear_wgrad, g, x.data, gwv)
-            if bname:
+            if bname and not bias_grad_elsewhere:
                 self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
 
         self._bwd_builders.append(bwd)
@@ -475,14 +475,16 @@ class Engine:
         self._bwd_builders.append(bwd)
         return out
 
-    def geglu(self, h):
+    def geglu(self, h, bias_name=None):
+        """bias_name: bias of the projection that produced h; its gradient (the column sums of dh) is then accumulated by
+        the GEGLU backward kernel itself and that linear skips its own column-sum pass."""
         y = self.node(h.M, h.C // 2)
         self.f(ops.geglu_fwd, h.data, y.data)
 
         def bwd():
             gh, acc = self._gout(h)
             assert not acc
-            self.b(ops.geglu_bwd, h.data, y.grad, gh)
+            self.b(ops.geglu_bwd, h.data, y.grad, gh, dbias=self.g32(bias_name) if bias_name else None)
 
         self._bwd_builders.append(bwd)
         return y
@@ -570,8 +572,10 @@ class Engine:
         h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1)
         # --- GEGLU feed-forward
         l3 = self.layernorm(h2, tb + '.norm3')
-        ff1 = self.linear(l3, tb + '.ff.net.0.proj.weight', tb + '.ff.net.0.proj.bias')
-        gg = self.geglu(ff1)
+        import os
+        fuse = os.environ.get('SD2_NO_GEGLU_BIAS_FUSE') != '1'  # A/B switch: bias gradient of ff.net.0.proj from geglu_bwd
+        ff1 = self.linear(l3, tb + '.ff.net.0.proj.weight', tb + '.ff.net.0.proj.bias', bias_grad_elsewhere=fuse)
+        gg = self.geglu(ff1, bias_name=tb + '.ff.net.0.proj.bias' if fuse else None)
         h3 = self.linear(gg, tb + '.ff.net.2.weight', tb + '.ff.net.2.bias', residual=h2)
         return self.linear(h3, prefix + '.proj_out.weight', prefix + '.proj_out.bias', residual=x)
 

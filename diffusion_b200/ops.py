@@ -356,8 +356,9 @@ def geglu_fwd(ctx, h, y):
     ctx.check(ctx.lib.sd2_geglu_fwd(ctx.h, _p(h), _p(y), h.shape[0], y.shape[1], _s()))
 
 
-def geglu_bwd(ctx, h, dy, dh):
-    ctx.check(ctx.lib.sd2_geglu_bwd(ctx.h, _p(h), _p(dy), _p(dh), h.shape[0], dy.shape[1], _s()))
+def geglu_bwd(ctx, h, dy, dh, dbias=None):
+    """dbias (fp32 [2C], optional) += column sums of dh: the bias gradient of the projection in front of the GEGLU."""
+    ctx.check(ctx.lib.sd2_geglu_bwd(ctx.h, _p(h), _p(dy), _p(dh), _p(dbias), h.shape[0], dy.shape[1], _s()))
 
 
 def silu_fwd(ctx, x, y):

@@ -154,7 +154,9 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
 /* ---- pointwise / layout kernels -------------------------------------------------------------------------------- */
 /* GEGLU: h = [a | g] ([rows][2*C]) -> y = a * gelu_erf(g) ([rows][C]) */
 int sd2_geglu_fwd(sd2_ctx* ctx, const void* h, void* y, long long rows, int C, sd2_stream stream);
-int sd2_geglu_bwd(sd2_ctx* ctx, const void* h, const void* dy, void* dh, long long rows, int C, sd2_stream stream);
+/* dbias (optional, fp32 [2C]): += column sums of dh = the bias gradient of the projection that produced h */
+int sd2_geglu_bwd(sd2_ctx* ctx, const void* h, const void* dy, void* dh, float* dbias, long long rows, int C,
+                  sd2_stream stream);
 int sd2_silu_fwd(sd2_ctx* ctx, const void* x, void* y, long long n, sd2_stream stream);
 int sd2_silu_bwd(sd2_ctx* ctx, const void* x, const void* dy, void* dx, long long n, sd2_stream stream);
 /* out = alpha*a + beta*b (b may be null); bf16 */

@@ -317,6 +317,14 @@ def test_geglu_silu_axpby(ctx):
     dh = torch.empty_like(h)
     ops.geglu_bwd(ctx, h, dy, dh)
     close(dh, hr.grad, name='geglu bwd')
+    # fused bias gradient of the projection in front: dbias += column sums of dh (ragged row count, accumulation)
+    for r in (rows, 1000, 37):
+        dh2 = torch.empty(r, 2 * Cc, dtype=torch.bfloat16, device='cuda')
+        dbias = torch.full((2 * Cc,), 0.5, device='cuda')
+        ops.geglu_bwd(ctx, h[:r], dy[:r], dh2, dbias=dbias)
+        assert torch.equal(dh2, dh[:r]), 'the fused kernel must write the same dh'
+        ref_b = hr.grad[:r].sum(0) + 0.5
+        close(dbias, ref_b, rtol=2e-3, atol=2e-3 * ref_b.abs().max().item(), name=f'geglu bwd bias rows={r}')
     x = bf(16, 1280, seed=3)
     ys = torch.empty_like(x)
     ops.silu_fwd(ctx, x, ys)
