@@ -113,7 +113,7 @@ SIGNATURES = {
                                _i, _i, _vp]),
     'sd2_layernorm_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     'sd2_layernorm_ws_floats': (_ll, [_ll, _i]),
-    'sd2_layernorm_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    'sd2_layernorm_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     'sd2_softmax_fwd': (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _i, _vp]),
     'sd2_softmax_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _f, _vp]),
     'sd2_attn_fwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _vp]),

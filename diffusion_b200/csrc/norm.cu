@@ -705,7 +705,9 @@ static inline int affine_slices(int n_part) {  // ~32 slabs per block: 8 partial
   return s < 1 ? 1 : (s > 16 ? 16 : s);
 }
 __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __restrict__ ws, int n_part, int C,
-                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 const float* __restrict__ ws_cs = nullptr,
+                                                                 float* __restrict__ dcs = nullptr) {
   pdl_grid_sync();
   __shared__ float sm[8][32][2];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -742,6 +744,19 @@ __global__ void __launch_bounds__(256) affine_grad_reduce_kernel(const float* __
     }
     atomicAdd(&dbeta[c], a1);
     atomicAdd(&dgamma[c], a2);
+  }
+  if (ws_cs != nullptr) {  // third sum: column sums of dx -> bias gradient of the producing linear
+    float a3 = 0.f;
+    if (c < C)
+      for (int i = blockIdx.y * 8 + pl; i < n_part; i += 8 * gridDim.y) a3 += ws_cs[(long long)i * C + c];
+    __syncthreads();
+    sm[pl][cl][0] = a3;
+    __syncthreads();
+    if (pl == 0 && c < C) {
+#pragma unroll
+      for (int k = 1; k < 8; ++k) a3 += sm[k][cl][0];
+      atomicAdd(&dcs[c], a3);
+    }
   }
 }
 
@@ -855,12 +870,15 @@ static LnTileCfg ln_tile_cfg(int C, bool has_add) {
   return c;
 }
 
-template <bool HAS_ADD>
+// CS: also emit per-block column sums of the dx written (ws_cs[block][C]) - dx (+dx_add) is the total gradient of the
+// residual-stream node in front of this norm, i.e. the output gradient of the linear that produced it, so its column sums
+// are that linear's bias gradient and the separate column-sum pass over the same tensor disappears.
+template <bool HAS_ADD, bool CS>
 __global__ void __launch_bounds__(512, 1) ln_bwd_tile_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                               const float* __restrict__ gamma, const float* __restrict__ stats,
                                                               const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
-                                                              float* __restrict__ ws, long long rows, int C, int RL,
-                                                              unsigned body_bytes) {
+                                                              float* __restrict__ ws, float* __restrict__ ws_cs, long long rows,
+                                                              int C, int RL, unsigned body_bytes) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   constexpr int NT = HAS_ADD ? 3 : 2;
   const int V = C / 8, R = 2 * RL;
@@ -911,6 +929,9 @@ __global__ void __launch_bounds__(512, 1) ln_bwd_tile_kernel(const bf16* __restr
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) ag[e] = ab[e] = 0.f;
+  float ac[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ac[e] = 0.f;
 
   int s = 0;
   uint32_t ph = 0;
@@ -977,6 +998,7 @@ __global__ void __launch_bounds__(512, 1) ln_bwd_tile_kernel(const bf16* __restr
           o[e] = HAS_ADD ? o[e] + t : t;
           ab[e] += df[j][e];
           ag[e] = fmaf(df[j][e], xh, ag[e]);
+          if (CS) ac[e] += o[e];
         }
         store8(dx + (row0 + r) * C + v * 8, o);
       }
@@ -1004,6 +1026,21 @@ __global__ void __launch_bounds__(512, 1) ln_bwd_tile_kernel(const bf16* __restr
     float t = 0.f;
     for (int r = 0; r < RL; ++r) t += red[(size_t)r * 2 * C + i];
     o[i] = t;
+  }
+  if (CS) {
+    __syncthreads();
+    if (p2) {
+      float* q = red + (size_t)rl * C + v * 8;
+      *reinterpret_cast<float4*>(q) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+      *reinterpret_cast<float4*>(q + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
+    }
+    __syncthreads();
+    float* oc = ws_cs + (long long)blockIdx.x * C;
+    for (int i = tid; i < C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < RL; ++r) t += red[(size_t)r * C + i];
+      oc[i] = t;
+    }
   }
 }
 
@@ -1072,7 +1109,7 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
       else if (ap) e = launch_gn_bwd_cluster<false, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
       else e = launch_gn_bwd_cluster<false, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
       if (e != cudaSuccess) return fail(ctx, std::string("sd2_groupnorm_bwd (cluster): ") + cudaGetErrorString(e));
-      launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(B * cc.NC)), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta);
+      launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(B * cc.NC)), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta, nullptr, nullptr);
       return check_launch(ctx, "groupnorm_bwd", 2);
     }
   }
@@ -1117,8 +1154,8 @@ int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const flo
 long long sd2_layernorm_ws_floats(long long rows, int C) { return (long long)148 * 4 * C * 2; }  // >= one [C][2] slab per CTA
 
 int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* gamma, const float* stats,
-                      const void* dx_add, void* dx, float* dgamma, float* dbeta, float* ws, long long rows, int C,
-                      sd2_stream stream_) {
+                      const void* dx_add, void* dx, float* dgamma, float* dbeta, float* dcolsum, float* ws, long long rows,
+                      int C, sd2_stream stream_) {
   if (!ctx) return 1;
   if (C % 8 != 0 || C < 8) return fail(ctx, "sd2_layernorm_bwd: unsupported C");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1127,22 +1164,27 @@ int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* 
   if (cfg.smem_bytes > 227 * 1024) return fail(ctx, "sd2_layernorm_bwd: tile does not fit in shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(ln_bwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(ln_bwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(ln_bwd_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(ln_bwd_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(ln_bwd_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(ln_bwd_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail(ctx, "sd2_layernorm_bwd: cannot raise the shared-memory limit");
     attr_set = true;
   }
   const long long tiles = (rows + cfg.R - 1) / cfg.R;
   const int blocks = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  if (dx_add)
-    launch_k(ln_bwd_tile_kernel<true>, dim3(blocks), dim3(cfg.threads), cfg.smem_bytes, stream,
-             reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,
-             reinterpret_cast<const bf16*>(dx_add), reinterpret_cast<bf16*>(dx), ws, rows, C, cfg.RL, (unsigned)cfg.body_bytes);
-  else
-    launch_k(ln_bwd_tile_kernel<false>, dim3(blocks), dim3(cfg.threads), cfg.smem_bytes, stream,
-             reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,
-             reinterpret_cast<const bf16*>(dx_add), reinterpret_cast<bf16*>(dx), ws, rows, C, cfg.RL, (unsigned)cfg.body_bytes);
-  launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(blocks)), dim3(256), 0, stream, ws, blocks, C, dgamma, dbeta);
+  float* ws_cs = ws + (long long)blocks * C * 2;  // the workspace holds 4 x 148 slabs of [C][2]: room for the [C] sums behind them
+#define LN_BWD(ADD, CSUM)                                                                                                  \
+  launch_k(ln_bwd_tile_kernel<ADD, CSUM>, dim3(blocks), dim3(cfg.threads), cfg.smem_bytes, stream,                          \
+           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,                              \
+           reinterpret_cast<const bf16*>(dx_add), reinterpret_cast<bf16*>(dx), ws, ws_cs, rows, C, cfg.RL, (unsigned)cfg.body_bytes)
+  if (dx_add && dcolsum) LN_BWD(true, true);
+  else if (dx_add) LN_BWD(true, false);
+  else if (dcolsum) LN_BWD(false, true);
+  else LN_BWD(false, false);
+#undef LN_BWD
+  launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(blocks)), dim3(256), 0, stream, ws, blocks, C, dgamma, dbeta,
+           dcolsum ? ws_cs : nullptr, dcolsum);
   return check_launch(ctx, "layernorm_bwd", 2);
 }
 

@@ -35,7 +35,7 @@ _OP_WRITES = {
     'conv3x3_fwd': ((5,), ('workspace',)), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
     'attn_fwd': ((3, 4), ()), 'attn_bwd': ((6, 7, 8, 9), ()),
     'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ()),
-    'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ()),
+    'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ('dcolsum',)),
     'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ('dbias',)), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
     'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
     'phase_split': ((1,), ()), 'phase_merge': ((1,), ()), 'colsum': ((1,), ()), 'cast_f32_to_bf16': ((1,), ()),
@@ -77,11 +77,12 @@ def _overlap(xs, ys):
 
 class Node:
     """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
-    __slots__ = ('data', 'grad', 'gw', 'M', 'C')
+    __slots__ = ('data', 'grad', 'gw', 'M', 'C', 'writes', 'last_writer', 'writes_at_norm')
 
     def __init__(self, data):
         self.data, self.grad, self.gw = data, None, False
         self.M, self.C = data.shape
+        self.writes, self.last_writer, self.writes_at_norm = 0, None, -1  # gradient-write bookkeeping (bias grads from norms)
 
 
 def _align(n, a=64):
@@ -317,10 +318,12 @@ class Engine:
             node.grad = torch.empty_like(node.data)
             self.act_bytes += node.grad.numel() * 2
         acc, node.gw = node.gw, True
+        node.writes += 1
         return node.grad, acc
 
     def _pass(self, g, node):
         """d(node) += g for an identity edge: alias the buffer when node has no gradient yet."""
+        node.writes += 1
         if not node.gw:
             node.grad, node.gw = g, True
         else:
@@ -348,6 +351,10 @@ class Engine:
             self.b(ops.linear_wgrad, g, x.data, gwv)
             if bname and not bias_grad_elsewhere:
                 self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
+            elif bname and bias_grad_elsewhere == 'norm':
+                # the norm that emitted the column sums must have been the LAST op to write this node's gradient
+                assert getattr(out, 'last_writer', None) is not None and out.writes == out.writes_at_norm, \
+                    f'{bname}: the bias gradient was taken from a norm backward that is not the last writer of the node'
 
         self._bwd_builders.append(bwd)
         return out
@@ -379,7 +386,10 @@ class Engine:
         self._bwd_builders.append(bwd)
         return y
 
-    def layernorm(self, x, prefix):
+    def layernorm(self, x, prefix, colsum_into=None):
+        """colsum_into: bias name of the linear that produced x.  This norm is the first forward consumer of x, hence the
+        last contributor to x.grad in backward: the dx (+ dx_add) it writes is the total output gradient of that linear,
+        and its column sums - accumulated by the same kernel - are the bias gradient (that linear skips its own pass)."""
         y = self.node(x.M, x.C)
         stats = self.buf(x.M, 2, dtype=torch.float32)
         gamma, beta = self.p32(prefix + '.weight'), self.p32(prefix + '.bias')
@@ -389,7 +399,9 @@ class Engine:
             assert y.gw
             gx, acc = self._gout(x)
             self.b(ops.layernorm_bwd, y.grad, x.data, gamma, stats, gx, self.g32(prefix + '.weight'),
-                   self.g32(prefix + '.bias'), self.ln_ws, dx_add=gx if acc else None)
+                   self.g32(prefix + '.bias'), self.ln_ws, dx_add=gx if acc else None,
+                   dcolsum=self.g32(colsum_into) if colsum_into else None)
+            x.last_writer, x.writes_at_norm = prefix, x.writes  # checked by the producing linear (bias_grad_elsewhere='norm')
 
         self._bwd_builders.append(bwd)
         return y
@@ -554,24 +566,26 @@ class Engine:
         C, B, L = x.C, self.B, self.L
         HW = Hc * Wc
         n = self.groupnorm(x, prefix + '.norm', 1e-6, 0, HW)
-        h0 = self.linear(n, prefix + '.proj_in.weight', prefix + '.proj_in.bias')
+        import os
+        nb = 'norm' if os.environ.get('SD2_NO_NORM_BIAS_FUSE') != '1' else False  # A/B switch: linear bias grads from LN backward
+        h0 = self.linear(n, prefix + '.proj_in.weight', prefix + '.proj_in.bias', bias_grad_elsewhere=nb)
         tb = prefix + '.transformer_blocks.0'
         # --- self attention
-        l1 = self.layernorm(h0, tb + '.norm1')
+        l1 = self.layernorm(h0, tb + '.norm1', colsum_into=prefix + '.proj_in.bias' if nb else None)
         names = [tb + '.attn1.to_q.weight', tb + '.attn1.to_k.weight', tb + '.attn1.to_v.weight']
         qkv = self.linear(l1, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names), gnames=names)
         o1 = self.attention(qkv.data[:, :C], qkv.data[:, C:2 * C], qkv.data[:, 2 * C:], qkv, qkv, 0, C, 2 * C, HW, HW, heads, C)
-        h1 = self.linear(o1, tb + '.attn1.to_out.0.weight', tb + '.attn1.to_out.0.bias', residual=h0)
+        h1 = self.linear(o1, tb + '.attn1.to_out.0.weight', tb + '.attn1.to_out.0.bias', residual=h0, bias_grad_elsewhere=nb)
         # --- cross attention over the text context
-        l2 = self.layernorm(h1, tb + '.norm2')
+        l2 = self.layernorm(h1, tb + '.norm2', colsum_into=tb + '.attn1.to_out.0.bias' if nb else None)
         q2 = self.linear(l2, tb + '.attn2.to_q.weight')
         names = [tb + '.attn2.to_k.weight', tb + '.attn2.to_v.weight']
         kv = self.linear(self.ctx_node, names[0], w16=arena.fused(arena.p16, names), gw=arena.fused(arena.g32, names),
                          gnames=names, side=True)  # depends only on the text context: off the critical path
         o2 = self.attention(q2.data, kv.data[:, :C], kv.data[:, C:], q2, kv, 0, 0, C, HW, L, heads, C)
-        h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1)
+        h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1, bias_grad_elsewhere=nb)
         # --- GEGLU feed-forward
-        l3 = self.layernorm(h2, tb + '.norm3')
+        l3 = self.layernorm(h2, tb + '.norm3', colsum_into=tb + '.attn2.to_out.0.bias' if nb else None)
         import os
         fuse = os.environ.get('SD2_NO_GEGLU_BIAS_FUSE') != '1'  # A/B switch: bias gradient of ff.net.0.proj from geglu_bwd
         ff1 = self.linear(l3, tb + '.ff.net.0.proj.weight', tb + '.ff.net.0.proj.bias', bias_grad_elsewhere=fuse)

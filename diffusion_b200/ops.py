@@ -334,11 +334,12 @@ def layernorm_ws(ctx, rows, Cc, device):
     return torch.empty(ctx.lib.sd2_layernorm_ws_floats(rows, Cc), dtype=torch.float32, device=device)
 
 
-def layernorm_bwd(ctx, dy, x, gamma, stats, dx, dgamma, dbeta, ws, dx_add=None):
+def layernorm_bwd(ctx, dy, x, gamma, stats, dx, dgamma, dbeta, ws, dx_add=None, dcolsum=None):
+    """dcolsum (fp32 [C], optional) += column sums of the dx written (= bias gradient of the linear that produced x)."""
     rows, Cc = x.shape
     ctx.check(
         ctx.lib.sd2_layernorm_bwd(ctx.h, _p(dy), _p(x), _p(gamma), _p(stats), _p(dx_add), _p(dx), _p(dgamma), _p(dbeta),
-                                  _p(ws), rows, Cc, _s()))
+                                  _p(dcolsum), _p(ws), rows, Cc, _s()))
 
 
 # ------------------------------------------------------------------------------------------------- pointwise

@@ -126,9 +126,11 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
 int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, float* stats,
                       long long rows, int C, float eps, sd2_stream stream);
 long long sd2_layernorm_ws_floats(long long rows, int C);
+/* dcolsum (optional, fp32 [C]): += column sums of the dx written (dx + dx_add = the total gradient of the normalised
+ * tensor, i.e. the bias gradient of the linear that produced it) */
 int sd2_layernorm_bwd(sd2_ctx* ctx, const void* dy, const void* x, const float* gamma, const float* stats,
-                      const void* dx_add, void* dx, float* dgamma, float* dbeta, float* ws, long long rows, int C,
-                      sd2_stream stream);
+                      const void* dx_add, void* dx, float* dgamma, float* dbeta, float* dcolsum, float* ws, long long rows,
+                      int C, sd2_stream stream);
 
 /* ---- attention pieces (materialised-score path; replaces xformers / SDPA, reference models.py:109-111) ------- */
 int sd2_softmax_fwd(sd2_ctx* ctx, const float* S, long long lds, void* P, long long ldp, long long rows, int cols,

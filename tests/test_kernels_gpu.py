@@ -299,6 +299,18 @@ def test_layernorm(ctx, rows, Cc):
     close(dx, xr.grad + add.float(), rtol=2e-2, atol=3e-2, name='ln dx')
     close(dg, gamma.grad, rtol=1e-2, atol=1e-2 * gamma.grad.abs().max().item(), name='ln dgamma')
     close(db, beta.grad, rtol=1e-2, atol=1e-2 * beta.grad.abs().max().item(), name='ln dbeta')
+    # fused column sums of the dx written (with and without dx_add): the bias gradient of the linear in front of the norm
+    for with_add in (True, False):
+        dx2 = torch.empty_like(x)
+        dg2, db2 = torch.zeros(Cc, device='cuda'), torch.zeros(Cc, device='cuda')
+        cs = torch.full((Cc,), 0.25, device='cuda')
+        ops.layernorm_bwd(ctx, dy, x, gamma.detach(), stats, dx2, dg2, db2, ws, dx_add=add if with_add else None, dcolsum=cs)
+        want_dx = xr.grad + (add.float() if with_add else 0)
+        if with_add:
+            assert torch.equal(dx2, dx), 'the column-sum variant must write the same dx'
+        ref_cs = want_dx.sum(0) + 0.25
+        close(cs, ref_cs, rtol=5e-3, atol=5e-3 * ref_cs.abs().max().item() + 2e-3 * rows**0.5, name=f'ln dx colsum add={with_add}')
+        close(dg2, gamma.grad, rtol=1e-2, atol=1e-2 * gamma.grad.abs().max().item(), name='ln dgamma (colsum variant)')
 
 
 # ------------------------------------------------------------------------------------------------ pointwise
