@@ -114,3 +114,26 @@ def test_low_precision_norm_surgery_finds_nothing_to_replace():
     assert len(norms) == 61 + 48  # 61 GroupNorms (resnets, transformers, conv_norm_out) + 3 LayerNorms in each of 16 blocks
     assert all(torch.equal(n.weight, torch.ones_like(n.weight)) and not n.bias.any() for n in norms)
     assert 'down_blocks.0.resnets.0.norm1.weight' in dict(u.named_parameters())
+
+
+def test_documents_reference_existing_files():
+    """Every profiles/ tools/ tests/ oracle/ diffusion_b200/ path named in the top-level documents exists."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    missing = []
+    for doc in ('DESIGN.md', 'INTEGRATION.md', 'README.md', os.path.join('profiles', 'README.md')):
+        text = open(os.path.join(root, doc)).read()
+        for m in re.finditer(r'`((?:profiles|tools|tests|oracle|diffusion_b200|include)/[\w./{},\-*]+)`', text):
+            path = m.group(1).split('::')[0].rstrip('.,')
+            if '*' in path:
+                continue
+            variants = [path]
+            b = re.search(r'\{([^}]*)\}', path)
+            if b:  # brace lists: a{1,2}b -> a1b, a2b
+                variants = [path[:b.start()] + alt + path[b.end():] for alt in b.group(1).split(',')]
+            for v in variants:
+                base = v if doc != os.path.join('profiles', 'README.md') or '/' in v else os.path.join('profiles', v)
+                if not os.path.exists(os.path.join(root, base)):
+                    missing.append((doc, v))
+    assert not missing, missing
