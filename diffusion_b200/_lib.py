@@ -41,6 +41,20 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(_BUILD, exist_ok=True)
+    # every rank of a torchrun job may find the library stale at the same time: one builds, the others wait on the lock and
+    # then find it fresh
+    import fcntl
+    with open(os.path.join(_BUILD, '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
 

@@ -229,6 +229,14 @@ class EMA:
             return True
         if ev == self.update_event and self.ema_started:
             return self._count(state, self.update_interval[1]) % self.update_interval[0] == 0
+        # reference ema.py:221-227: on checkpoint events, match when a checkpoint saver is about to write, so that apply()
+        # swaps the EMA weights into the model and the checkpoint carries them with ema_weights_active=True.  Savers are found
+        # by duck type (Composer is not importable here): a callback with a callable `save_interval(state, event)`.
+        if ev in ('BATCH_CHECKPOINT', 'EPOCH_CHECKPOINT') and self.ema_started:
+            for cb in getattr(state, 'callbacks', None) or ():
+                interval = getattr(cb, 'save_interval', None)
+                if callable(interval) and interval(state, event) is True:
+                    return True
         return False
 
     def apply(self, event, state, logger=None) -> None:

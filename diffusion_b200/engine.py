@@ -183,10 +183,9 @@ class ParamArena:
 
 class Engine:
 
-    def __init__(self, unet, B, H, W, L, shared=None, io=None, own_scratch=False, forward_only=False):
-        """io: optional dict of externally owned static buffers (in_x8, in_temb, in_ctx, pred8, dpred8) - used by
-        DualEngine, whose two half-batch engines work on slices of full-batch buffers.  own_scratch: do not share the
-        split-K workspaces with `shared` (engines that run concurrently need private scratch)."""
+    def __init__(self, unet, B, H, W, L, shared=None, forward_only=False):
+        """shared: an engine of the same module built earlier (other geometry): its parameter arena and split-K scratch
+        are reused."""
         dev = unet.conv_in.weight.device
         self.ctx = ops.get_ctx(dev)
         self.dev = dev
@@ -200,8 +199,8 @@ class Engine:
         self.B, self.H, self.W, self.L = B, H, W, L
         self.fwd, self.bwd, self._bwd_builders = [], [], []
         self._touched, self.grad_ready = set(), {}
-        reuse = shared is not None and not own_scratch and getattr(shared, 'ws', None) is not None
-        self.ws = shared.ws if reuse else torch.empty((128 if own_scratch else 256) << 20, dtype=torch.uint8, device=dev)
+        reuse = shared is not None and getattr(shared, 'ws', None) is not None
+        self.ws = shared.ws if reuse else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         self.G = self.cfg['norm_num_groups']
         cmax = max(self.cfg['block_out_channels']) * 2
         self.gn_ws = ops.groupnorm_ws(self.ctx, B, cmax, dev)
@@ -214,16 +213,16 @@ class Engine:
         self.ws_side = shared.ws_side if reuse else torch.empty(64 << 20, dtype=torch.uint8, device=dev)
         # static inputs (written by K1 / the prep kernels)
         c0 = self.cfg['block_out_channels'][0]
-        io = io or {}
-        self.in_x8 = io['in_x8'] if 'in_x8' in io else torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
-        self.in_temb = io['in_temb'] if 'in_temb' in io else torch.zeros(B, c0, dtype=BF16, device=dev)
-        self.in_ctx = io['in_ctx'] if 'in_ctx' in io else torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
-        self.pred8 = io.get('pred8')
-        self.dpred8 = io['dpred8'] if 'dpred8' in io else torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
+        self.in_x8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
+        self.in_temb = torch.zeros(B, c0, dtype=BF16, device=dev)
+        self.in_ctx = torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
+        self.pred8 = None
+        self.dpred8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
         self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
         self.forward_only = forward_only  # sampling / eval: no backward schedule, no gradient buffers
         self._build()
         self.graph_fwd = self.graph_bwd = None
+        self.generation = 0  # bumped by every run_forward: an autograd node may only replay the backward of ITS forward
 
     def params_bound(self):
         return self.arena.bound()
@@ -566,8 +565,7 @@ class Engine:
         C, B, L = x.C, self.B, self.L
         HW = Hc * Wc
         n = self.groupnorm(x, prefix + '.norm', 1e-6, 0, HW)
-        import os
-        nb = 'norm' if os.environ.get('SD2_NO_NORM_BIAS_FUSE') != '1' else False  # A/B switch: linear bias grads from LN backward
+        nb = 'norm'  # bias gradients of proj_in / attn1.to_out / attn2.to_out come from the LayerNorm backward behind them
         h0 = self.linear(n, prefix + '.proj_in.weight', prefix + '.proj_in.bias', bias_grad_elsewhere=nb)
         tb = prefix + '.transformer_blocks.0'
         # --- self attention
@@ -586,8 +584,7 @@ class Engine:
         h2 = self.linear(o2, tb + '.attn2.to_out.0.weight', tb + '.attn2.to_out.0.bias', residual=h1, bias_grad_elsewhere=nb)
         # --- GEGLU feed-forward
         l3 = self.layernorm(h2, tb + '.norm3', colsum_into=tb + '.attn2.to_out.0.bias' if nb else None)
-        import os
-        fuse = os.environ.get('SD2_NO_GEGLU_BIAS_FUSE') != '1'  # A/B switch: bias gradient of ff.net.0.proj from geglu_bwd
+        fuse = True  # bias gradient of ff.net.0.proj is accumulated by geglu_bwd
         ff1 = self.linear(l3, tb + '.ff.net.0.proj.weight', tb + '.ff.net.0.proj.bias', bias_grad_elsewhere=fuse)
         gg = self.geglu(ff1, bias_name=tb + '.ff.net.0.proj.bias' if fuse else None)
         h3 = self.linear(gg, tb + '.ff.net.2.weight', tb + '.ff.net.2.bias', residual=h2)
@@ -774,6 +771,7 @@ class Engine:
 
     # ---------------------------------------------------------------------------------------------- execution
     def run_forward(self):
+        self.generation += 1
         self.arena.refresh_shadow(self.ctx)  # fp32 master -> bf16 shadow, only if the weights changed outside FusedAdamW
         if self.graph_fwd is not None:
             self.graph_fwd.replay()
@@ -888,164 +886,6 @@ class Engine:
         return g, n
 
 
-class DualEngine:
-    """The per-GPU microbatch as TWO concurrent half-batch chains.
-
-    The step time of one chain is ~9 ms of dependent-launch latency plus ~0.74 ms per image (measured): most kernels of
-    the UNet at B=16 cannot fill 148 SMs and each waits for its predecessor.  Two half-batch engines share the weight
-    arenas and work on slices of the full-batch I/O buffers; inside the CUDA graphs each runs on its own (main, side)
-    stream pair, so one chain's kernels fill the other's bubbles.  Gradients of both halves accumulate into the same
-    fp32 arena (TMA reduce-add / atomics).  Samples are independent in this network (GroupNorm is per sample), so the
-    result equals the single-chain result up to fp32 summation order.  Same interface as Engine."""
-
-    def __init__(self, unet, B, H, W, L, shared=None):
-        assert B % 2 == 0
-        dev = unet.conv_in.weight.device
-        self.ctx, self.dev, self.cfg = ops.get_ctx(dev), dev, unet.config
-        self.B, self.H, self.W, self.L = B, H, W, L
-        c0 = self.cfg['block_out_channels'][0]
-        M, Bh = B * H * W, B // 2
-        self.in_x8 = torch.zeros(M, 8, dtype=BF16, device=dev)
-        self.in_temb = torch.zeros(B, c0, dtype=BF16, device=dev)
-        self.in_ctx = torch.zeros(B * L, self.cfg['cross_attention_dim'], dtype=BF16, device=dev)
-        self.pred8 = torch.zeros(M, 8, dtype=BF16, device=dev)
-        self.dpred8 = torch.zeros(M, 8, dtype=BF16, device=dev)
-        self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
-        self.halves = []
-        for h in range(2):
-            rows = slice(h * Bh * H * W, (h + 1) * Bh * H * W)
-            io = dict(in_x8=self.in_x8[rows], in_temb=self.in_temb[h * Bh:(h + 1) * Bh],
-                      in_ctx=self.in_ctx[h * Bh * L:(h + 1) * Bh * L], pred8=self.pred8[rows], dpred8=self.dpred8[rows])
-            prev = self.halves[0] if self.halves else shared
-            self.halves.append(Engine(unet, Bh, H, W, L, shared=prev, io=io, own_scratch=True))
-        self.arena = self.halves[0].arena
-        self.buckets, self.segments = self.halves[0].buckets, self.halves[0].segments
-        self.graph_fwd = self.graph_bwd = None
-        self.forward_only = False
-        self.ws = None  # no scratch to lend to later engines
-
-    # ---- aggregate views used by tools / tests
-    @property
-    def fwd(self):
-        return self.halves[0].fwd + self.halves[1].fwd
-
-    @property
-    def bwd(self):
-        return self.halves[0].bwd + self.halves[1].bwd
-
-    @property
-    def gemm_flops(self):
-        return sum(e.gemm_flops for e in self.halves)
-
-    @property
-    def act_bytes(self):
-        return sum(e.act_bytes for e in self.halves)
-
-    def params_bound(self):
-        return self.arena.bound()
-
-    prepare_inputs = Engine.prepare_inputs
-    set_context = Engine.set_context
-    enable_grad_sync = Engine.enable_grad_sync
-    no_sync = Engine.no_sync
-    _allreduce_bucket = Engine._allreduce_bucket
-
-    # ---- execution
-    def run_forward(self):
-        self.arena.refresh_shadow(self.ctx)
-        if self.graph_fwd is not None:
-            self.graph_fwd.replay()
-        else:
-            for e in self.halves:
-                for op in e.fwd:
-                    op()
-
-    def run_backward(self):
-        if self.forward_only:
-            raise RuntimeError('this engine was built forward-only (sampling / eval): it has no backward schedule')
-        sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
-        start = 0
-        for k, end in enumerate(self.segments):
-            if self.graph_bwd is not None:
-                self.graph_bwd[k].replay()
-            else:
-                for e in self.halves:
-                    for op in e.bwd[start:end]:
-                        op()
-            if sync:
-                for lo, hi, ready in self.buckets:
-                    if ready == end:
-                        self._allreduce_bucket(lo, hi)
-            start = end
-        if sync and self.comm_stream is not None:
-            torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
-
-    def _capture_pair(self, graph, s, streams, lists):
-        """One graph: half 0 on (s, streams[0]), half 1 on (streams[1], streams[2]), forked from / joined to s."""
-        (ops0, side0), (ops1, side1) = lists
-        with torch.cuda.graph(graph, stream=s):
-            fork = torch.cuda.Event()
-            fork.record(s)
-            streams[1].wait_event(fork)
-            with torch.cuda.stream(streams[1]):
-                self.halves[1]._run_two_streams(ops1, side1, streams[1], streams[2])
-                done = torch.cuda.Event()
-                done.record(streams[1])
-            self.halves[0]._run_two_streams(ops0, side0, s, streams[0])
-            s.wait_event(done)
-
-    def capture_graphs(self):
-        torch.cuda.synchronize(self.dev)
-        s = torch.cuda.Stream(self.dev)
-        extra = [torch.cuda.Stream(self.dev) for _ in range(3)]
-        s.wait_stream(torch.cuda.current_stream(self.dev))
-        a, b = self.halves
-        gf, gbs = torch.cuda.CUDAGraph(), []
-        with torch.cuda.stream(s):
-            self._capture_pair(gf, s, extra, ((a.fwd, a.fwd_side), (b.fwd, b.fwd_side)))
-            start = 0
-            for end in self.segments:
-                gb = torch.cuda.CUDAGraph()
-                self._capture_pair(gb, s, extra, ((a.bwd[start:end], a.bwd_side[start:end]),
-                                                  (b.bwd[start:end], b.bwd_side[start:end])))
-                gbs.append(gb)
-                start = end
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        torch.cuda.synchronize(self.dev)
-        self.graph_fwd, self.graph_bwd = gf, gbs
-
-    def capture_gemm_only(self):
-        """Tensor-core launches of one step (both halves, concurrently on two streams as in the real step)."""
-        torch.cuda.synchronize(self.dev)
-        s, s1 = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
-        g = torch.cuda.CUDAGraph()
-        n = 0
-
-        def gemms(e):
-            k = 0
-            for op, is_gemm in list(zip(e.fwd, e.fwd_is_gemm)) + list(zip(e.bwd, e.bwd_is_gemm)):
-                if is_gemm:
-                    op()
-                    k += 1
-            return k
-
-        with torch.cuda.stream(s):
-            with torch.cuda.graph(g, stream=s):
-                fork = torch.cuda.Event()
-                fork.record(s)
-                s1.wait_event(fork)
-                with torch.cuda.stream(s1):
-                    n += gemms(self.halves[1])
-                    done = torch.cuda.Event()
-                    done.record(s1)
-                n += gemms(self.halves[0])
-                s.wait_event(done)
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        torch.cuda.synchronize(self.dev)
-        return g, n
-
-
 # ==================================================================================================== autograd glue
 class _UNetFn(torch.autograd.Function):
     """pred = UNet(sample, t, ctx) on the static schedule; backward replays the backward schedule and hands the
@@ -1059,12 +899,17 @@ class _UNetFn(torch.autograd.Function):
         pred = torch.empty(eng.B, 4, eng.H, eng.W, dtype=BF16, device=eng.dev)
         ops.nhwc8_to_nchw4(eng.ctx, eng.pred8, pred, eng.B, eng.H, eng.W)
         ctx_.eng = eng
+        ctx_.generation = eng.generation
         ctx_.nparams = len(params)
         return pred
 
     @staticmethod
     def backward(ctx_, gpred):
         eng = ctx_.eng
+        if eng.generation != ctx_.generation:
+            raise RuntimeError('the UNet engine ran another forward on this input geometry after the forward this backward belongs '
+                               'to: its saved activations are gone.  Call backward() before the next forward of the same shape '
+                               '(no-grad / eval calls use a separate forward-only engine and are safe).')
         arena = eng.arena
         fused = getattr(eng, '_fused_loss_scale', None)
         if fused is not None and gpred.stride() == (0, 0, 0, 0):
@@ -1092,6 +937,14 @@ class _UNetFn(torch.autograd.Function):
 
 def unet_apply(unet, sample, timestep, enc, prepared=False):
     B, C, H, W = sample.shape
+    if not torch.is_grad_enabled() and not prepared:
+        # eval / no-grad call: a forward-only engine, so the activations a pending training backward needs stay intact
+        eng = unet.engine(B, H, W, enc.shape[1], forward_only=True)
+        eng.prepare_inputs(sample, timestep, enc)
+        eng.run_forward()
+        pred = torch.empty(B, 4, H, W, dtype=BF16, device=eng.dev)
+        ops.nhwc8_to_nchw4(eng.ctx, eng.pred8, pred, B, H, W)
+        return pred
     eng = unet.engine(B, H, W, enc.shape[1])
     params = [p for _, p in eng.arena.params.items()]
     return _UNetFn.apply(eng, prepared, sample, timestep, enc, *params)

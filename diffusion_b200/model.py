@@ -159,6 +159,22 @@ class _FusedMSE(torch.autograd.Function):
         return g.to(torch.bfloat16).expand(ctx_.shape), None, None
 
 
+_IMAGE_METRICS = ('FrechetInceptionDistance', 'InceptionScore', 'CLIPScore')
+
+
+def _clone_metric(metric):
+    """A fresh metric of the same class and constructor state.  The reference does `type(m)(**vars(m))` (:117,:125), which
+    relies on torchmetrics accepting its own attribute dict; fall back to a plain re-construction / deep copy."""
+    import copy
+    try:
+        return type(metric)(**{k: v for k, v in vars(metric).items() if not k.startswith('_')})
+    except Exception:
+        try:
+            return copy.deepcopy(metric)
+        except Exception:
+            return type(metric)()
+
+
 class StableDiffusion(ComposerModel):
     """Stable Diffusion ComposerModel on the B200-native UNet (see module docstring for the reference mapping)."""
 
@@ -201,13 +217,19 @@ class StableDiffusion(ComposerModel):
         self.val_guidance_scales = val_guidance_scales
         self.val_metrics = {}
         for metric in val_metrics:
-            if isinstance(metric, MeanSquaredError):
+            kind = metric.__class__.__name__
+            if kind in _IMAGE_METRICS:  # one copy per guidance scale, fed with the images generated at that scale (ref :114-122)
+                for scale in val_guidance_scales:
+                    new_metric = _clone_metric(metric)
+                    new_metric.guidance_scale = scale
+                    self.val_metrics[f'{kind}-scale-' + str(scale).replace('.', 'p')] = new_metric
+            elif isinstance(metric, MeanSquaredError):  # one copy per timestep bin (ref :123-129)
                 for bin_ in loss_bins:
-                    new_metric = type(metric)()
+                    new_metric = _clone_metric(metric)
                     new_metric.loss_bin = bin_
-                    self.val_metrics[f'{metric.__class__.__name__}-bin-{bin_[0]}-to-{bin_[1]}'.replace('.', 'p')] = new_metric
+                    self.val_metrics[f'{kind}-bin-{bin_[0]}-to-{bin_[1]}'.replace('.', 'p')] = new_metric
             else:
-                self.val_metrics[metric.__class__.__name__] = metric
+                self.val_metrics[kind] = metric
         self.val_metrics['MeanSquaredError'] = MeanSquaredError()
         self.text_encoder = text_encoder
         self.tokenizer = tokenizer
@@ -295,14 +317,39 @@ class StableDiffusion(ComposerModel):
             return {metrics.__class__.__name__: metrics}
         if isinstance(metrics, list):
             return {m.__class__.__name__: m for m in metrics}
+        for name, metric in metrics.items():
+            if not isinstance(metric, Metric):
+                raise TypeError(f'val metric {name!r} is a {type(metric).__name__}, not a torchmetrics Metric')
         return dict(metrics)
 
     def update_metric(self, batch, outputs, metric):
+        """reference :228-257.  MSE metrics see (prediction, noise), per timestep bin when the metric carries one; image
+        metrics see the images `eval_forward` generated at the metric's guidance scale."""
+        kind = metric.__class__.__name__
         if isinstance(metric, MeanSquaredError) and hasattr(metric, 'loss_bin'):
             lo, hi = metric.loss_bin
             T_max = self.noise_scheduler.num_train_timesteps
             idx = torch.where((outputs[2] >= lo * T_max) & (outputs[2] < hi * T_max))
             metric.update(outputs[0][idx], outputs[1][idx])
+        elif isinstance(metric, MeanSquaredError):
+            metric.update(outputs[0], outputs[1])
+        elif kind in _IMAGE_METRICS:
+            scale = getattr(metric, 'guidance_scale', None)
+            if len(outputs) < 4 or scale not in outputs[3]:
+                raise ValueError(f'{kind} needs the images eval_forward generates at guidance scale {scale}: the batch must carry '
+                                 f'{self.image_key!r} and {self.text_key!r} and the model its VAE and text encoder')
+            images = outputs[3][scale]
+            if kind == 'FrechetInceptionDistance':
+                metric.update(batch[self.image_key], real=True)
+                metric.update(images, real=False)
+            elif kind == 'InceptionScore':
+                metric.update(images)
+            else:  # CLIPScore scores the images against the caption strings
+                if self.tokenizer is None:
+                    raise ValueError('CLIPScore needs the tokenizer to turn the token ids back into captions; this model was '
+                                     'built without one (no vocabulary files on disk)')
+                captions = [self.tokenizer.decode(c, skip_special_tokens=True) for c in batch[self.text_key]]
+                metric.update((images * 255).to(torch.uint8), captions)
         else:
             metric.update(outputs[0], outputs[1])
 
@@ -444,9 +491,11 @@ def stable_diffusion_2(
     """Same signature as reference diffusion/models/models.py:28-39 (+ `unet_config` to override the SD-2-base UNet
     config for small test models).  The UNet is random-initialised from the SD-2-base config (`pretrained=False`,
     the yaml default); the HF hub is not reachable here, so `pretrained=True` raises, and VAE / CLIP / tokenizer are
-    attached (native modules of diffusion_b200/encoders.py, random init) when `build_encoders` is true - by default when
-    precomputed latents are not used; the tokenizer needs vocabulary files that are not on disk, so batches must carry
-    token ids (the reference dataset tokenizes in `__getitem__`)."""
+    ALWAYS attached like the reference does at models.py:80-85 (native modules of diffusion_b200/encoders.py, random
+    init, frozen, their engines built lazily on first use) - the SD-2-base yamls train on precomputed latents but evaluate
+    on image / caption batches; `build_encoders=False` skips them explicitly (small test models).  The tokenizer needs
+    vocabulary files that are not on disk, so batches must carry token ids (the reference dataset tokenizes in
+    `__getitem__`)."""
     if pretrained:
         raise ValueError('pretrained=True needs the HF hub checkpoint of the UNet; load a state_dict into '
                          'model.unet instead (parameter names follow diffusers)')
@@ -461,7 +510,7 @@ def stable_diffusion_2(
     unet = UNet2DConditionModel(**(unet_config or SD2_BASE_UNET_CONFIG))
     vae = text_encoder = None
     if build_encoders is None:
-        build_encoders = not precomputed_latents
+        build_encoders = True
     if build_encoders:  # random-init native VAE / text tower (diffusers / transformers parameter names: load_state_dict works)
         from diffusion_b200.encoders import SD2_TEXT_CONFIG, SD2_VAE_CONFIG, AutoencoderKL, CLIPTextModel
         vae = AutoencoderKL(**(vae_config or SD2_VAE_CONFIG))

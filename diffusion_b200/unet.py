@@ -177,7 +177,7 @@ class UNet2DConditionModel(nn.Module):
     def engine(self, B, H, W, ctx_len, forward_only=False):
         """Static kernel schedule for one input geometry (built lazily, cached)."""
         import os
-        from diffusion_b200.engine import DualEngine, Engine
+        from diffusion_b200.engine import Engine
         dev = self.conv_in.weight.device
         from diffusion_b200.ops import dry_run
         if dev.type != 'cuda' and not dry_run():
@@ -186,14 +186,7 @@ class UNet2DConditionModel(nn.Module):
         eng = self._engines.get(key)
         if eng is None or not eng.params_bound():
             prev = next(iter(self._engines.values()), None)
-            # opt-in: the microbatch as two concurrent half-batch chains (DualEngine).  Measured on B200 at B=16, 256^2:
-            # 27.5 ms vs 25.3 ms single-chain - persistent one-CTA-per-SM GEMM kernels of two streams do not share the
-            # SMs well - so the single chain stays the default.
-            dual = B >= 8 and B % 2 == 0 and os.environ.get('SD2_DUAL_CHAIN') == '1'
-            if forward_only:
-                eng = Engine(self, B, H, W, ctx_len, shared=prev, forward_only=True)
-            else:
-                eng = (DualEngine if dual else Engine)(self, B, H, W, ctx_len, shared=prev)
+            eng = Engine(self, B, H, W, ctx_len, shared=prev, forward_only=forward_only)
             self._engines[key] = eng
             # data parallel by default: with torch.distributed initialised on more than one rank the engine averages its
             # gradient buckets itself (idempotent under an additional DDP wrapper; SD2_NO_AUTO_SYNC=1 or eng.sync_grads = False
@@ -202,7 +195,14 @@ class UNet2DConditionModel(nn.Module):
                 import torch.distributed as dist
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not getattr(eng, 'sync_grads', False):
                     eng.enable_grad_sync()
-        eng.ddp_compat = self.ddp_compat
+        # Under a torch DistributedDataParallel wrapper (Composer's default; the wrapper marks itself active for the duration
+        # of its forward) the wrapper owns the gradient reduction: its per-parameter hooks only fire when autograd receives a
+        # gradient for every parameter (ddp_compat), and the engine's own bucket all-reduce is switched off so the arena is
+        # reduced once, and DDP.no_sync() / Composer microbatching keep their meaning.
+        wrapped = getattr(torch.nn.parallel.DistributedDataParallel, '_active_ddp_module', None) is not None
+        if wrapped and not forward_only:
+            eng.sync_grads = False
+        eng.ddp_compat = self.ddp_compat or wrapped
         return eng
 
     def forward(self, sample, timestep, encoder_hidden_states, **_unused):

@@ -44,11 +44,120 @@ def test_reference_import_paths():
         stable_diffusion_2(pretrained=True)
 
 
+def _instantiate(block):
+    """Hydra's `instantiate` for the subset the recipes use: `_target_` = dotted path, nested blocks / lists recursed.
+    `torchmetrics.*` resolves to the stand-in the product ships when torchmetrics is not installed (as in this image)."""
+    import importlib
+    if isinstance(block, list):
+        return [_instantiate(b) for b in block]
+    if not isinstance(block, dict):
+        return block
+    kwargs = {k: _instantiate(v) for k, v in block.items() if k != '_target_'}
+    if '_target_' not in block:
+        return kwargs
+    mod, _, attr = block['_target_'].rpartition('.')
+    if mod == 'torchmetrics':
+        try:
+            importlib.import_module(mod)
+        except ImportError:
+            mod = 'diffusion_b200.model'
+    return getattr(importlib.import_module(mod), attr)(**kwargs)
+
+
+@pytest.mark.parametrize('recipe', ['SD-2-base-256.yaml', 'SD-2-base-512.yaml'])
+def test_factory_accepts_the_reference_yaml_model_block(recipe):
+    """Drop-in at the recipe level: the `model:` block of the reference yamls (`_target_:
+    diffusion.models.models.stable_diffusion_2` + kwargs, fixture tests/golden/reference_model_blocks.json) instantiates
+    the B200-native model through the reference import path with exactly those keyword arguments."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, 'golden', 'reference_model_blocks.json')) as f:
+        block = json.load(f)[recipe]
+    ref = f'/root/reference/yamls/hydra-yamls/{recipe}'
+    if os.path.exists(ref):  # in the build container: the committed fixture must be the reference's current block
+        import yaml
+        with open(ref) as f:
+            assert yaml.safe_load(f)['model'] == block
+    assert block['_target_'] == 'diffusion.models.models.stable_diffusion_2'
+    assert block['precomputed_latents'] is True and block['fsdp'] is True and block['pretrained'] is False
+    model = _instantiate(block)
+    from diffusion.models.stable_diffusion import StableDiffusion
+    assert isinstance(model, StableDiffusion)
+    assert sum(p.numel() for p in model.unet.parameters()) == 865910724
+    assert len(list(model.unet.named_parameters())) == 686
+    # like the reference (models.py:80-85) the recipe's model carries frozen VAE + text encoder for the image/caption eval set
+    assert model.vae is not None and model.text_encoder is not None
+    assert not any(p.requires_grad for p in model.vae.parameters())
+    assert not any(p.requires_grad for p in model.text_encoder.parameters())
+    assert model.precomputed_latents and model.encode_latents_in_fp16
+    # val_guidance_scales: [] / loss_bins: [] in the recipe -> only the full-loss MSE metric remains (reference :111-133)
+    assert list(model.get_metrics(is_train=False)) == ['MeanSquaredError']
+    assert list(model.get_metrics(is_train=True)) == ['MeanSquaredError']
+    assert all(getattr(m, '_fsdp_wrap', None) is False for m in (model.unet, model.vae, model.text_encoder))
+
+
+def test_metric_plumbing_mirrors_the_reference():
+    """reference stable_diffusion.py:111-133 (per-guidance-scale / per-bin metric copies) and :228-257 (update_metric)."""
+    from diffusion_b200.model import MeanSquaredError, Metric, StableDiffusion, DDPMScheduler
+
+    class FrechetInceptionDistance(Metric):
+        def __init__(self, feature=64, **_kw):
+            super().__init__()
+            self.feature, self.calls = feature, []
+
+        def update(self, imgs, real):
+            self.calls.append((tuple(imgs.shape), real))
+
+    class InceptionScore(Metric):
+        def __init__(self, **_kw):
+            super().__init__()
+            self.calls = []
+
+        def update(self, imgs):
+            self.calls.append(tuple(imgs.shape))
+
+    class Other(Metric):
+        def update(self, a, b):
+            self.seen = (a, b)
+
+    unet = torch.nn.Linear(1, 1)
+    m = StableDiffusion(unet, None, None, None, DDPMScheduler(), None,
+                        val_metrics=[MeanSquaredError(), FrechetInceptionDistance(feature=192), InceptionScore(), Other()],
+                        val_guidance_scales=[1.0, 7.5], loss_bins=[(0, 0.5), (0.5, 1)])
+    names = list(m.get_metrics(is_train=False))
+    assert names == ['MeanSquaredError-bin-0-to-0p5', 'MeanSquaredError-bin-0p5-to-1', 'FrechetInceptionDistance-scale-1p0',
+                     'FrechetInceptionDistance-scale-7p5', 'InceptionScore-scale-1p0', 'InceptionScore-scale-7p5', 'Other',
+                     'MeanSquaredError']
+    vm = m.get_metrics(is_train=False)
+    assert vm['FrechetInceptionDistance-scale-7p5'].guidance_scale == 7.5 and vm['FrechetInceptionDistance-scale-7p5'].feature == 192
+    assert vm['FrechetInceptionDistance-scale-1p0'] is not vm['FrechetInceptionDistance-scale-7p5']
+    pred, noise, ts = torch.ones(4, 2), torch.zeros(4, 2), torch.tensor([10, 400, 600, 999])
+    imgs = {1.0: torch.rand(4, 3, 8, 8), 7.5: torch.rand(4, 3, 8, 8)}
+    batch = {'image': torch.rand(4, 3, 8, 8), 'captions': torch.zeros(4, 77, dtype=torch.long)}
+    out = (pred, noise, ts, imgs)
+    m.update_metric(batch, out, vm['MeanSquaredError-bin-0-to-0p5'])
+    assert float(vm['MeanSquaredError-bin-0-to-0p5'].total) == 4.0  # two of four samples fall in [0, 500)
+    m.update_metric(batch, out, vm['MeanSquaredError'])
+    assert float(vm['MeanSquaredError'].compute()) == 1.0
+    m.update_metric(batch, out, vm['FrechetInceptionDistance-scale-7p5'])
+    assert vm['FrechetInceptionDistance-scale-7p5'].calls == [((4, 3, 8, 8), True), ((4, 3, 8, 8), False)]
+    m.update_metric(batch, out, vm['InceptionScore-scale-1p0'])
+    assert vm['InceptionScore-scale-1p0'].calls == [(4, 3, 8, 8)]
+    m.update_metric(batch, out, vm['Other'])
+    assert vm['Other'].seen[0] is pred
+    with pytest.raises(ValueError):  # image metrics without generated images fail loudly instead of mis-updating
+        m.update_metric(batch, (pred, noise, ts), vm['InceptionScore-scale-1p0'])
+    m.val_metrics['bad'] = object()
+    with pytest.raises(TypeError):
+        m.get_metrics(is_train=False)
+
+
 def test_cpu_model_fails_loudly():
     from diffusion_b200.model import stable_diffusion_2
     if torch.cuda.is_available():
         pytest.skip('CPU-only check')
-    m = stable_diffusion_2(pretrained=False, precomputed_latents=True, unet_config=TINY_UNET_CONFIG, fsdp=False)
+    m = stable_diffusion_2(pretrained=False, precomputed_latents=True, build_encoders=False, unet_config=TINY_UNET_CONFIG, fsdp=False)
     batch = {'image_latents': torch.randn(2, 4, 32, 32), 'caption_latents': torch.randn(2, 77, 1024)}
     with pytest.raises(RuntimeError):
         m(batch)

@@ -451,7 +451,9 @@ def test_fused_adamw_matches_torch(ctx):
 
 # ------------------------------------------------------------------------------------------------ fused attention
 ATTN_SHAPES = [(2, 5, 1024, 1024), (2, 10, 256, 77), (1, 4, 64, 64), (2, 2, 16, 77), (1, 2, 300, 200), (1, 1, 2048, 2048),
-               (3, 1, 128, 128), (1, 3, 129, 257)]
+               (3, 1, 128, 128), (1, 3, 129, 257),
+               (2, 5, 4096, 4096), (2, 5, 4096, 77),  # SD-2-base-512 top level: self- and cross-attention
+               (2, 20, 16, 16), (3, 20, 64, 64), (2, 10, 1024, 77)]
 
 
 def _attn_inputs(B, heads, Nq, Nk, self_attn):

@@ -86,6 +86,44 @@ def test_ema_has_no_cpu_path():
     assert e.update(m, batch=1) is False and e.ema_model is None  # not started yet
 
 
+def test_ema_matches_checkpoint_events_when_a_saver_is_about_to_write():
+    """reference ema.py:221-227, 276-279: on BATCH_CHECKPOINT / EPOCH_CHECKPOINT the algorithm matches iff EMA has started
+    and a checkpoint saver's save_interval(state, event) is True; apply() then swaps the EMA weights into the model."""
+    from diffusion_b200.ema import EMA
+
+    class Saver:
+        def __init__(self, due):
+            self.due = due
+
+        def save_interval(self, state, event):
+            return self.due
+
+    class State:
+        callbacks = []
+        model = None
+
+    class Params:
+        swaps = 0
+
+        def swap_params(self, model):
+            Params.swaps += 1
+
+    e = EMA(half_life=None, smoothing=0.5)
+    st = State()
+    st.callbacks = [object(), Saver(True)]
+    assert e.match('BATCH_CHECKPOINT', st) is False  # not started
+    e.ema_started, e.ema_model = True, Params()
+    assert e.match('BATCH_CHECKPOINT', st) is True and e.match('EPOCH_CHECKPOINT', st) is True
+    st.callbacks = [Saver(False)]
+    assert e.match('BATCH_CHECKPOINT', st) is False
+    st.callbacks = []
+    assert e.match('EPOCH_CHECKPOINT', st) is False
+    e.apply('BATCH_CHECKPOINT', st)
+    assert Params.swaps == 1 and e.ema_weights_active is True
+    e.apply('BATCH_START', st)  # training resumes on the training weights
+    assert Params.swaps == 2 and e.ema_weights_active is False
+
+
 # ------------------------------------------------------------------------------------------------ f4: DDIM / generate
 def test_ddim_scheduler_matches_oracle_and_known_answers():
     from diffusion_b200.model import DDIMScheduler

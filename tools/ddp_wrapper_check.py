@@ -21,7 +21,7 @@ def main():
 
     def make():
         torch.manual_seed(17)
-        return stable_diffusion_2(pretrained=False, precomputed_latents=True, unet_config=TINY_UNET_CONFIG, fsdp=True)
+        return stable_diffusion_2(pretrained=False, precomputed_latents=True, build_encoders=False, unet_config=TINY_UNET_CONFIG, fsdp=True)
 
     g = torch.Generator(device=dev).manual_seed(100 + rank)  # different data per rank
     batch = {'image_latents': torch.randn(2, 4, 16, 16, device=dev, generator=g).to(torch.bfloat16),

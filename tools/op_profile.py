@@ -49,7 +49,7 @@ def sig(p):
 def main(B=16, R=32, out=None):
     dev = torch.device('cuda', 0)
     torch.manual_seed(17)
-    model = stable_diffusion_2(pretrained=False, precomputed_latents=True, fsdp=False)
+    model = stable_diffusion_2(pretrained=False, precomputed_latents=True, build_encoders=False, fsdp=False)
     batch = {'image_latents': torch.randn(B, 4, R, R, device=dev).to(torch.bfloat16),
              'caption_latents': torch.randn(B, 77, 1024, device=dev).to(torch.bfloat16)}
     o = model(batch)
