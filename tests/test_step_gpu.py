@@ -178,7 +178,7 @@ def test_non_square_latents_and_other_context_lengths(B, H, W, L):
     train_step(oracle, {k: v.float() for k, v in batch.items()}, timesteps=out[2], noise=out[1].float())
     # 8x8 latents put the mid block at 1x1: self-attention over a single token has exactly zero q / k gradients, for which a
     # cosine is meaningless - there the product's gradient must vanish as well
-    dead = [n for n, p in oracle.unet.named_parameters() if p.grad.float().norm().item() < 1e-12]
+    dead = [n for n, p in oracle.unet.named_parameters() if p.grad.float().norm().item() < 1e-9]
     for n in dead:
         assert model.unet.get_parameter(n).grad.float().norm().item() < 1e-6, n
     assert len(dead) == (2 if H * W == 64 else 0), dead
