@@ -31,7 +31,9 @@ struct AttnParams {
   bf16* o;
   long long ldo;
   float* lse;         // [B*heads][Nq]
-  const float* dvec;  // [B*heads][Nq]  rowsum(dO * O)
+  const float* stats;  // backward: [B*heads][query tiles][lse 128 | rowsum(dO * O) 128], see attn_bwd_prep_kernel
+  bf16* dq;            // backward, single key tile: dQ is written directly
+  long long lddq;
   bf16* dk;
   long long lddk;
   bf16* dv;
@@ -50,26 +52,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // ================================================================================================ forward
 static constexpr int AT_FWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
 
-// exp2(S c2 - m c2) of one 32-column chunk -> bf16 -> swizzled smem; returns the fp32 row sum of the chunk
+// exp2(S c2 - m c2) of one 32-column chunk -> bf16 pairs -> 16 columns of the P operand in tensor memory (row = this
+// thread's TMEM lane); returns the fp32 row sum of the chunk
 template <bool MASKED>
-__device__ __forceinline__ float attn_exp_chunk(const uint32_t* rs, float c2, float mc, int col0, int nvalid, uint8_t* prow,
-                                                int c, int r) {
+__device__ __forceinline__ float attn_exp_chunk(const uint32_t* rs, float c2, float mc, int col0, int nvalid, uint32_t tP) {
   float sum = 0.f;
+  uint32_t pk[16];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float pv[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float x = ex2(fmaf(__uint_as_float(rs[g * 8 + e]), c2, -mc));
-      if (MASKED && col0 + g * 8 + e >= nvalid) x = 0.f;
-      pv[e] = x;
-      sum += x;
-    }
-    uint4 u;
-    u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]);
-    u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
-    *reinterpret_cast<uint4*>(prow + (((c * 4 + g) ^ (r & 7)) << 4)) = u;
+  for (int e = 0; e < 32; e += 2) {
+    float x0 = ex2(fmaf(__uint_as_float(rs[e]), c2, -mc));
+    float x1 = ex2(fmaf(__uint_as_float(rs[e + 1]), c2, -mc));
+    if (MASKED && col0 + e >= nvalid) x0 = 0.f;
+    if (MASKED && col0 + e + 1 >= nvalid) x1 = 0.f;
+    sum += x0 + x1;
+    pk[e >> 1] = pack_bf16x2(x0, x1);
   }
+  tmem_st_32x32b_x16(tP, pk);
   return sum;
 }
 
@@ -81,8 +79,7 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_TILE;      // [2] K tiles (ring)
   uint8_t* sV = sK + 2 * AT_TILE;  // one V tile (consumed late in a step, so a single buffer suffices)
-  uint8_t* sP = sV + AT_TILE;      // [2] the two 64-column halves of P: [128 rows][128 B] each
-  float* xch = reinterpret_cast<float*>(sP + 2 * AT_TILE);  // [2 parities][2 halves][128 rows] row-max / row-sum exchange
+  float* xch = reinterpret_cast<float*>(sV + AT_TILE);  // [2 parities][2 halves][128 rows] row-max / row-sum exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 512);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;   // [2]
@@ -131,7 +128,8 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  // S: 128 fp32 columns; O: 64; P (bf16, two keys per column, A operand of the second GEMM straight from tensor memory): 64
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
   pdl_grid_sync();
 
   if (warp == 0) {
@@ -161,7 +159,6 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
     const uint64_t dQ0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-    const uint64_t dP0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
     const uint64_t dK0 = umma_desc_sw128(smem_u32(sK), 16, 1024);   // K-major
     const uint64_t dV0 = umma_desc_sw128(smem_u32(sV), 8192, 1024); // MN-major
     constexpr uint64_t TS = AT_TILE >> 4;
@@ -198,8 +195,8 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            tc_mma_bf16(tO, dP0 + (uint64_t)hlf * TS + 2 * ks, dV0 + (uint64_t)(hlf * 4 + ks) * 128, idesc_o,
-                        (hlf | ks) != 0 ? 1u : 0u);
+            tc_mma_bf16_ts(tO, tP + (uint32_t)((hlf * 4 + ks) * 8), dV0 + (uint64_t)(hlf * 4 + ks) * 128, idesc_o,
+                           (hlf | ks) != 0 ? 1u : 0u);
           tc_commit(&p_empty[hlf]);
           if (hlf == 1) {
             tc_commit(o_full);
@@ -218,7 +215,8 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t tS_h = tS + lane_off + (uint32_t)(hh * 64);
-    uint8_t* prow = sP + hh * AT_TILE + r * 128;
+    const uint32_t tP_h = tP + lane_off + (uint32_t)(hh * 32);
+    const uint32_t xch_s = smem_u32(xch);
     float m = -INFINITY, l = 0.f, a_pend = 0.f;
     float o[32];
 #pragma unroll
@@ -244,10 +242,10 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
             if (hh * 64 + c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(rs[e]));
         }
       }
-      float* xb = xch + (j & 1) * 256;
-      xb[hh * 128 + r] = mx;
+      const uint32_t xb = xch_s + (uint32_t)(j & 1) * 1024;
+      sts32f(xb + (hh * 128 + r) * 4, mx);
       named_bar_sync(1, 256);
-      const float m_new = fmaxf(m, fmaxf(mx, xb[(hh ^ 1) * 128 + r]));
+      const float m_new = fmaxf(m, fmaxf(mx, lds32f(xb + ((hh ^ 1) * 128 + r) * 4)));
       if (j > 0) {  // O += P_{j-1} V_{j-1}: deferred to here so that the tensor pipe's latency is hidden behind pass 1
         mbar_wait(o_full, (uint32_t)((j - 1) & 1));
         tc_fence_after();
@@ -277,11 +275,12 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
           if (lane == 0) mbar_arrive(s_empty);
         }
         if (!masked)
-          rowsum += attn_exp_chunk<false>(rs, p.c2, mc, 0, 0, prow, c, r);
+          rowsum += attn_exp_chunk<false>(rs, p.c2, mc, 0, 0, tP_h + (uint32_t)(c * 16));
         else
-          rowsum += attn_exp_chunk<true>(rs, p.c2, mc, hh * 64 + c * 32, nvalid, prow, c, r);
+          rowsum += attn_exp_chunk<true>(rs, p.c2, mc, hh * 64 + c * 32, nvalid, tP_h + (uint32_t)(c * 16));
       }
-      fence_proxy_async_smem();
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[hh]);
       l = l * a + rowsum;
@@ -297,10 +296,10 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
       for (int e = 0; e < 32; ++e) o[e] = fmaf(o[e], a_pend, __uint_as_float(ro[e]));
     }
     // total row sum = both halves
-    float* xb = xch + (nkt & 1) * 256;
-    xb[hh * 128 + r] = l;
+    const uint32_t xb = xch_s + (uint32_t)(nkt & 1) * 1024;
+    sts32f(xb + (hh * 128 + r) * 4, l);
     named_bar_sync(1, 256);
-    l += xb[(hh ^ 1) * 128 + r];
+    l += lds32f(xb + ((hh ^ 1) * 128 + r) * 4);
     const int row = qt * 128 + r;
     if (row < p.Nq) {
       const float inv = 1.f / l;
@@ -321,33 +320,47 @@ __global__ void __launch_bounds__(AT_FWD_THREADS, 2)
 }
 
 // ================================================================================================ backward
-// D[bh][i] = sum_d O[i][d] dO[i][d]; 8 lanes per (row, head): 16-byte loads, shuffle reduce.
-__global__ void attn_dot_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o, long long lddo,
-                                float* __restrict__ dvec, int B, int heads, int Nq) {
+// Pre-pass of the backward: D[bh][i] = sum_d O[i][d] dO[i][d] and a copy of the forward's log-sum-exp, both into a
+// buffer padded to whole 128-query tiles - st[bh][tile][0][128] = lse (+inf for rows >= Nq, which makes P vanish there),
+// st[bh][tile][1][128] = D (0 for padding) - so that the main kernel fetches one contiguous 1 KB block per query tile
+// with a bulk copy.  8 lanes per (row, head): 16-byte loads, shuffle reduce.
+__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o, long long lddo,
+                                     const float* __restrict__ lse, float* __restrict__ st, int B, int heads, int Nq, int nqt) {
   pdl_grid_sync();
-  const long long total = (long long)B * Nq * heads * 8;
+  const int Np = nqt * 128;
+  const long long total = (long long)B * Np * heads * 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float acc = 0.f;
-  long long rowh = i >> 3;
+  const long long rowh = i >> 3;
   const int sub = (int)(i & 7);
   const bool ok = i < total;
-  long long row = 0;
-  int h = 0;
+  long long rowp = 0;
+  int h = 0, qi = 0;
+  long long bb = 0;
+  bool real = false;
   if (ok) {
-    row = rowh / heads;
+    rowp = rowh / heads;
     h = (int)(rowh % heads);
-    const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + h * 64 + sub * 8);
-    const uint4 g = *reinterpret_cast<const uint4*>(d_o + row * lddo + h * 64 + sub * 8);
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-    const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
-    acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+    bb = rowp / Np;
+    qi = (int)(rowp % Np);
+    real = qi < Nq;
+    if (real) {
+      const long long row = bb * Nq + qi;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + h * 64 + sub * 8);
+      const uint4 g = *reinterpret_cast<const uint4*>(d_o + row * lddo + h * 64 + sub * 8);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+      acc = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+    }
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
   if (ok && sub == 0) {
-    const long long bb = row / Nq, qi = row % Nq;
-    dvec[(bb * heads + h) * Nq + qi] = acc;
+    const long long bh = bb * heads + h;
+    float* dst = st + ((bh * nqt + (qi >> 7)) * 2) * 128 + (qi & 127);
+    dst[0] = real ? lse[bh * Nq + qi] : INFINITY;
+    dst[128] = real ? acc : 0.f;
   }
 }
 
@@ -370,61 +383,55 @@ __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __re
 
 static constexpr int AT_BWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 compute (two threads per key row)
 
-// P^T = exp2(S^T c2 - lse), dS^T = P^T (dP^T - D) for one 32-column (query) chunk of this thread's key row, packed to
-// bf16 in registers (the 1/sqrt(d) factor of dS is applied when dQ / dK are drained)
-template <bool MASKED>
-__device__ __forceinline__ void attn_bwd_chunk(const uint32_t* rs, const uint32_t* rd, const float* lse_t, const float* d_t,
-                                               float c2, bool key_ok, uint4* pk_p, uint4* pk_d) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float4 l0 = *reinterpret_cast<const float4*>(lse_t + g * 8);
-    const float4 l1 = *reinterpret_cast<const float4*>(lse_t + g * 8 + 4);
-    const float4 d0 = *reinterpret_cast<const float4*>(d_t + g * 8);
-    const float4 d1 = *reinterpret_cast<const float4*>(d_t + g * 8 + 4);
-    const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    float pv[8], dsv[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float pe = ex2(fmaf(__uint_as_float(rs[g * 8 + e]), c2, -ls[e]));
-      if (MASKED && !key_ok) pe = 0.f;
-      pv[e] = pe;
-      dsv[e] = pe * (__uint_as_float(rd[g * 8 + e]) - dd[e]);
-    }
-    pk_p[g].x = pack_bf16x2(pv[0], pv[1]); pk_p[g].y = pack_bf16x2(pv[2], pv[3]);
-    pk_p[g].z = pack_bf16x2(pv[4], pv[5]); pk_p[g].w = pack_bf16x2(pv[6], pv[7]);
-    pk_d[g].x = pack_bf16x2(dsv[0], dsv[1]); pk_d[g].y = pack_bf16x2(dsv[2], dsv[3]);
-    pk_d[g].z = pack_bf16x2(dsv[4], dsv[5]); pk_d[g].w = pack_bf16x2(dsv[6], dsv[7]);
-  }
-}
-
-// dQ tile of one query block: this warp group's 32 columns, TMEM -> fp32 staging -> TMA reduce-add
-__device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint8_t* my_stg, int lane, float scale, uint64_t* dq_empty,
-                                                  const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h, int b) {
+// dQ tile of one query block, this warp group's 32 columns.  Several key tiles (DIRECT = false): TMEM -> fp32 staging ->
+// TMA reduce-add into the fp32 accumulator.  A single key tile (cross-attention over 77 tokens, self-attention over
+// <= 128 tokens): the tile is complete, it goes to the bf16 gradient directly (no accumulator, no memset, no cast pass).
+template <bool DIRECT>
+__device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_stg, const void* my_stg_g, int lane, float scale,
+                                                  uint64_t* dq_empty,
+                                                  const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h, int b,
+                                                  bf16* dq, long long lddq) {
   uint32_t rq[32];
   tmem_ld_32x32b_x32(taddr, rq);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) {
-    mbar_arrive(dq_empty);
-    bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
-  }
-  __syncwarp();
-  uint8_t* bufp = my_stg + lane * 128;
+  if (DIRECT) {
+    if (lane == 0) mbar_arrive(dq_empty);
+    const int row = row0 + lane;
+    if (row < Nq) {
+      bf16* dst = dq + ((long long)b * Nq + row) * lddq + h * 64 + col0;
 #pragma unroll
-  for (int g = 0; g < 8; ++g)
-    *reinterpret_cast<float4*>(bufp + ((g ^ (lane & 7)) << 4)) =
-        make_float4(__uint_as_float(rq[g * 4]) * scale, __uint_as_float(rq[g * 4 + 1]) * scale,
-                    __uint_as_float(rq[g * 4 + 2]) * scale, __uint_as_float(rq[g * 4 + 3]) * scale);
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) {
-    if (row0 < Nq) tma_reduce_add_4d(tmDQ, my_stg, col0, row0, h, b);
-    bulk_commit();
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(rq[g * 8 + 0]) * scale, __uint_as_float(rq[g * 8 + 1]) * scale);
+        u.y = pack_bf16x2(__uint_as_float(rq[g * 8 + 2]) * scale, __uint_as_float(rq[g * 8 + 3]) * scale);
+        u.z = pack_bf16x2(__uint_as_float(rq[g * 8 + 4]) * scale, __uint_as_float(rq[g * 8 + 5]) * scale);
+        u.w = pack_bf16x2(__uint_as_float(rq[g * 8 + 6]) * scale, __uint_as_float(rq[g * 8 + 7]) * scale);
+        *reinterpret_cast<uint4*>(dst + g * 8) = u;
+      }
+    }
+  } else {
+    if (lane == 0) {
+      mbar_arrive(dq_empty);
+      bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
+    }
+    __syncwarp();
+    const uint32_t bufp = my_stg + lane * 128;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      sts128f(bufp + ((g ^ (lane & 7)) << 4), __uint_as_float(rq[g * 4]) * scale, __uint_as_float(rq[g * 4 + 1]) * scale,
+              __uint_as_float(rq[g * 4 + 2]) * scale, __uint_as_float(rq[g * 4 + 3]) * scale);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (row0 < Nq) tma_reduce_add_4d(tmDQ, my_stg_g, col0, row0, h, b);
+      bulk_commit();
+    }
   }
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -438,20 +445,21 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
   uint8_t* sPT = sdO + 2 * AT_TILE;  // P^T  : 2 query chunks x [128 key rows][128 B]
   uint8_t* sdS = sPT + 2 * AT_TILE;  // dS^T : same layout
   uint8_t* stg = sdS + 2 * AT_TILE;  // 8 warps x 4 KB fp32 staging for the dQ reduce-add
-  float* sLSE = reinterpret_cast<float*>(stg + 8 * 4096);  // [2][128]
-  float* sD = sLSE + 256;                                   // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  float* sStat = reinterpret_cast<float*>(stg + 8 * 4096);  // [2 stages][lse 128 | D 128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 512);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;   // [2]
   uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* sdp_empty = bars + 6;
-  uint64_t* pds_full = bars + 7;
-  uint64_t* pds_empty = bars + 8;
-  uint64_t* dq_full = bars + 9;
-  uint64_t* dq_empty = bars + 10;
-  uint64_t* dkv_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* dp_full = bars + 7;
+  uint64_t* dp_empty = bars + 8;
+  uint64_t* pds_full = bars + 9;
+  uint64_t* pds_empty = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint64_t* dq_empty = bars + 12;
+  uint64_t* dkv_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmdO);
-    tma_prefetch_desc(&tmDQ);
+    if (!DIRECT) tma_prefetch_desc(&tmDQ);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -471,8 +479,10 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
         mbar_init(&qdo_full[s], 1);
         mbar_init(&qdo_empty[s], 1);
       }
-      mbar_init(sdp_full, 1);
-      mbar_init(sdp_empty, 8);
+      mbar_init(s_full, 1);
+      mbar_init(s_empty, 8);
+      mbar_init(dp_full, 1);
+      mbar_init(dp_empty, 8);
       mbar_init(pds_full, 8);
       mbar_init(pds_empty, 1);
       mbar_init(dq_full, 1);
@@ -500,18 +510,23 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
       tma_load_4d(sV, &tmV, kv_full, 0, kt * 128, h, b);
     }
     __syncwarp();
+    const float* st_bh = p.stats + ((long long)b * p.heads + h) * nqt * 256;
     for (int i = 0; i < nqt; ++i) {
       const int s = i & 1;
       mbar_wait(&qdo_empty[s], (uint32_t)((i >> 1) & 1) ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * AT_TILE);
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * AT_TILE + 1024);
         tma_load_4d(sQ + s * AT_TILE, &tmQ, &qdo_full[s], 0, i * 128, h, b);
         tma_load_4d(sdO + s * AT_TILE, &tmdO, &qdo_full[s], 0, i * 128, h, b);
+        bulk_load_1d(sStat + s * 256, st_bh + (long long)i * 256, 1024, &qdo_full[s]);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
+    // Tensor-pipe order per query tile i:  [dV, dK, dQ of tile i-1]  S^T(i+1)  dP^T(i+1)  - the score tile of the next
+    // iteration is issued as soon as the compute warps hold S^T(i) in registers (s_empty, early in their iteration), the
+    // dP^T one when dP^T(i) has been read (late), so both are complete long before tile i+1 needs them.
     constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : A K-major, B K-major
     constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major (smem P^T / dS^T), B MN-major
     constexpr uint32_t id_mn = umma_idesc_bf16(128, 64, 1, 1);   // dQ        : A MN-major (dS), B MN-major (K)
@@ -528,25 +543,32 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK + 2 * ks, bQ0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+      tc_commit(s_full);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV + 2 * ks, bdO0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
-      tc_commit(sdp_full);
+      tc_commit(dp_full);
     }
     __syncwarp();
     for (int i = 0; i < nqt; ++i) {
       const int s = i & 1;
-      if (i + 1 < nqt) {  // next tile's scores as soon as S^T_i / dP^T_i have been read
+      if (i + 1 < nqt) {
         const int s1 = (i + 1) & 1;
-        mbar_wait(sdp_empty, (uint32_t)(i & 1));
+        const uint64_t bQ = bQ0 + (uint64_t)s1 * TS, bdO = bdO0 + (uint64_t)s1 * TS;
+        mbar_wait(s_empty, (uint32_t)(i & 1));
         mbar_wait(&qdo_full[s1], (uint32_t)(((i + 1) >> 1) & 1));
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t bQ = bQ0 + (uint64_t)s1 * TS, bdO = bdO0 + (uint64_t)s1 * TS;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK + 2 * ks, bQ + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+          tc_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait(dp_empty, (uint32_t)(i & 1));
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV + 2 * ks, bdO + 2 * ks, id_s, ks != 0 ? 1u : 0u);
-          tc_commit(sdp_full);
+          tc_commit(dp_full);
         }
         __syncwarp();
       }
@@ -585,70 +607,80 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int key = kt * 128 + r;
     const bool key_ok = key < p.Nk;
-    const bool masked = (kt + 1) * 128 > p.Nk;  // only the last key tile has padding rows
-    const long long bh = (long long)b * p.heads + h;
-    uint8_t* my_stg = stg + (size_t)(warp - 2) * 4096;
-    uint8_t* pt_row = sPT + hh * AT_TILE + r * 128;
-    uint8_t* ds_row = sdS + hh * AT_TILE + r * 128;
-    float nlse = INFINITY, nD = 0.f;
-    if (hh == 0 && r < p.Nq) {
-      nlse = p.lse[bh * p.Nq + r];
-      nD = p.dvec[bh * p.Nq + r];
-    }
+    // Padding key rows of the last key tile need no masking: their K rows are zero-filled by TMA, so they add nothing to
+    // dQ = dS K, and their dV / dK rows are never stored.
+    const uint8_t* my_stg_g = stg + (size_t)(warp - 2) * 4096;
+    const uint32_t my_stg = smem_u32(my_stg_g);
+    const uint32_t pt_row = smem_u32(sPT) + hh * AT_TILE + r * 128;
+    const uint32_t ds_row = smem_u32(sdS) + hh * AT_TILE + r * 128;
+    const uint32_t stat0 = smem_u32(sStat) + hh * 256;  // this group's 64 queries of the lse block; D block is 512 B further
+    const float c2 = p.c2;
     for (int i = 0; i < nqt; ++i) {
-      const int buf = i & 1;
-      if (hh == 0) {
-        sLSE[buf * 128 + r] = nlse;
-        sD[buf * 128 + r] = nD;
-      }
-      named_bar_sync(1, 256);
-      if (hh == 0) {  // prefetch the next tile's per-query statistics
-        const int qn = (i + 1) * 128 + r;
-        nlse = INFINITY;
-        nD = 0.f;
-        if (i + 1 < nqt && qn < p.Nq) {
-          nlse = p.lse[bh * p.Nq + qn];
-          nD = p.dvec[bh * p.Nq + qn];
-        }
-      }
-      mbar_wait(sdp_full, (uint32_t)(i & 1));
+      const uint32_t stat = stat0 + (uint32_t)(i & 1) * 1024;
+      mbar_wait(&qdo_full[i & 1], (uint32_t)((i >> 1) & 1));  // the statistics block of this query tile has landed
+      mbar_wait(s_full, (uint32_t)(i & 1));
       tc_fence_after();
-      const float* lse_t = sLSE + buf * 128 + hh * 64;
-      const float* d_t = sD + buf * 128 + hh * 64;
-      // all of this tile's math goes to registers first: the MMAs of the previous tile (which still read the P^T / dS^T
-      // smem and produce dQ_{i-1}) run underneath it
+      // P^T = exp2(S^T c2 - lse): both 32-column chunks are pulled into registers first, which hands the S^T buffer back to
+      // the tensor pipe right away
+      uint32_t rs[64];
+      tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64), rs);
+      tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64 + 32), rs + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
       uint4 pk_p[8], pk_d[8];
 #pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const float4 l = lds128f(stat + g * 16);
+        float e0 = ex2(fmaf(__uint_as_float(rs[g * 4 + 0]), c2, -l.x));
+        float e1 = ex2(fmaf(__uint_as_float(rs[g * 4 + 1]), c2, -l.y));
+        float e2 = ex2(fmaf(__uint_as_float(rs[g * 4 + 2]), c2, -l.z));
+        float e3 = ex2(fmaf(__uint_as_float(rs[g * 4 + 3]), c2, -l.w));
+        rs[g * 4 + 0] = __float_as_uint(e0); rs[g * 4 + 1] = __float_as_uint(e1);
+        rs[g * 4 + 2] = __float_as_uint(e2); rs[g * 4 + 3] = __float_as_uint(e3);
+        const uint32_t lo = pack_bf16x2(e0, e1), hi = pack_bf16x2(e2, e3);
+        if (g & 1) { pk_p[g >> 1].z = lo; pk_p[g >> 1].w = hi; } else { pk_p[g >> 1].x = lo; pk_p[g >> 1].y = hi; }
+      }
+      // dS^T = P^T (dP^T - D)   (the 1/sqrt(d) factor is applied when dQ / dK are drained)
+      mbar_wait(dp_full, (uint32_t)(i & 1));
+      tc_fence_after();
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64 + c * 32), rs);
+        uint32_t rd[32];
         tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(hh * 64 + c * 32), rd);
         tmem_wait_ld();
         if (c == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_empty);
+          if (lane == 0) mbar_arrive(dp_empty);
         }
-        if (!masked)
-          attn_bwd_chunk<false>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, true, pk_p + c * 4, pk_d + c * 4);
-        else
-          attn_bwd_chunk<true>(rs, rd, lse_t + c * 32, d_t + c * 32, p.c2, key_ok, pk_p + c * 4, pk_d + c * 4);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 d = lds128f(stat + 512 + (c * 8 + g) * 16);
+          const int e = c * 32 + g * 4;
+          const float v0 = __uint_as_float(rs[e + 0]) * (__uint_as_float(rd[g * 4 + 0]) - d.x);
+          const float v1 = __uint_as_float(rs[e + 1]) * (__uint_as_float(rd[g * 4 + 1]) - d.y);
+          const float v2 = __uint_as_float(rs[e + 2]) * (__uint_as_float(rd[g * 4 + 2]) - d.z);
+          const float v3 = __uint_as_float(rs[e + 3]) * (__uint_as_float(rd[g * 4 + 3]) - d.w);
+          const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
+          const int gi = c * 4 + (g >> 1);
+          if (g & 1) { pk_d[gi].z = lo; pk_d[gi].w = hi; } else { pk_d[gi].x = lo; pk_d[gi].y = hi; }
+        }
       }
       if (i > 0) {  // dQ_{i-1} (rows = queries): drained now, after its MMAs had a whole tile of math to complete
         mbar_wait(dq_full, (uint32_t)((i - 1) & 1));
         tc_fence_after();
-        attn_bwd_drain_dq(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, lane, p.scale, dq_empty, &tmDQ, hh * 32,
-                          (i - 1) * 128 + q * 32, p.Nq, h, b);
+        attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hh * 32,
+                                  (i - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
       }
       mbar_wait(pds_empty, (uint32_t)(i & 1) ^ 1u);  // P^T / dS^T smem consumed by the previous tile's MMAs
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int off = ((c * 4 + g) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(pt_row + off) = pk_p[c * 4 + g];
-          *reinterpret_cast<uint4*>(ds_row + off) = pk_d[c * 4 + g];
-        }
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t off = (uint32_t)((g ^ (r & 7)) << 4);
+        sts128(pt_row + off, pk_p[g]);
+        sts128(ds_row + off, pk_d[g]);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
@@ -656,8 +688,8 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     {  // last tile's dQ
       mbar_wait(dq_full, (uint32_t)((nqt - 1) & 1));
       tc_fence_after();
-      attn_bwd_drain_dq(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, lane, p.scale, dq_empty, &tmDQ, hh * 32,
-                        (nqt - 1) * 128 + q * 32, p.Nq, h, b);
+      attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hh * 32,
+                                (nqt - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
     }
     // dV, dK of this key tile (this group's 32 columns of each)
     mbar_wait(dkv_full, 0);
@@ -681,8 +713,10 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
         }
       }
     }
-    if (lane == 0) bulk_wait_read<0>();
-    __syncwarp();
+    if (!DIRECT) {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -730,7 +764,7 @@ int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.o = reinterpret_cast<bf16*>(o);
   p.ldo = ldo;
   p.lse = lse;
-  const size_t smem = 6 * AT_TILE + 512 * 4 + 16 * 8 + 16 + 1024;
+  const size_t smem = 4 * AT_TILE + 512 * 4 + 16 * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -743,7 +777,8 @@ int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
 }
 
 long long sd2_attn_bwd_ws_bytes(int B, int heads, int Nq) {
-  return (long long)B * Nq * heads * 64 * 4 + (long long)B * heads * Nq * 4;
+  const long long nqt = (Nq + 127) / 128;
+  return (long long)B * Nq * heads * 64 * 4 + (long long)B * heads * nqt * 256 * 4;
 }
 
 int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
@@ -757,8 +792,10 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   if (!ws) return fail(ctx, "sd2_attn_bwd: workspace required (sd2_attn_bwd_ws_bytes)");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int C = heads * 64;
-  float* dq32 = reinterpret_cast<float*>(ws);                      // [B*Nq][C] fp32 accumulation of dQ
-  float* dvec = dq32 + (long long)B * Nq * C;                      // [B*heads][Nq]
+  const int nqt = (Nq + 127) / 128, nkt = (Nk + 127) / 128;
+  const bool direct = nkt == 1;  // one key tile: every dQ tile has a single contribution and is written as bf16 directly
+  float* dq32 = reinterpret_cast<float*>(ws);      // [B*Nq][C] fp32 accumulation of dQ (several key tiles only)
+  float* stats = dq32 + (long long)B * Nq * C;     // [B*heads][nqt][lse 128 | D 128]
   CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
   std::string err;
   if (!head_tmap(&tmQ, q, ldq, Nq, heads, B, &err) || !head_tmap(&tmK, k, ldk, Nk, heads, B, &err) ||
@@ -771,25 +808,35 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk;
   p.scale = scale;
   p.c2 = scale * 1.4426950408889634f;
-  p.lse = const_cast<float*>(lse);
-  p.dvec = dvec;
+  p.stats = stats;
+  p.dq = reinterpret_cast<bf16*>(dq);
+  p.lddq = lddq;
   p.dk = reinterpret_cast<bf16*>(dk);
   p.lddk = lddk;
   p.dv = reinterpret_cast<bf16*>(dv);
   p.lddv = lddv;
-  const long long nd = (long long)B * Nq * heads * 8;
-  launch_k(attn_dot_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(o), ldo,
-           reinterpret_cast<const bf16*>(d_o), lddo, dvec, B, heads, Nq);
-  cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * Nq * C * 4, stream);
-  if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
-  const size_t smem = 10 * AT_TILE + 8 * 4096 + 4 * 128 * 4 + 13 * 8 + 16 + 1024;
+  const long long nd = (long long)B * nqt * 128 * heads * 8;
+  launch_k(attn_bwd_prep_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(o), ldo,
+           reinterpret_cast<const bf16*>(d_o), lddo, lse, stats, B, heads, Nq, nqt);
+  cudaError_t e;
+  if (!direct) {
+    e = cudaMemsetAsync(dq32, 0, (size_t)B * Nq * C * 4, stream);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
+  }
+  const size_t smem = 10 * AT_TILE + 8 * 4096 + 512 * 4 + 15 * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
-    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd attr: ") + cudaGetErrorString(e));
     attr = true;
   }
-  attn_bwd_kernel<<<dim3((Nk + 127) / 128, heads, B), AT_BWD_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+  if (direct) {
+    e = launch_k(attn_bwd_kernel<true>, dim3(nkt, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd launch: ") + cudaGetErrorString(e));
+    return check_launch(ctx, "attn_bwd", 2);
+  }
+  attn_bwd_kernel<false><<<dim3(nkt, heads, B), AT_BWD_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
   launch_k(cast2d_f32_bf16_kernel, dim3(grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream,
            (const float*)dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
   return check_launch(ctx, "attn_bwd", 3);

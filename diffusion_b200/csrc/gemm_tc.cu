@@ -122,6 +122,7 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
   const int cl = c - st.c0;  // chunk index within this warp's column range
   const bool new_buf = f32_out || OUT_CH == 32 || (cl & 1) == 0;
   uint8_t* buf = stg;
+  const uint32_t buf_s = smem_u32(stg);
   bool waited = false;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -151,19 +152,20 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
       __syncwarp();
       waited = true;
     }
+    // explicit st.shared (the re-aligned dynamic smem pointer would otherwise compile to generic ST.E)
     if (f32_out) {  // staging tile: 32 rows x 32 fp32 (128 B rows), SWIZZLE_128B
-      uint8_t* rowp = buf + lane * 128;
-      *reinterpret_cast<float4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+      const uint32_t rowp = buf_s + lane * 128;
+      sts128f(rowp + (((2 * g) ^ (lane & 7)) << 4), v[0], v[1], v[2], v[3]);
+      sts128f(rowp + (((2 * g + 1) ^ (lane & 7)) << 4), v[4], v[5], v[6], v[7]);
     } else {
       uint4 o;
       o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
       o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
       if (OUT_CH == 64) {  // 32 rows x 64 bf16 (128 B rows), SWIZZLE_128B; this ld fills half a row
         const int j = (cl & 1) * 4 + g;
-        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        sts128(buf_s + lane * 128 + ((j ^ (lane & 7)) << 4), o);
       } else {  // 32 rows x 32 bf16 (64 B rows), SWIZZLE_64B
-        *reinterpret_cast<uint4*>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+        sts128(buf_s + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4), o);
       }
     }
   }

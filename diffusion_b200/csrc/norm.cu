@@ -24,12 +24,6 @@ __device__ __forceinline__ void store8(bf16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// contiguous global -> shared bulk copy (no tensor map), completion on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // Pixel chunks per image: B * P blocks should fill two waves of (2 resident blocks per SM) without a ragged tail.
 static inline int gn_chunks(int HW, int B, int C, int num_sms) {
