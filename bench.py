@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 # algorithmic training FLOPs per image = 3 (fwd+dgrad+wgrad) * 2 * forward MACs
 TFLOP_PER_IMAGE = {32: 3 * 2 * 90.55e9 / 1e12, 64: 3 * 2 * 402.13e9 / 1e12}
 METRIC = 'sd2_unet_train_images_per_sec'
+CPU_SAMPLE_BATCH = 2  # images per CPU step in BOTH CPU legs (--impl reference and cpu_baseline): one baseline, not two
 
 
 def measured_traffic(batch, latent):
@@ -117,12 +118,57 @@ def oracle_cpu_step_rate(res, batch, steps, warmup, threads):
     return batch * steps / dt, dt / steps
 
 
+def gpu_library_step_rate(res, batch, steps, warmup, dev):
+    """SURVEY.md 8(d) comparator: the oracle restatement of the reference step under bf16 autocast, eager torch on the SAME
+    GPU (cuDNN implicit-GEMM convs, cuBLASLt linears, SDPA attention - what reference models.py:74-78,109-111 would dispatch
+    to on this box) + torch's fused AdamW.  Informational: it never touches the product path."""
+    from oracle.stable_diffusion import StableDiffusionOracle, train_step
+    from oracle.unet import SD2_BASE_UNET_CONFIG
+    torch.manual_seed(17)
+    model = StableDiffusionOracle(SD2_BASE_UNET_CONFIG).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1.0e-4, weight_decay=0.01, fused=True)
+    b = {'image_latents': torch.randn(batch, 4, res, res, device=dev).bfloat16(),
+         'caption_latents': torch.randn(batch, 77, 1024, device=dev).bfloat16()}
+
+    def one():
+        train_step(model, b, autocast_dtype=torch.bfloat16)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt
+    torch.cuda.empty_cache()
+    return batch / (ms * 1e-3), ms
+
+
+def time_graph(g, reps=5):
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    batch = 1  # bounded sample of the microbatch so that K steps end within minutes on host cores
+    batch = CPU_SAMPLE_BATCH  # bounded sample of the microbatch (the same one the cpu_baseline leg of our arm times)
     val, s_per_step = oracle_cpu_step_rate(args.latent, batch, args.steps, max(1, min(args.warmup, 1)), cores)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
@@ -135,6 +181,40 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_microbatch(model, opt, mb, R, dev, steps, warmup, graphs):
+    """The same training step at another per-GPU microbatch (own engine over the shared parameter arena): images/s."""
+    lat = torch.randn(mb, 4, R, R, device=dev).to(torch.bfloat16)
+    ctx = torch.randn(mb, 77, 1024, device=dev).to(torch.bfloat16)
+    batch = {'image_latents': lat, 'caption_latents': ctx}
+    eng = model.unet.engine(mb, R, R, 77)
+
+    def step():
+        loss = model.loss(model(batch), batch)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    l0 = eng.ctx.launches
+    step()
+    torch.cuda.synchronize()
+    launches = eng.ctx.launches - l0
+    if graphs:
+        eng.capture_graphs()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'per_gpu_microbatch': mb, 'value': mb / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms,
+            'gpu_launches_per_step': launches,
+            'note': 'reference yaml device_train_microbatch_size (SD-2-base-256.yaml:87); optimizer step every microbatch like the headline line'}
 
 
 def run_ours(args):
@@ -237,23 +317,26 @@ def run_ours(args):
     if rank == 0:
         sustained, burst, hbm, how = read_peaks()
         g, n_gemm = eng.capture_gemm_only()
-        for _ in range(2):
-            g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record()
-        for _ in range(reps):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        gemm_ms = e0.elapsed_time(e1) / reps
+        gemm_ms = time_graph(g)
         achieved = TFLOP_PER_IMAGE[R] * B / (gemm_ms * 1e-3)
+        step_ms = ms_dev / args.steps
+        step_tflops = TFLOP_PER_IMAGE[R] * B / (step_ms * 1e-3)
+        # fused attention alone (attn_fwd / attn_bwd launches of the step): its own algorithmic FLOPs (4 N_q N_k d forward,
+        # 10 N_q N_k d backward per head) over its own time
+        ga, n_attn = eng.capture_gemm_only(only=('attn_fwd', 'attn_bwd'))
+        attn_ms = time_graph(ga)
+        attn_tf = eng.attn_flops / 1e12
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s', 'frac': achieved / sustained,
                 'traffic': measured_traffic(B, R), 'kernel': 'tensor-core family of one step replayed alone: gemm_tc_kernel<BN,A_MN,B_MN> (every GEMM/conv) + attn_fwd/bwd_kernel',
                 'launches_per_step': n_gemm, 'ms_per_step_in_kernel': gemm_ms,
-                'share_of_step': gemm_ms / (ms_dev / args.steps), 'peak_source': f'{how} bf16_tflops_sustained',
-                'plan_tflop_per_step': eng.gemm_flops / 1e12}
+                'share_of_step': gemm_ms / step_ms, 'peak_source': f'{how} bf16_tflops_sustained',
+                'plan_tflop_per_step': eng.gemm_flops / 1e12,
+                'frac_of_burst_peak': achieved / burst,
+                'step': {'achieved': step_tflops, 'frac': step_tflops / sustained,
+                         'note': 'algorithmic TFLOP of the step / whole step time (every kernel, optimizer included)'},
+                'attention': {'achieved': attn_tf / (attn_ms * 1e-3), 'frac': attn_tf / (attn_ms * 1e-3) / sustained,
+                              'ms_per_step_in_kernel': attn_ms, 'launches_per_step': n_attn, 'tflop_per_step': attn_tf,
+                              'kernel': 'attn_fwd_kernel + attn_bwd_kernel (+ its pre / cast passes) replayed alone'}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -263,9 +346,29 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_cpu = 8 if R <= 32 else 2  # ~10-20 s of host work
-        v, s_per = oracle_cpu_step_rate(R, 2, n_cpu, 1, cores)
+        v, s_per = oracle_cpu_step_rate(R, CPU_SAMPLE_BATCH, n_cpu, 1, cores)
         cpu = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-               'sample': f'{n_cpu} timed steps of batch 2 (of the {B}-image microbatch) after 1 warm-up, fp32 oracle, {s_per:.2f} s/step'}
+               'sample': f'{n_cpu} timed steps of batch {CPU_SAMPLE_BATCH} (of the {B}-image microbatch) after 1 warm-up, fp32 oracle, {s_per:.2f} s/step'}
+    # ---- the yaml's own microbatch (SD-2-base-256.yaml:87 device_train_microbatch_size: 16): same step, N=1 only
+    yaml_mb = None
+    if world == 1 and not args.in_loop and B != 16 and not args.no_secondary:
+        yaml_mb = measure_microbatch(model, opt, 16, R, dev, args.steps, args.warmup, not args.no_graphs)
+    # ---- same-GPU library comparator (eager torch bf16 autocast of the oracle), N=1 only, after our arm is done
+    lib = None
+    if world == 1 and not args.in_loop and not args.no_secondary:
+        del eng
+        model.unet.drop_engines()
+        torch.cuda.empty_cache()
+        lib = {'unit': 'images/s', 'impl': 'oracle restatement of the reference step, torch eager, bf16 autocast, cuDNN / cuBLASLt / '
+                                           'SDPA kernels + torch fused AdamW, same GPU',
+               'torch': torch.__version__}
+        for lb in ((16, 64) if R <= 32 else (4, 16)):
+            try:
+                v, ms = gpu_library_step_rate(R, lb, 5, 2, dev)
+                lib[f'batch_{lb}'] = {'value': v, 'ms_per_step': ms}
+            except Exception as e:  # informational leg: never fail the bench line
+                lib[f'batch_{lb}'] = {'error': f'{type(e).__name__}: {str(e)[:120]}'}
+                torch.cuda.empty_cache()
     imgs = B * world * args.steps
     line = {
         'metric': METRIC, 'value': imgs / (ms_dev * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
@@ -283,6 +386,7 @@ def run_ours(args):
                 'd2h_bytes_per_step': 4},
         'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
         'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'loss': loss_e2e,
+        'yaml_microbatch': yaml_mb, 'gpu_library_baseline': lib,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -302,6 +406,8 @@ def main():
                     help='BASELINE config 5: precomputed_latents=false, VAE encoder + CLIP text encoder run inside the step')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='skip the informational legs (yaml microbatch 16 line, same-GPU torch library baseline)')
     ap.add_argument('--profile-step', action='store_true',
                     help='run one warmed-up step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     args = ap.parse_args()

@@ -14,7 +14,7 @@ _CSRC = os.path.join(_HERE, 'csrc')
 _ROOT = os.path.dirname(_HERE)
 _BUILD = os.path.join(_ROOT, 'build')
 LIB_PATH = os.path.join(_HERE, 'libsd2b200.so')
-SOURCES = ['api.cu', 'gemm_tc.cu', 'attn.cu', 'k1_noise_sched.cu', 'norm.cu', 'pointwise.cu', 'sampler.cu', 'encoders.cu']
+SOURCES = ['api.cu', 'ddp.cu', 'gemm_tc.cu', 'attn.cu', 'k1_noise_sched.cu', 'norm.cu', 'pointwise.cu', 'sampler.cu', 'encoders.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
     '-Wno-deprecated-gpu-targets'
@@ -161,6 +161,12 @@ SIGNATURES = {
     'sd2_softmax_causal_fwd': (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp]),
     'sd2_gelu_fwd': (_i, [_vp, _vp, _vp, _ll, _vp]),
     'sd2_pixel_linear8': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
+    'sd2_ddp_unique_id': (_i, [_vp, _vp]),
+    'sd2_ddp_init': (_i, [_vp, _vp, _i, _i]),
+    'sd2_ddp_world': (_i, [_vp]),
+    'sd2_ddp_allreduce_bucket': (_i, [_vp, _vp, _ll, _i, _i, _vp]),
+    'sd2_ddp_destroy': (_i, [_vp]),
+    'sd2_workspace_bytes': (_ll, [_ll, _ll, _i]),
 }
 
 _lib = None
@@ -210,7 +216,7 @@ class DryLib:
             if name == 'sd2_groupnorm_ws_floats':
                 return a[0] * 64 * a[1] * 2 + a[0] * 128
             if name == 'sd2_attn_bwd_ws_bytes':
-                return a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * a[2] * 4
+                return a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * ((a[2] + 127) // 128) * 256 * 4
             if name == 'sd2_layernorm_ws_floats':
                 return 148 * 4 * a[1] * 2
             if name == 'sd2_last_error':

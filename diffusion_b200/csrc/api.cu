@@ -188,6 +188,7 @@ int sd2_ctx_create(int device, sd2_ctx** out) {
 }
 
 int sd2_ctx_destroy(sd2_ctx* ctx) {
+  if (ctx) sd2_ddp_destroy(ctx);
   delete ctx;
   return 0;
 }

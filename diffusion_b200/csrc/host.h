@@ -18,6 +18,8 @@ struct sd2_ctx {
   int num_sms = 148;
   long long launches = 0;
   std::string err;
+  void* nccl_comm = nullptr;  // ncclComm_t of sd2_ddp_init (ddp.cu), or null
+  int ddp_rank = 0, ddp_world = 0;
 };
 
 namespace sd2 {

@@ -208,6 +208,7 @@ class Engine:
         self.act_bytes = 0
         self.attn_ws = None  # scratch of the fused attention backward (fp32 dQ accumulation), shared by all layers
         self.gemm_flops = 0  # algorithmic 2*M*N*K of every tensor-core GEMM recorded (fwd + bwd)
+        self.attn_flops = 0  # the fused-attention share of it
         self.fwd_is_gemm, self.bwd_is_gemm = [], []
         self.fwd_side, self.bwd_side = [], []
         self.ws_side = shared.ws_side if reuse else torch.empty(64 << 20, dtype=torch.uint8, device=dev)
@@ -510,6 +511,7 @@ class Engine:
         lse = self.buf(B * heads, Nq, dtype=torch.float32)
         self.f(ops.attn_fwd, q, k, v, out.data, lse, B, heads, Nq, Nk, scale)
         self.gemm_flops += 4 * B * heads * Nq * Nk * d
+        self.attn_flops += 4 * B * heads * Nq * Nk * d
         need = self.ctx.lib.sd2_attn_bwd_ws_bytes(B, heads, Nq)
         if self.attn_ws is None or self.attn_ws.numel() < need:
             self.attn_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
@@ -526,6 +528,7 @@ class Engine:
             dv = kvn.grad[:, v_col:v_col + C]
             self.b(ops.attn_bwd, q, k, v, out.data, dO, lse, dq, dk, dv, self.attn_ws, B, heads, Nq, Nk, scale)
             self.gemm_flops += 10 * B * heads * Nq * Nk * d
+            self.attn_flops += 10 * B * heads * Nq * Nk * d
             qn.gw = kvn.gw = True
 
         self._bwd_builders.append(bwd)
@@ -733,11 +736,16 @@ class Engine:
         self.segments = sorted(set(b[2] for b in self.buckets))
 
     def enable_grad_sync(self, group=None):
-        """Average gradients over the data-parallel group, bucket by bucket, overlapped with the rest of backward."""
+        """Average gradients over the data-parallel group, bucket by bucket, overlapped with the rest of backward.
+        On CUDA the all-reduce is the library's own entry point (sd2_ddp_allreduce_bucket: NCCL on the communication stream,
+        communicator created here from a unique id that torch.distributed merely ships between the ranks); on CPU (gloo,
+        host-logic tests) it is torch.distributed's."""
         import torch.distributed as dist
         self.dp_group = group
         self.dp_world = dist.get_world_size(group)
         self.comm_stream = torch.cuda.Stream(self.dev) if self.dev.type == 'cuda' else None
+        if self.comm_stream is not None and not ops.dry_run():
+            ops.ddp_init(self.ctx, group)
         self.sync_grads = True
 
     def no_sync(self):
@@ -766,8 +774,7 @@ class Engine:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.dp_group)
+        ops.ddp_allreduce_bucket(self.ctx, flat, True, self.comm_stream)
 
     # ---------------------------------------------------------------------------------------------- execution
     def run_forward(self):
@@ -867,9 +874,10 @@ class Engine:
         torch.cuda.synchronize(self.dev)
         self.graph_fwd, self.graph_bwd = gf, gbs
 
-    def capture_gemm_only(self):
+    def capture_gemm_only(self, only=None):
         """A CUDA graph holding only the tensor-core GEMM launches of one step (forward + backward), replayed by
-        bench.py to time the dominant kernel family on its own stream with CUDA events (roofline.achieved)."""
+        bench.py to time the dominant kernel family on its own stream with CUDA events (roofline.achieved).
+        only: restrict to ops with these names (e.g. ('attn_fwd', 'attn_bwd'))."""
         torch.cuda.synchronize(self.dev)
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -878,7 +886,7 @@ class Engine:
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s):
                 for op, is_gemm in list(zip(self.fwd, self.fwd_is_gemm)) + list(zip(self.bwd, self.bwd_is_gemm)):
-                    if is_gemm:
+                    if is_gemm and (only is None or op.func.__name__ in only):
                         op()
                         n += 1
         torch.cuda.current_stream(self.dev).wait_stream(s)

@@ -507,3 +507,29 @@ def taps_stride2_vae(B):
     right zero padding is the TMA out-of-bounds fill."""
     m = {0: (0, 0), 1: (1, 0), 2: (0, 1)}
     return [(m[kh][1], m[kw][1], (m[kh][0] * 2 + m[kw][0]) * B, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+
+
+# ---- data parallel (csrc/ddp.cu) ----------------------------------------------------------------------------------
+def ddp_init(ctx, group=None):
+    """Create this context's NCCL communicator over the ranks of `group` (idempotent).  torch.distributed is only the
+    rendezvous: rank 0 of the group draws the unique id, a broadcast ships its 128 bytes."""
+    import ctypes
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if ctx.lib.sd2_ddp_world(ctx.h) == world:
+        return
+    rank = dist.get_rank(group)
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        ctx.check(ctx.lib.sd2_ddp_unique_id(ctx.h, ctypes.cast(buf, ctypes.c_void_p)))
+    box = [bytes(buf.raw)]
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast_object_list(box, src=src, group=group)
+    idbuf = ctypes.create_string_buffer(box[0], 128)
+    ctx.check(ctx.lib.sd2_ddp_init(ctx.h, ctypes.cast(idbuf, ctypes.c_void_p), rank, world))
+
+
+def ddp_allreduce_bucket(ctx, flat, average, stream):
+    """In-place all-reduce of a contiguous gradient range on `stream` (a torch.cuda.Stream)."""
+    dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[flat.dtype]
+    ctx.check(ctx.lib.sd2_ddp_allreduce_bucket(ctx.h, _p(flat), flat.numel(), dt, 1 if average else 0, stream.cuda_stream))

@@ -174,6 +174,10 @@ class UNet2DConditionModel(nn.Module):
             self._arena = ParamArena(self, dev)
         return self._arena
 
+    def drop_engines(self):
+        """Release every cached kernel schedule (activation buffers, CUDA graphs); the parameter arena stays."""
+        self._engines.clear()
+
     def engine(self, B, H, W, ctx_len, forward_only=False):
         """Static kernel schedule for one input geometry (built lazily, cached)."""
         import os

@@ -241,6 +241,24 @@ int sd2_pixel_linear8(sd2_ctx* ctx, const void* in_nhwc8, const float* w, const 
 /* y = gelu(x) (erf form), bf16, n % 8 == 0 */
 int sd2_gelu_fwd(sd2_ctx* ctx, const void* x, void* y, long long n, sd2_stream stream);
 
+/* ---- data parallel: gradient buckets over NCCL -------------------------------------------------------------------
+ * Replaces the DistributedDataParallel bucket all-reduce Composer's Trainer wraps the model in (reference
+ * diffusion/train.py:40).  The batch shards by rows, so this is the only collective of the path.  libnccl is resolved
+ * at run time (the copy torch already loaded, else the system one).  Rendezvous stays with the host framework: rank 0
+ * calls sd2_ddp_unique_id and ships the 128 bytes to the other ranks (torch.distributed broadcast, MPI, a file ...), every
+ * rank then calls sd2_ddp_init.  sd2_ddp_allreduce_bucket reduces `count` elements in place on the caller's stream
+ * (average != 0: mean over ranks, else sum) and returns without synchronising; call it as each bucket of the flat
+ * gradient arena becomes final to overlap it with the rest of backward. */
+int sd2_ddp_unique_id(sd2_ctx* ctx, void* out128);
+int sd2_ddp_init(sd2_ctx* ctx, const void* unique_id128, int rank, int world);
+int sd2_ddp_world(sd2_ctx* ctx);
+int sd2_ddp_allreduce_bucket(sd2_ctx* ctx, void* ptr, long long count, int dtype, int average, sd2_stream stream);
+int sd2_ddp_destroy(sd2_ctx* ctx);
+
+/* Split-K scratch that leaves the GEMM / conv planner unconstrained for an [M, N] output cut into `splits` K ranges
+ * (fp32 partial tiles).  Any smaller workspace (or none) is valid: the planner splits less. */
+long long sd2_workspace_bytes(long long M, long long N, int splits);
+
 #ifdef __cplusplus
 }
 #endif
