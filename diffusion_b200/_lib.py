@@ -124,7 +124,7 @@ SIGNATURES = {
     'sd2_groupnorm_ws_floats': (_ll, [_i, _i]),
     'sd2_groupnorm_fwd': (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'sd2_groupnorm_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _i, _i, _i,
-                               _i, _i, _vp]),
+                               _i, _i, _vp, _vp, _vp, _vp]),
     'sd2_layernorm_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     'sd2_layernorm_ws_floats': (_ll, [_ll, _i]),
     'sd2_layernorm_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
@@ -214,7 +214,7 @@ class DryLib:
                     raise TypeError(f'{name}: argument {i} ({v!r}) is not a {t}') from e
             self.calls[name] = self.calls.get(name, 0) + 1
             if name == 'sd2_groupnorm_ws_floats':
-                return a[0] * 64 * a[1] * 2 + a[0] * 128
+                return a[0] * 64 * a[1] * 3 + a[0] * 128
             if name == 'sd2_attn_bwd_ws_bytes':
                 return a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * ((a[2] + 127) // 128) * 256 * 4
             if name == 'sd2_layernorm_ws_floats':

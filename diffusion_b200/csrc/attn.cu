@@ -34,6 +34,7 @@ struct AttnParams {
   const float* stats;  // backward: [B*heads][query tiles][lse 128 | rowsum(dO * O) 128], see attn_bwd_prep_kernel
   bf16* dq;            // backward, single key tile: dQ is written directly
   long long lddq;
+  float* dq32;         // backward, several key tiles: fp32 dQ accumulator [B*Nq][heads*64]
   bf16* dk;
   long long lddk;
   bf16* dv;
@@ -381,18 +382,20 @@ __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __re
   }
 }
 
-static constexpr int AT_BWD_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 compute (two threads per key row)
+static constexpr int AT_BWD_CWARPS = 16;                       // compute warps: four threads per key row
+static constexpr int AT_BWD_THREADS = 64 + AT_BWD_CWARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..17 compute
 
-// dQ tile of one query block, this warp group's 32 columns.  Several key tiles (DIRECT = false): TMEM -> fp32 staging ->
-// TMA reduce-add into the fp32 accumulator.  A single key tile (cross-attention over 77 tokens, self-attention over
-// <= 128 tokens): the tile is complete, it goes to the bf16 gradient directly (no accumulator, no memset, no cast pass).
+// dQ tile of one query block, this thread's query row x 16 columns.  Several key tiles (DIRECT = false): TMEM -> fp32
+// staging (one [32 rows][16 fp32] box per warp, SWIZZLE_64B) -> TMA reduce-add into the fp32 accumulator: the copy engine
+// sends whole 64-byte row segments to the L2 reduction units.  A single key tile (cross-attention over 77 tokens,
+// self-attention over <= 128 tokens): the tile is complete, it goes to the bf16 gradient directly (no accumulator, no
+// memset, no cast pass).
 template <bool DIRECT>
 __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_stg, const void* my_stg_g, int lane, float scale,
-                                                  uint64_t* dq_empty,
-                                                  const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h, int b,
-                                                  bf16* dq, long long lddq) {
-  uint32_t rq[32];
-  tmem_ld_32x32b_x32(taddr, rq);
+                                                  uint64_t* dq_empty, const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h,
+                                                  int b, bf16* dq, long long lddq) {
+  uint32_t rq[16];
+  tmem_ld_32x32b_x16(taddr, rq);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
@@ -402,7 +405,7 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
     if (row < Nq) {
       bf16* dst = dq + ((long long)b * Nq + row) * lddq + h * 64 + col0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
         uint4 u;
         u.x = pack_bf16x2(__uint_as_float(rq[g * 8 + 0]) * scale, __uint_as_float(rq[g * 8 + 1]) * scale);
         u.y = pack_bf16x2(__uint_as_float(rq[g * 8 + 2]) * scale, __uint_as_float(rq[g * 8 + 3]) * scale);
@@ -417,11 +420,11 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
       bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
     }
     __syncwarp();
-    const uint32_t bufp = my_stg + lane * 128;
+    const uint32_t bufp = my_stg + lane * 64;  // 64 B rows, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-      sts128f(bufp + ((g ^ (lane & 7)) << 4), __uint_as_float(rq[g * 4]) * scale, __uint_as_float(rq[g * 4 + 1]) * scale,
-              __uint_as_float(rq[g * 4 + 2]) * scale, __uint_as_float(rq[g * 4 + 3]) * scale);
+    for (int g = 0; g < 4; ++g)
+      sts128f(bufp + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4), __uint_as_float(rq[g * 4]) * scale,
+              __uint_as_float(rq[g * 4 + 1]) * scale, __uint_as_float(rq[g * 4 + 2]) * scale, __uint_as_float(rq[g * 4 + 3]) * scale);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -442,10 +445,9 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
   uint8_t* sV = sK + AT_TILE;
   uint8_t* sQ = sV + AT_TILE;        // [2]
   uint8_t* sdO = sQ + 2 * AT_TILE;   // [2]
-  uint8_t* sPT = sdO + 2 * AT_TILE;  // P^T  : 2 query chunks x [128 key rows][128 B]
-  uint8_t* sdS = sPT + 2 * AT_TILE;  // dS^T : same layout
-  uint8_t* stg = sdS + 2 * AT_TILE;  // 8 warps x 4 KB fp32 staging for the dQ reduce-add
-  float* sStat = reinterpret_cast<float*>(stg + 8 * 4096);  // [2 stages][lse 128 | D 128]
+  uint8_t* sdS = sdO + 2 * AT_TILE;  // dS^T : [2 buffers] x 2 query chunks x [128 key rows][128 B]
+  uint8_t* stg = sdS + 4 * AT_TILE;  // 16 warps x 2 KB fp32 staging for the dQ reduce-add (DIRECT: unused)
+  float* sStat = reinterpret_cast<float*>(stg + AT_BWD_CWARPS * 2048);  // [2 stages][lse 128 | D 128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 512);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;   // [2]
@@ -455,11 +457,12 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
   uint64_t* dp_full = bars + 7;
   uint64_t* dp_empty = bars + 8;
   uint64_t* pds_full = bars + 9;
-  uint64_t* pds_empty = bars + 10;
+  uint64_t* pt_empty = bars + 10;   // P^T (tensor memory) consumed by dV
   uint64_t* dq_full = bars + 11;
   uint64_t* dq_empty = bars + 12;
   uint64_t* dkv_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* ds_empty = bars + 14;   // [2] dS^T smem buffer consumed by dK and dQ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -480,13 +483,15 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
         mbar_init(&qdo_empty[s], 1);
       }
       mbar_init(s_full, 1);
-      mbar_init(s_empty, 8);
+      mbar_init(s_empty, AT_BWD_CWARPS);
       mbar_init(dp_full, 1);
-      mbar_init(dp_empty, 8);
-      mbar_init(pds_full, 8);
-      mbar_init(pds_empty, 1);
+      mbar_init(dp_empty, AT_BWD_CWARPS);
+      mbar_init(pds_full, AT_BWD_CWARPS);
+      mbar_init(pt_empty, 1);
+      mbar_init(&ds_empty[0], 1);
+      mbar_init(&ds_empty[1], 1);
       mbar_init(dq_full, 1);
-      mbar_init(dq_empty, 8);
+      mbar_init(dq_empty, AT_BWD_CWARPS);
       mbar_init(dkv_full, 1);
       fence_mbar_init();
     }
@@ -498,8 +503,9 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // S^T, dP^T: 128 fp32 columns each; dV, dK, dQ accumulators: 64 each; P^T as bf16 pairs (A operand of dV): 64
   const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
-                 tdQ = tmem_base + 384;
+                 tdQ = tmem_base + 384, tPT = tmem_base + 448;
   pdl_grid_sync();
 
   if (warp == 0) {
@@ -528,11 +534,11 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     // iteration is issued as soon as the compute warps hold S^T(i) in registers (s_empty, early in their iteration), the
     // dP^T one when dP^T(i) has been read (late), so both are complete long before tile i+1 needs them.
     constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : A K-major, B K-major
-    constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major (smem P^T / dS^T), B MN-major
+    constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major (TMEM P^T / smem dS^T), B MN-major
     constexpr uint32_t id_mn = umma_idesc_bf16(128, 64, 1, 1);   // dQ        : A MN-major (dS), B MN-major (K)
     const uint64_t aK = umma_desc_sw128(smem_u32(sK), 16, 1024), aV = umma_desc_sw128(smem_u32(sV), 16, 1024);
     const uint64_t bQ0 = umma_desc_sw128(smem_u32(sQ), 16, 1024), bdO0 = umma_desc_sw128(smem_u32(sdO), 16, 1024);
-    const uint64_t aPT = umma_desc_sw128(smem_u32(sPT), 16, 1024), adS = umma_desc_sw128(smem_u32(sdS), 16, 1024);
+    const uint64_t adS = umma_desc_sw128(smem_u32(sdS), 16, 1024);
     const uint64_t bQ0mn = umma_desc_sw128(smem_u32(sQ), 8192, 1024), bdO0mn = umma_desc_sw128(smem_u32(sdO), 8192, 1024);
     const uint64_t adSmn = umma_desc_sw128(smem_u32(sdS), 16384, 1024);  // M chunks (64 queries) 16 KB apart
     const uint64_t bKmn = umma_desc_sw128(smem_u32(sK), 8192, 1024);
@@ -573,24 +579,28 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
         __syncwarp();
       }
       mbar_wait(pds_full, (uint32_t)(i & 1));
-      if (i > 0) mbar_wait(dq_empty, (uint32_t)((i - 1) & 1));
       tc_fence_after();
+      const uint64_t bQ = bQ0mn + (uint64_t)s * TS, bdO = bdO0mn + (uint64_t)s * TS;
+      const uint64_t dsb = (uint64_t)s * 2 * TS;  // dS^T buffer of this tile
       if (elect_one()) {
-        const uint64_t bQ = bQ0mn + (uint64_t)s * TS, bdO = bdO0mn + (uint64_t)s * TS;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // K = 128 queries: chunk ks>>2 of P^T (16 KB apart), 32 B per K step inside
-          const uint64_t a = aPT + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
-          tc_mma_bf16(tdV, a, bdO + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
-        }
+        for (int ks = 0; ks < 8; ++ks)  // K = 128 queries, 16 per step = 8 TMEM columns of P^T
+          tc_mma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), bdO + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
+        tc_commit(pt_empty);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = adS + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
+        for (int ks = 0; ks < 8; ++ks) {  // dS^T from smem: chunk ks>>2 (16 KB apart), 32 B per K step inside
+          const uint64_t a = adS + dsb + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
           tc_mma_bf16(tdK, a, bQ + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
         }
+      }
+      __syncwarp();
+      if (i > 0) mbar_wait(dq_empty, (uint32_t)((i - 1) & 1));  // dQ_{i-1} has left tensor memory (drained right after pds_full)
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)  // K = 128 keys: 16 key rows (2048 B) per step in both operands
-          tc_mma_bf16(tdQ, adSmn + (uint64_t)ks * 128, bKmn + (uint64_t)ks * 128, id_mn, ks != 0 ? 1u : 0u);
-        tc_commit(pds_empty);
+          tc_mma_bf16(tdQ, adSmn + dsb + (uint64_t)ks * 128, bKmn + (uint64_t)ks * 128, id_mn, ks != 0 ? 1u : 0u);
+        tc_commit(&ds_empty[s]);
         tc_commit(dq_full);
         tc_commit(&qdo_empty[s]);
         if (i == nqt - 1) tc_commit(dkv_full);
@@ -599,111 +609,108 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     }
   } else {
     // ---------------------------------------------------------------- compute warps
-    // Two threads per key row: warp group hh owns query columns hh*64 .. hh*64+63 of S^T / dP^T (= query chunk hh of the
-    // P^T / dS^T operands), output columns hh*32 .. +31 of dQ, dV and dK.
+    // Four threads per key row: thread (r, hq) owns query columns hq*32 .. +31 of S^T / dP^T (16 bf16-pair columns of
+    // P^T, four 16-byte groups of a dS^T row) and output columns hq*16 .. +15 of dQ, dV and dK.  Four warps per SM
+    // sub-partition keep the MUFU / FMA pipes busy across each other's TMEM-load and barrier latencies.
     const int q = warp & 3;
-    const int hh = (warp - 2) >> 2;
+    const int hq = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int key = kt * 128 + r;
     const bool key_ok = key < p.Nk;
     // Padding key rows of the last key tile need no masking: their K rows are zero-filled by TMA, so they add nothing to
     // dQ = dS K, and their dV / dK rows are never stored.
-    const uint8_t* my_stg_g = stg + (size_t)(warp - 2) * 4096;
+    const uint32_t ds_row0 = smem_u32(sdS) + (uint32_t)(hq >> 1) * AT_TILE + r * 128;
+    const int dsg0 = (hq & 1) * 4;  // first 16-byte group of this thread inside the 128-byte dS^T row
+    const uint32_t stat0 = smem_u32(sStat) + hq * 128;  // this thread's 32 queries of the lse block; D block 512 B further
+    const uint8_t* my_stg_g = stg + (size_t)(warp - 2) * 2048;
     const uint32_t my_stg = smem_u32(my_stg_g);
-    const uint32_t pt_row = smem_u32(sPT) + hh * AT_TILE + r * 128;
-    const uint32_t ds_row = smem_u32(sdS) + hh * AT_TILE + r * 128;
-    const uint32_t stat0 = smem_u32(sStat) + hh * 256;  // this group's 64 queries of the lse block; D block is 512 B further
     const float c2 = p.c2;
     for (int i = 0; i < nqt; ++i) {
       const uint32_t stat = stat0 + (uint32_t)(i & 1) * 1024;
+      const uint32_t ds_row = ds_row0 + (uint32_t)(i & 1) * 2 * AT_TILE;
       mbar_wait(&qdo_full[i & 1], (uint32_t)((i >> 1) & 1));  // the statistics block of this query tile has landed
       mbar_wait(s_full, (uint32_t)(i & 1));
       tc_fence_after();
-      // P^T = exp2(S^T c2 - lse): both 32-column chunks are pulled into registers first, which hands the S^T buffer back to
-      // the tensor pipe right away
-      uint32_t rs[64];
-      tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64), rs);
-      tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hh * 64 + 32), rs + 32);
+      uint32_t rs[32];
+      tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hq * 32), rs);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-      uint4 pk_p[8], pk_d[8];
+      if (lane == 0) mbar_arrive(s_empty);  // S^T is in registers: the tensor pipe may overwrite it with tile i+1
+      // P^T = exp2(S^T c2 - lse), kept in fp32 for dS and packed to bf16 pairs for the dV operand
+      uint32_t pk[16];
 #pragma unroll
-      for (int g = 0; g < 16; ++g) {
+      for (int g = 0; g < 8; ++g) {
         const float4 l = lds128f(stat + g * 16);
-        float e0 = ex2(fmaf(__uint_as_float(rs[g * 4 + 0]), c2, -l.x));
-        float e1 = ex2(fmaf(__uint_as_float(rs[g * 4 + 1]), c2, -l.y));
-        float e2 = ex2(fmaf(__uint_as_float(rs[g * 4 + 2]), c2, -l.z));
-        float e3 = ex2(fmaf(__uint_as_float(rs[g * 4 + 3]), c2, -l.w));
+        const float e0 = ex2(fmaf(__uint_as_float(rs[g * 4 + 0]), c2, -l.x));
+        const float e1 = ex2(fmaf(__uint_as_float(rs[g * 4 + 1]), c2, -l.y));
+        const float e2 = ex2(fmaf(__uint_as_float(rs[g * 4 + 2]), c2, -l.z));
+        const float e3 = ex2(fmaf(__uint_as_float(rs[g * 4 + 3]), c2, -l.w));
         rs[g * 4 + 0] = __float_as_uint(e0); rs[g * 4 + 1] = __float_as_uint(e1);
         rs[g * 4 + 2] = __float_as_uint(e2); rs[g * 4 + 3] = __float_as_uint(e3);
-        const uint32_t lo = pack_bf16x2(e0, e1), hi = pack_bf16x2(e2, e3);
-        if (g & 1) { pk_p[g >> 1].z = lo; pk_p[g >> 1].w = hi; } else { pk_p[g >> 1].x = lo; pk_p[g >> 1].y = hi; }
+        pk[g * 2] = pack_bf16x2(e0, e1);
+        pk[g * 2 + 1] = pack_bf16x2(e2, e3);
       }
+      mbar_wait(pt_empty, (uint32_t)(i & 1) ^ 1u);  // P^T of the previous tile consumed by its dV MMAs (first in their order)
+      tc_fence_after();
+      tmem_st_32x32b_x16(tPT + lane_off + (uint32_t)(hq * 16), pk);
       // dS^T = P^T (dP^T - D)   (the 1/sqrt(d) factor is applied when dQ / dK are drained)
       mbar_wait(dp_full, (uint32_t)(i & 1));
       tc_fence_after();
+      uint32_t rd[32];
+      tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(hq * 32), rd);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_empty);
+      mbar_wait(&ds_empty[i & 1], (uint32_t)((i >> 1) & 1) ^ 1u);  // this dS^T buffer was read by the MMAs of tile i-2
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rd[32];
-        tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(hh * 64 + c * 32), rd);
-        tmem_wait_ld();
-        if (c == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dp_empty);
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 d = lds128f(stat + 512 + (c * 8 + g) * 16);
-          const int e = c * 32 + g * 4;
-          const float v0 = __uint_as_float(rs[e + 0]) * (__uint_as_float(rd[g * 4 + 0]) - d.x);
-          const float v1 = __uint_as_float(rs[e + 1]) * (__uint_as_float(rd[g * 4 + 1]) - d.y);
-          const float v2 = __uint_as_float(rs[e + 2]) * (__uint_as_float(rd[g * 4 + 2]) - d.z);
-          const float v3 = __uint_as_float(rs[e + 3]) * (__uint_as_float(rd[g * 4 + 3]) - d.w);
-          const uint32_t lo = pack_bf16x2(v0, v1), hi = pack_bf16x2(v2, v3);
-          const int gi = c * 4 + (g >> 1);
-          if (g & 1) { pk_d[gi].z = lo; pk_d[gi].w = hi; } else { pk_d[gi].x = lo; pk_d[gi].y = hi; }
-        }
+      for (int g = 0; g < 4; ++g) {
+        const float4 d0 = lds128f(stat + 512 + g * 32), d1 = lds128f(stat + 512 + g * 32 + 16);
+        const int e = g * 8;
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(rs[e + 0]) * (__uint_as_float(rd[e + 0]) - d0.x),
+                          __uint_as_float(rs[e + 1]) * (__uint_as_float(rd[e + 1]) - d0.y));
+        u.y = pack_bf16x2(__uint_as_float(rs[e + 2]) * (__uint_as_float(rd[e + 2]) - d0.z),
+                          __uint_as_float(rs[e + 3]) * (__uint_as_float(rd[e + 3]) - d0.w));
+        u.z = pack_bf16x2(__uint_as_float(rs[e + 4]) * (__uint_as_float(rd[e + 4]) - d1.x),
+                          __uint_as_float(rs[e + 5]) * (__uint_as_float(rd[e + 5]) - d1.y));
+        u.w = pack_bf16x2(__uint_as_float(rs[e + 6]) * (__uint_as_float(rd[e + 6]) - d1.z),
+                          __uint_as_float(rs[e + 7]) * (__uint_as_float(rd[e + 7]) - d1.w));
+        sts128(ds_row + (uint32_t)(((dsg0 + g) ^ (r & 7)) << 4), u);
       }
-      if (i > 0) {  // dQ_{i-1} (rows = queries): drained now, after its MMAs had a whole tile of math to complete
-        mbar_wait(dq_full, (uint32_t)((i - 1) & 1));
-        tc_fence_after();
-        attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hh * 32,
-                                  (i - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
-      }
-      mbar_wait(pds_empty, (uint32_t)(i & 1) ^ 1u);  // P^T / dS^T smem consumed by the previous tile's MMAs
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint32_t off = (uint32_t)((g ^ (r & 7)) << 4);
-        sts128(pt_row + off, pk_p[g]);
-        sts128(ds_row + off, pk_d[g]);
-      }
+      tmem_wait_st();
+      tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (i > 0) {  // dQ_{i-1} (rows = queries): its MMAs were issued a whole tile of math ago
+        mbar_wait(dq_full, (uint32_t)((i - 1) & 1));
+        tc_fence_after();
+        attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
+                                  (i - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
+      }
     }
     {  // last tile's dQ
       mbar_wait(dq_full, (uint32_t)((nqt - 1) & 1));
       tc_fence_after();
-      attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hh * 32), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hh * 32,
+      attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
                                 (nqt - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
     }
-    // dV, dK of this key tile (this group's 32 columns of each)
+    // dV, dK of this key tile (this thread's 16 columns of each)
     mbar_wait(dkv_full, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
-      bf16* dst = (t == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (t == 0 ? p.lddv : p.lddk) + h * 64 + hh * 32;
+      bf16* dst = (t == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (t == 0 ? p.lddv : p.lddk) + h * 64 + hq * 16;
       const float mul = t == 0 ? 1.f : p.scale;
-      uint32_t rr[32];
-      tmem_ld_32x32b_x32((t == 0 ? tdV : tdK) + lane_off + (uint32_t)(hh * 32), rr);
+      uint32_t rr[16];
+      tmem_ld_32x32b_x16((t == 0 ? tdV : tdK) + lane_off + (uint32_t)(hq * 16), rr);
       tmem_wait_ld();
       if (key_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint4 u;
           u.x = pack_bf16x2(__uint_as_float(rr[g * 8 + 0]) * mul, __uint_as_float(rr[g * 8 + 1]) * mul);
           u.y = pack_bf16x2(__uint_as_float(rr[g * 8 + 2]) * mul, __uint_as_float(rr[g * 8 + 3]) * mul);
@@ -801,7 +808,8 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   if (!head_tmap(&tmQ, q, ldq, Nq, heads, B, &err) || !head_tmap(&tmK, k, ldk, Nk, heads, B, &err) ||
       !head_tmap(&tmV, v, ldv, Nk, heads, B, &err) || !head_tmap(&tmdO, d_o, lddo, Nq, heads, B, &err))
     return fail(ctx, "sd2_attn_bwd: " + err);
-  if (!out_tmap(&tmDQ, dq32, true, 32, 64, Nq, C, heads, B, 64, (long long)Nq * C, &err))
+  // fp32 dQ accumulator as [B][heads][Nq][64]-strided view, box = 32 rows x 16 columns (64-byte rows, SWIZZLE_64B)
+  if (!out_tmap(&tmDQ, dq32, true, 16, 64, Nq, C, heads, B, 64, (long long)Nq * C, &err))
     return fail(ctx, "sd2_attn_bwd dq map: " + err);
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -811,6 +819,7 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.stats = stats;
   p.dq = reinterpret_cast<bf16*>(dq);
   p.lddq = lddq;
+  p.dq32 = dq32;
   p.dk = reinterpret_cast<bf16*>(dk);
   p.lddk = lddk;
   p.dv = reinterpret_cast<bf16*>(dv);
@@ -823,7 +832,7 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
     e = cudaMemsetAsync(dq32, 0, (size_t)B * Nq * C * 4, stream);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
   }
-  const size_t smem = 10 * AT_TILE + 8 * 4096 + 512 * 4 + 15 * 8 + 16 + 1024;
+  const size_t smem = 10 * AT_TILE + AT_BWD_CWARPS * 2048 + 512 * 4 + 17 * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
     e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

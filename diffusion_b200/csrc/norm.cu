@@ -248,15 +248,17 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restr
   }
 }
 
-// grid (P, B): dx = rstd * (gamma*dyh - (db_g + xhat*ds_g)/n) (+ dx_add)
+// grid (P, B): dx = rstd * (gamma*dyh - (db_g + xhat*ds_g)/n) (+ dx_add); cs_ws != null: per-block column sums of dx
+// -> cs_ws[b*P+p][C] (dynamic shared memory [R][C] floats then)
 __global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
                                                                   const bf16* __restrict__ x, long long ldx,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ stats, const float* __restrict__ gstat,
                                                                   const bf16* __restrict__ dx_add, long long ldadd,
-                                                                  bf16* __restrict__ dx, long long lddx, int HW, int C, int G,
-                                                                  int silu) {
+                                                                  bf16* __restrict__ dx, long long lddx,
+                                                                  float* __restrict__ cs_ws, int HW, int C, int G, int silu) {
   pdl_grid_sync();
+  extern __shared__ float cs_sm[];  // [R][C] (only with cs_ws)
   __shared__ float s_ds[64], s_db[64];
   const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
   const int cpg = C / G;
@@ -267,40 +269,97 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_apply_kernel(const bf16*
   __syncthreads();
   const int V = C / 8, R = GN_THREADS / V;
   const int v = threadIdx.x % V, r = threadIdx.x / V;
-  if (r >= R) return;
-  const float inv_n = 1.f / ((float)cpg * (float)HW);
-  float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
+  float cs[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = v * 8 + e, g = c / cpg;
-    mean[e] = stats[((long long)b * G + g) * 2];
-    rstd[e] = stats[((long long)b * G + g) * 2 + 1];
-    ga[e] = gamma[c];
-    be[e] = beta[c];
-    k1[e] = s_db[g] * inv_n;
-    k2[e] = s_ds[g] * inv_n;
-  }
-  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
-  const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
-  const bf16* db = dy + ((long long)b * HW) * lddy + v * 8;
-  bf16* ob = dx + ((long long)b * HW) * lddx + v * 8;
-  const bf16* ab = dx_add ? dx_add + ((long long)b * HW) * ldadd + v * 8 : nullptr;
-#pragma unroll 4
-  for (int row = row0 + r; row < row1; row += R) {
-    float f[8], d[8], a[8];
-    load8(xb + (long long)row * ldx, f);
-    load8(db + (long long)row * lddy, d);
-    if (ab) load8(ab + (long long)row * ldadd, a);
+  for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+  if (r < R) {
+    const float inv_n = 1.f / ((float)cpg * (float)HW);
+    float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float xh = (f[e] - mean[e]) * rstd[e];
-      float dyh = d[e];
-      if (silu) dyh *= silu_grad(xh * ga[e] + be[e]);
-      float o = rstd[e] * (ga[e] * dyh - k1[e] - xh * k2[e]);
-      if (ab) o += a[e];
-      f[e] = o;
+      const int c = v * 8 + e, g = c / cpg;
+      mean[e] = stats[((long long)b * G + g) * 2];
+      rstd[e] = stats[((long long)b * G + g) * 2 + 1];
+      ga[e] = gamma[c];
+      be[e] = beta[c];
+      k1[e] = s_db[g] * inv_n;
+      k2[e] = s_ds[g] * inv_n;
     }
-    store8(ob + (long long)row * lddx, f);
+    const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+    const bf16* xb = x + ((long long)b * HW) * ldx + v * 8;
+    const bf16* db = dy + ((long long)b * HW) * lddy + v * 8;
+    bf16* ob = dx + ((long long)b * HW) * lddx + v * 8;
+    const bf16* ab = dx_add ? dx_add + ((long long)b * HW) * ldadd + v * 8 : nullptr;
+#pragma unroll 4
+    for (int row = row0 + r; row < row1; row += R) {
+      float f[8], d[8], a[8];
+      load8(xb + (long long)row * ldx, f);
+      load8(db + (long long)row * lddy, d);
+      if (ab) load8(ab + (long long)row * ldadd, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (f[e] - mean[e]) * rstd[e];
+        float dyh = d[e];
+        if (silu) dyh *= silu_grad(xh * ga[e] + be[e]);
+        float o = rstd[e] * (ga[e] * dyh - k1[e] - xh * k2[e]);
+        if (ab) o += a[e];
+        f[e] = o;
+        cs[e] += o;
+      }
+      store8(ob + (long long)row * lddx, f);
+    }
+  }
+  if (cs_ws != nullptr) {
+    if (r < R) {
+      float* o = cs_sm + (size_t)r * C + v * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+    }
+    __syncthreads();
+    float* wo = cs_ws + ((long long)b * P + p) * C;
+    for (int i = threadIdx.x; i < C; i += GN_THREADS) {
+      float t = 0.f;
+      for (int rr = 0; rr < R; ++rr) t += cs_sm[(size_t)rr * C + i];
+      wo[i] = t;
+    }
+  }
+}
+
+// Column sums emitted by the GroupNorm backward -> their consumers.  cs_ws[b*NP + i][C] (NP partial slabs per image):
+//   rowsum[b][c]  = sum_i cs_ws[b*NP+i][c]                 (overwritten; per-image sums = gradient of a per-image bias)
+//   dcs1/dcs2[c] += sum_b rowsum[b][c]                     (bias gradients)
+// grid (ceil(C/32), slices over images), block (32 channels, 8 image lanes).
+__global__ void __launch_bounds__(256) gn_colsum_finalize_kernel(const float* __restrict__ cs_ws, int B, int NP, int C,
+                                                                 float* __restrict__ rowsum, float* __restrict__ dcs1,
+                                                                 float* __restrict__ dcs2) {
+  pdl_grid_sync();
+  __shared__ float sm[8][32];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float tot = 0.f;
+  if (c < C) {
+    for (int b = blockIdx.y * 8 + pl; b < B; b += 8 * gridDim.y) {
+      const float* src = cs_ws + ((long long)b * NP) * C + c;
+      float t = 0.f;
+      int i = 0;
+      for (; i + 3 < NP; i += 4) {
+        const float t0 = src[(long long)i * C], t1 = src[(long long)(i + 1) * C], t2 = src[(long long)(i + 2) * C],
+                    t3 = src[(long long)(i + 3) * C];
+        t += (t0 + t1) + (t2 + t3);
+      }
+      for (; i < NP; ++i) t += src[(long long)i * C];
+      if (rowsum != nullptr) rowsum[(long long)b * C + c] = t;
+      tot += t;
+    }
+  }
+  sm[pl][cl] = tot;
+  __syncthreads();
+  if (pl == 0 && c < C && (dcs1 != nullptr || dcs2 != nullptr)) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][cl];
+    if (dcs1 != nullptr) atomicAdd(&dcs1[c], t);
+    if (dcs2 != nullptr) atomicAdd(&dcs2[c], t);
   }
 }
 
@@ -401,8 +460,11 @@ template <bool SILU, bool HAS_ADD>
 __global__ void __launch_bounds__(512, 1) gn_bwd_cluster_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ stats, const bf16* __restrict__ dx_add,
-                                                                 bf16* __restrict__ dx, float* __restrict__ ws, int HW, int C,
-                                                                 int G, int PX, int RL) {
+                                                                 bf16* __restrict__ dx, float* __restrict__ ws,
+                                                                 float* __restrict__ cs_ws, int HW, int C, int G, int PX,
+                                                                 int RL) {
+  // cs_ws != null: also emit this CTA's per-channel column sums of the dx it writes (cs_ws[b*NC+rank][C]) - the bias
+  // gradient of the conv / linear that produced x, and per image the gradient of its time-embedding projection
   extern __shared__ __align__(128) uint8_t gsm[];
   const int NC = gridDim.x, rank = blockIdx.x, b = blockIdx.y;  // cluster = the NC blocks of one image
   const int V = C / 8, cpg = C / G;
@@ -519,6 +581,8 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_cluster_kernel(const bf16* __re
     }
     const bf16* ab = HAS_ADD ? dx_add + pix0 * C + v * 8 : nullptr;
     bf16* ob = dx + pix0 * C + v * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = 0.f;
 #pragma unroll 4
     for (int r = rl; r < PX; r += RL) {
       float xf[8], df[8], o[8];
@@ -531,8 +595,23 @@ __global__ void __launch_bounds__(512, 1) gn_bwd_cluster_kernel(const bf16* __re
         float t = fmaf(df[e], a[e], k1[e]);
         t = fmaf(xh, k2[e], t);
         o[e] = HAS_ADD ? o[e] + t : t;
+        s1[e] += o[e];
       }
       store8(ob + (size_t)r * C, o);
+    }
+  }
+  if (cs_ws != nullptr) {  // column sums of this CTA's dx rows: row lanes -> red[RL][C] -> cs_ws slab
+    if (act) {
+      float* o = red + (size_t)rl * C + v * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+    }
+    __syncthreads();
+    float* wo = cs_ws + ((long long)b * NC + rank) * C;
+    for (int i = tid; i < C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < RL; ++r) t += red[(size_t)r * C + i];
+      wo[i] = t;
     }
   }
   cluster_wait();  // no CTA of the cluster exits while a peer may still read its gpart
@@ -677,7 +756,7 @@ static cudaError_t launch_cluster(void (*kern)(P...), dim3 grid, dim3 block, siz
 template <bool SILU, bool HAS_ADD>
 static cudaError_t launch_gn_bwd_cluster(const GnClusterCfg& c, int B, cudaStream_t stream, const bf16* dy, const bf16* x,
                                          const float* gamma, const float* beta, const float* stats, const bf16* dx_add,
-                                         bf16* dx, float* ws, int HW, int C, int G) {
+                                         bf16* dx, float* ws, float* cs_ws, int HW, int C, int G) {
   auto kern = gn_bwd_cluster_kernel<SILU, HAS_ADD>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -688,7 +767,7 @@ static cudaError_t launch_gn_bwd_cluster(const GnClusterCfg& c, int B, cudaStrea
     attr_set = true;
   }
   return launch_cluster(kern, dim3(c.NC, B), dim3(c.threads), c.smem_bytes, c.NC, stream, dy, x, gamma, beta, stats, dx_add, dx,
-                        ws, HW, C, G, c.PX, c.RL);
+                        ws, cs_ws, HW, C, G, c.PX, c.RL);
 }
 
 // dgamma[c] += sum_i ws[i][c][1], dbeta[c] += sum_i ws[i][c][0] over `n_part` partial slabs.
@@ -1044,7 +1123,8 @@ using namespace sd2;
 
 extern "C" {
 
-long long sd2_groupnorm_ws_floats(int B, int C) { return (long long)B * GN_MAXP * C * 2 + (long long)B * 64 * 2; }
+// [B][GN_MAXP][C][2] channel partials | [B][64][2] group sums | [B][GN_MAXP][C] column-sum partials (bias gradients)
+long long sd2_groupnorm_ws_floats(int B, int C) { return (long long)B * GN_MAXP * C * 3 + (long long)B * 64 * 2; }
 
 int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* gamma, const float* beta, void* y,
                       long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
@@ -1086,10 +1166,13 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
 int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
                       const float* beta, const float* stats, const void* dx_add, long long ldadd, void* dx,
                       long long lddx, float* dgamma, float* dbeta, float* ws, int B, int HW, int C, int G, int silu,
-                      sd2_stream stream_) {
+                      float* drowsum, float* dcolsum1, float* dcolsum2, sd2_stream stream_) {
   if (!ctx) return 1;
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_bwd: unsupported C/G");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bool emit = drowsum != nullptr || dcolsum1 != nullptr || dcolsum2 != nullptr;
+  float* cs_ws = emit ? ws + (long long)B * GN_MAXP * C * 2 + (long long)B * 64 * 2 : nullptr;
+  const dim3 fin_grid((C + 31) / 32, B >= 64 ? 8 : (B >= 8 ? 2 : 1));
   if (ldx == C && lddy == C && lddx == C && (dx_add == nullptr || ldadd == C)) {
     const GnClusterCfg cc = gn_cluster_cfg(HW, C, 2);
     if (cc.ok) {  // single-pass cluster kernel + the dgamma/dbeta reduction over the B * NC per-CTA slabs
@@ -1098,13 +1181,15 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
       const bf16* ap = reinterpret_cast<const bf16*>(dx_add);
       bf16* dxp = reinterpret_cast<bf16*>(dx);
       cudaError_t e;
-      if (silu && ap) e = launch_gn_bwd_cluster<true, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
-      else if (silu) e = launch_gn_bwd_cluster<true, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
-      else if (ap) e = launch_gn_bwd_cluster<false, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
-      else e = launch_gn_bwd_cluster<false, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, HW, C, G);
+      if (silu && ap) e = launch_gn_bwd_cluster<true, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, cs_ws, HW, C, G);
+      else if (silu) e = launch_gn_bwd_cluster<true, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, cs_ws, HW, C, G);
+      else if (ap) e = launch_gn_bwd_cluster<false, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, cs_ws, HW, C, G);
+      else e = launch_gn_bwd_cluster<false, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, cs_ws, HW, C, G);
       if (e != cudaSuccess) return fail(ctx, std::string("sd2_groupnorm_bwd (cluster): ") + cudaGetErrorString(e));
       launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(B * cc.NC)), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta, nullptr, nullptr);
-      return check_launch(ctx, "groupnorm_bwd", 2);
+      if (emit)
+        launch_k(gn_colsum_finalize_kernel, fin_grid, dim3(256), 0, stream, (const float*)cs_ws, B, cc.NC, C, drowsum, dcolsum1, dcolsum2);
+      return check_launch(ctx, "groupnorm_bwd", emit ? 3 : 2);
     }
   }
   const int P = gn_chunks(HW, B, C, ctx->num_sms);
@@ -1123,11 +1208,22 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
     }
   }
   launch_k(gn_bwd_reduce_kernel, dim3(G), dim3(256), t_smem, stream, ws, gamma, gstat, dgamma, dbeta, B, P, C, G);
-  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(dy), lddy,
+  const size_t cs_smem = emit ? (size_t)(GN_THREADS / (C / 8)) * C * sizeof(float) : 0;
+  if (cs_smem > 48 * 1024) {
+    static bool opted_apply = false;
+    if (!opted_apply) {
+      if (cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024) != cudaSuccess)
+        return fail(ctx, "sd2_groupnorm_bwd: cannot raise the shared-memory limit of the apply pass");
+      opted_apply = true;
+    }
+  }
+  launch_k(gn_bwd_apply_kernel, dim3(grid), dim3(GN_THREADS), cs_smem, stream, reinterpret_cast<const bf16*>(dy), lddy,
                                                        reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, gstat,
                                                        reinterpret_cast<const bf16*>(dx_add), ldadd,
-                                                       reinterpret_cast<bf16*>(dx), lddx, HW, C, G, silu);
-  return check_launch(ctx, "groupnorm_bwd", 3);
+                                                       reinterpret_cast<bf16*>(dx), lddx, cs_ws, HW, C, G, silu);
+  if (emit)
+    launch_k(gn_colsum_finalize_kernel, fin_grid, dim3(256), 0, stream, (const float*)cs_ws, B, P, C, drowsum, dcolsum1, dcolsum2);
+  return check_launch(ctx, "groupnorm_bwd", emit ? 4 : 3);
 }
 
 int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, float* stats,

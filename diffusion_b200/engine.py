@@ -34,7 +34,7 @@ _OP_WRITES = {
     'linear_fwd': ((2,), ('workspace',)), 'linear_dgrad': ((2,), ('workspace',)), 'linear_wgrad': ((2,), ()),
     'conv3x3_fwd': ((5,), ('workspace',)), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
     'attn_fwd': ((3, 4), ()), 'attn_bwd': ((6, 7, 8, 9), ()),
-    'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ()),
+    'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ('drowsum', 'dcolsum', 'dcolsum2')),
     'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ('dcolsum',)),
     'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ('dbias',)), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
     'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
@@ -77,12 +77,20 @@ def _overlap(xs, ys):
 
 class Node:
     """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
-    __slots__ = ('data', 'grad', 'gw', 'M', 'C', 'writes', 'last_writer', 'writes_at_norm')
+    __slots__ = ('data', 'grad', 'gw', 'M', 'C', 'writes', 'last_writer', 'writes_at_norm', 'reads', 'bias_names', 'rowsum',
+                 'claimed')
 
     def __init__(self, data):
         self.data, self.grad, self.gw = data, None, False
         self.M, self.C = data.shape
         self.writes, self.last_writer, self.writes_at_norm = 0, None, -1  # gradient-write bookkeeping (bias grads from norms)
+        # Bias gradients taken from the GroupNorm backward (no separate column-sum pass over the output gradient):
+        #   reads      - forward ops recorded so far that consume this node,
+        #   bias_names - parameters whose gradient is the column sum of this node's TOTAL gradient (set by the producer),
+        #   rowsum     - [B, C] fp32 buffer that wants the per-image sums (time-embedding projection of a ResNet conv1),
+        #   claimed    - a GroupNorm is the node's FIRST forward consumer, hence the last writer of its gradient: its
+        #                backward kernel emits those sums and the producer skips its own pass.
+        self.reads, self.bias_names, self.rowsum, self.claimed = 0, [], None, False
 
 
 def _align(n, a=64):
@@ -199,6 +207,7 @@ class Engine:
         self.B, self.H, self.W, self.L = B, H, W, L
         self.fwd, self.bwd, self._bwd_builders = [], [], []
         self._touched, self.grad_ready = set(), {}
+        self._norm_emitted = set()  # bias parameters whose gradient a GroupNorm backward produced
         reuse = shared is not None and getattr(shared, 'ws', None) is not None
         self.ws = shared.ws if reuse else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         self.G = self.cfg['norm_num_groups']
@@ -336,6 +345,9 @@ class Engine:
         N = w.shape[0]
         out = self.node(x.M, N)
         bias = self.p32(bname) if bname else None
+        self._use(x, residual)
+        if bname and not bias_grad_elsewhere:
+            out.bias_names = [bname]
         self.f(ops.linear_fwd, x.data, w, out.data, bias=bias, residual=residual.data if residual else None,
                workspace=self.ws_side if side else self.ws, side=side)
 
@@ -350,7 +362,17 @@ class Engine:
             self._touched.update(gnames or (wname,))
             self.b(ops.linear_wgrad, g, x.data, gwv)
             if bname and not bias_grad_elsewhere:
-                self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
+                if self._bias_from_norm(out, bname):
+                    self._touched.add(bname)
+                else:
+                    self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
+            elif bname and bias_grad_elsewhere == 'deferred':
+                # conv_shortcut: its output is only the residual of conv2, so its output gradient IS conv2's; when a GroupNorm
+                # emitted conv2's bias gradient it emitted this one with it (Node.bias_names of conv2's output)
+                if bname in getattr(self, '_norm_emitted', ()):
+                    self._touched.add(bname)
+                else:
+                    self.b(ops.colsum, g, self.g32(bname), 1, x.M, True)
             elif bname and bias_grad_elsewhere == 'norm':
                 # the norm that emitted the column sums must have been the LAST op to write this node's gradient
                 assert getattr(out, 'last_writer', None) is not None and out.writes == out.writes_at_norm, \
@@ -361,6 +383,7 @@ class Engine:
 
     def silu(self, x):
         out = self.node(x.M, x.C)
+        self._use(x)
         self.f(ops.silu_fwd, x.data, out.data)
 
         def bwd():
@@ -371,17 +394,47 @@ class Engine:
         self._bwd_builders.append(bwd)
         return out
 
+    def _use(self, *nodes):
+        for n in nodes:
+            if n is not None:
+                n.reads += 1
+
+    def _bias_from_norm(self, out, bname):
+        """True if a GroupNorm backward already produced the gradient of `bname` (it claimed the node at forward time);
+        checks that the norm really was the last writer of the node's gradient."""
+        if not out.claimed or bname not in out.bias_names:
+            return False
+        assert out.last_writer is not None and out.writes == out.writes_at_norm, \
+            f'{bname}: bias gradient was taken from a GroupNorm backward that is not the last writer of the node'
+        return True
+
     def groupnorm(self, x, prefix, eps, silu, HW):
         y = self.node(x.M, x.C)
         stats = self.buf(self.B, self.G, 2, dtype=torch.float32)
         gamma, beta = self.p32(prefix + '.weight'), self.p32(prefix + '.bias')
+        # first forward consumer of a conv / linear output = last writer of its gradient: this norm's backward emits the
+        # producer's bias gradient(s) (and the per-image sums a ResNet conv1 needs) as column sums of the dx it writes
+        if x.reads == 0 and (x.bias_names or x.rowsum is not None) and len(x.bias_names) <= 2 and not self.forward_only:
+            x.claimed = True
+        self._use(x)
         self.f(ops.groupnorm_fwd, x.data, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
 
         def bwd():
             assert y.gw
             gx, acc = self._gout(x)
+            extra = {}
+            if x.claimed:
+                names = list(x.bias_names)
+                if x.rowsum is not None:
+                    extra['drowsum'] = x.rowsum
+                if len(names) > 0:
+                    extra['dcolsum'] = self.arena.storage(self.arena.g32, names[0])
+                if len(names) > 1:
+                    extra['dcolsum2'] = self.arena.storage(self.arena.g32, names[1])
+                self._norm_emitted.update(names)
             self.b(ops.groupnorm_bwd, y.grad, x.data, gamma, beta, stats, gx, self.g32(prefix + '.weight'),
-                   self.g32(prefix + '.bias'), self.gn_ws, self.B, HW, self.G, silu, dx_add=gx if acc else None)
+                   self.g32(prefix + '.bias'), self.gn_ws, self.B, HW, self.G, silu, dx_add=gx if acc else None, **extra)
+            x.last_writer, x.writes_at_norm = prefix, x.writes
 
         self._bwd_builders.append(bwd)
         return y
@@ -393,6 +446,7 @@ class Engine:
         y = self.node(x.M, x.C)
         stats = self.buf(x.M, 2, dtype=torch.float32)
         gamma, beta = self.p32(prefix + '.weight'), self.p32(prefix + '.bias')
+        self._use(x)
         self.f(ops.layernorm_fwd, x.data, gamma, beta, y.data, stats)
 
         def bwd():
@@ -406,25 +460,35 @@ class Engine:
         self._bwd_builders.append(bwd)
         return y
 
-    def conv3(self, x, Hc, Wc, prefix, rowbias=None, residual=None, rowbias_bwd=None):
-        """3x3 stride-1 conv (+bias +per-image bias +residual).  rowbias_bwd(g) is called with the output gradient."""
+    def conv3(self, x, Hc, Wc, prefix, rowbias=None, residual=None, rowbias_bwd=None, rowsum=None, extra_bias=()):
+        """3x3 stride-1 conv (+bias +per-image bias +residual).  rowbias_bwd(g, have_rowsum) is called with the output
+        gradient; rowsum = [B, Cout] fp32 buffer for the per-image sums of that gradient (filled by the GroupNorm backward
+        behind this conv when it can, have_rowsum tells); extra_bias: further parameters whose gradient is the column sum
+        of this conv's output gradient (the bias of the conv_shortcut that feeds its residual)."""
         w, bias = self.w16(prefix + '.weight'), self.p32(prefix + '.bias')
         out = self.node(x.M, w.shape[1])
+        out.bias_names = [prefix + '.bias'] + list(extra_bias)
+        out.rowsum = rowsum
         B = self.B
+        self._use(x, residual)
         self.f(ops.conv3x3_fwd, x.data, B, Hc, Wc, w, out.data, bias=bias, rowbias=rowbias,
                residual=residual.data if residual else None, workspace=self.ws)
 
         def bwd():
             g = out.grad
             assert out.gw
+            from_norm = self._bias_from_norm(out, prefix + '.bias')
             if residual is not None:
                 self._pass(g, residual)
             if rowbias_bwd is not None:
-                rowbias_bwd(g)
+                rowbias_bwd(g, from_norm)
             gx, acc = self._gout(x)
             self.b(ops.conv3x3_dgrad, g, B, Hc, Wc, w, gx, residual=gx if acc else None, workspace=self.ws)
             self.b(ops.conv3x3_wgrad, g, x.data, B, Hc, Wc, self.g32(prefix + '.weight'))
-            self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, x.M, True)
+            if from_norm:
+                self._touched.add(prefix + '.bias')
+            else:
+                self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, x.M, True)
 
         self._bwd_builders.append(bwd)
         return out
@@ -436,7 +500,9 @@ class Engine:
         w, bias = self.w16(prefix + '.weight'), self.p32(prefix + '.bias')
         planes = self.buf(4 * Mo, C)
         out = self.node(Mo, C)
+        out.bias_names = [prefix + '.bias']
         taps = ops.taps_stride2(B)
+        self._use(x)
         self.f(ops.phase_split, x.data, planes, B, Hc, Wc)
         self.f(ops.conv3x3_fwd, planes, B, Ho, Wo, w, out.data, bias=bias, taps=taps, n_planes=4 * B, workspace=self.ws)
 
@@ -454,13 +520,17 @@ class Engine:
             else:
                 self.b(ops.phase_merge, dplanes, gx, B, Hc, Wc)
             self.b(ops.conv3x3_wgrad, g, planes, B, Ho, Wo, self.g32(prefix + '.weight'), taps=taps, n_planes=4 * B)
-            self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, Mo, True)
+            if self._bias_from_norm(out, prefix + '.bias'):
+                self._touched.add(prefix + '.bias')
+            else:
+                self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, Mo, True)
 
         self._bwd_builders.append(bwd)
         return out
 
     def upsample(self, x, Hc, Wc, prefix):
         up = self.node(4 * x.M, x.C)
+        self._use(x)
         self.f(ops.upsample2x_fwd, x.data, up.data, self.B, Hc, Wc)
 
         def bwd():
@@ -474,6 +544,7 @@ class Engine:
 
     def concat(self, a, b_):
         out = self.node(a.M, a.C + b_.C)
+        self._use(a, b_)
         self.f(ops.copy2d, a.data, out.data[:, :a.C], a.M, a.C)
         self.f(ops.copy2d, b_.data, out.data[:, a.C:], a.M, b_.C)
 
@@ -491,6 +562,7 @@ class Engine:
         """bias_name: bias of the projection that produced h; its gradient (the column sums of dh) is then accumulated by
         the GEGLU backward kernel itself and that linear skips its own column-sum pass."""
         y = self.node(h.M, h.C // 2)
+        self._use(h)
         self.f(ops.geglu_fwd, h.data, y.data)
 
         def bwd():
@@ -509,6 +581,7 @@ class Engine:
         scale = float(d)**-0.5
         out = self.node(B * Nq, C)
         lse = self.buf(B * heads, Nq, dtype=torch.float32)
+        self._use(qn, kvn)
         self.f(ops.attn_fwd, q, k, v, out.data, lse, B, heads, Nq, Nk, scale)
         self.gemm_flops += 4 * B * heads * Nq * Nk * d
         self.attn_flops += 4 * B * heads * Nq * Nk * d
@@ -549,19 +622,23 @@ class Engine:
         d_tp32 = self.buf(B, cout, dtype=torch.float32)
         d_tp16 = self.buf(B, cout)
 
-        def tproj_bwd(g):
-            # d(time_emb_proj out)[b] = sum over the image's pixels of d(h1)
-            self.b(ops.colsum, g, d_tp32, B, HW, False, side=True)
+        def tproj_bwd(g, have_rowsum):
+            # d(time_emb_proj out)[b] = sum over the image's pixels of d(h1): emitted by norm2's backward when it could
+            # (have_rowsum), else one column-sum pass per image
+            if not have_rowsum:
+                self.b(ops.colsum, g, d_tp32, B, HW, False, side=True)
             self.b(ops.cast_f32_to_bf16, d_tp32.view(-1), d_tp16.view(-1), side=True)
             gs, acc = self._gout(semb)
             self.b(ops.linear_dgrad, d_tp16, wt, gs, residual=gs if acc else None, side=True)
             self.b(ops.linear_wgrad, d_tp16, semb.data, self.g32(prefix + '.time_emb_proj.weight'))
             self.b(ops.colsum, d_tp16, self.g32(prefix + '.time_emb_proj.bias'), 1, B, True)
 
-        h1 = self.conv3(a1, Hc, Wc, prefix + '.conv1', rowbias=rb, rowbias_bwd=tproj_bwd)
+        h1 = self.conv3(a1, Hc, Wc, prefix + '.conv1', rowbias=rb, rowbias_bwd=tproj_bwd, rowsum=d_tp32)
         a2 = self.groupnorm(h1, prefix + '.norm2', eps, 1, HW)
-        sc = self.linear(x, prefix + '.conv_shortcut.weight', prefix + '.conv_shortcut.bias') if has_sc else x
-        return self.conv3(a2, Hc, Wc, prefix + '.conv2', residual=sc)
+        if has_sc:
+            sc = self.linear(x, prefix + '.conv_shortcut.weight', prefix + '.conv_shortcut.bias', bias_grad_elsewhere='deferred')
+            return self.conv3(a2, Hc, Wc, prefix + '.conv2', residual=sc, extra_bias=(prefix + '.conv_shortcut.bias',))
+        return self.conv3(a2, Hc, Wc, prefix + '.conv2', residual=x)
 
     def transformer(self, x, prefix, Hc, Wc, heads):
         arena = self.arena
@@ -615,6 +692,7 @@ class Engine:
         # ---- conv_in (4 latent channels zero-padded to 8 so that the pixel stride is 16 bytes)
         x8 = Node(self.in_x8)
         x = self.node(M, boc[0])
+        x.bias_names = ['conv_in.bias']
         self.f(ops.conv3x3_fwd, x8.data, B, H, W, self.w_in16, x.data, bias=self.p32('conv_in.bias'), workspace=self.ws)
         gw_in = self.buf(9, boc[0], 8, dtype=torch.float32)
         x0 = x  # `x` is rebound below; the closure must keep conv_in's own output node
@@ -624,7 +702,10 @@ class Engine:
             self.b(ops.fill_f32, gw_in, 0.0)
             self.b(ops.conv3x3_wgrad, x0.grad, x8.data, B, H, W, gw_in)
             self.b(ops.unpad_accum_rows, gw_in.view(-1), 8, self.g32('conv_in.weight').reshape(-1), 4, 9 * boc[0], True)
-            self.b(ops.colsum, x0.grad, self.g32('conv_in.bias'), 1, M, True)
+            if self._bias_from_norm(x0, 'conv_in.bias'):
+                self._touched.add('conv_in.bias')
+            else:
+                self.b(ops.colsum, x0.grad, self.g32('conv_in.bias'), 1, M, True)
 
         self._bwd_builders.append(conv_in_bwd)
         # ---- down path

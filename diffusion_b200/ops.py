@@ -317,12 +317,15 @@ def groupnorm_fwd(ctx, x, gamma, beta, y, stats, ws, B, HW, G, eps, silu):
                                   HW, Cc, G, float(eps), int(silu), _s()))
 
 
-def groupnorm_bwd(ctx, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, B, HW, G, silu, dx_add=None):
+def groupnorm_bwd(ctx, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, B, HW, G, silu, dx_add=None, drowsum=None,
+                  dcolsum=None, dcolsum2=None):
+    """drowsum [B, C] (overwritten) / dcolsum, dcolsum2 [C] (accumulated): column sums of the dx written, see sd2b200.h."""
     Cc = x.shape[1]
     ctx.check(
         ctx.lib.sd2_groupnorm_bwd(ctx.h, _p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), _p(beta), _p(stats),
                                   _p(dx_add), dx_add.stride(0) if dx_add is not None else 0, _p(dx), dx.stride(0),
-                                  _p(dgamma), _p(dbeta), _p(ws), B, HW, Cc, G, int(silu), _s()))
+                                  _p(dgamma), _p(dbeta), _p(ws), B, HW, Cc, G, int(silu), _p(drowsum), _p(dcolsum),
+                                  _p(dcolsum2), _s()))
 
 
 def layernorm_fwd(ctx, x, gamma, beta, y, stats, eps=1e-5):

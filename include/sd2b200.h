@@ -117,11 +117,15 @@ long long sd2_groupnorm_ws_floats(int B, int C);
 int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* gamma, const float* beta, void* y,
                       long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
                       sd2_stream stream);
-/* dx = d(loss)/dx (+ dx_add if non-null); dgamma/dbeta accumulated (+=) in fp32 */
+/* dx = d(loss)/dx (+ dx_add if non-null); dgamma/dbeta accumulated (+=) in fp32.
+ * Optional column sums of the dx this call writes (it is then the complete output gradient of the conv / linear that
+ * produced x, so these are that layer's bias gradients - no separate pass over dx): drowsum fp32 [B][C] overwritten with
+ * the per-image sums (gradient of a per-image bias: the ResNet time-embedding projection), dcolsum1 / dcolsum2 fp32 [C]
+ * accumulated (+=) with the sums over the whole batch.  Any of the three may be null. */
 int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
                       const float* beta, const float* stats, const void* dx_add, long long ldadd, void* dx,
                       long long lddx, float* dgamma, float* dbeta, float* ws, int B, int HW, int C, int G, int silu,
-                      sd2_stream stream);
+                      float* drowsum, float* dcolsum1, float* dcolsum2, sd2_stream stream);
 /* LayerNorm over the last dim of [rows][C]; stats fp32 [rows][2] */
 int sd2_layernorm_fwd(sd2_ctx* ctx, const void* x, const float* gamma, const float* beta, void* y, float* stats,
                       long long rows, int C, float eps, sd2_stream stream);

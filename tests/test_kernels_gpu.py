@@ -275,6 +275,25 @@ def test_groupnorm(ctx, B, HW, Cc, silu):
     close(dx.view(B, HW, Cc), xr.grad.permute(0, 2, 1) + add.float().view(B, HW, Cc), rtol=2e-2, atol=3e-2, name='gn dx')
     close(dg, gamma.grad, rtol=1e-2, atol=1e-2 * gamma.grad.abs().max().item(), name='gn dgamma')
     close(db, beta.grad, rtol=1e-2, atol=1e-2 * beta.grad.abs().max().item(), name='gn dbeta')
+    # column sums of the dx just written (bias gradients of the producing conv): per image (overwritten) and over the batch
+    # (accumulated onto what the two destinations already hold), with and without the residual-gradient input
+    for use_add in (True, False):
+        dx2 = torch.empty_like(x)
+        rows_ = torch.full((B, Cc), 7.0, device='cuda')
+        c1, c2 = torch.full((Cc,), 3.0, device='cuda'), torch.zeros(Cc, device='cuda')
+        dg2, db2 = torch.zeros(Cc, device='cuda'), torch.zeros(Cc, device='cuda')
+        ops.groupnorm_bwd(ctx, dy, x, gamma.detach(), beta.detach(), stats, dx2, dg2, db2, ws, B, HW, G, silu,
+                          dx_add=add if use_add else None, drowsum=rows_, dcolsum=c1, dcolsum2=c2)
+        want_dx = xr.grad.permute(0, 2, 1) + (add.float().view(B, HW, Cc) if use_add else 0)
+        close(dx2.view(B, HW, Cc), want_dx, rtol=2e-2, atol=3e-2, name='gn dx (emitting)')
+        want_rows = dx2.float().view(B, HW, Cc).sum(1)  # the kernel sums before the bf16 rounding of dx: compare loosely
+        scale_ = want_rows.abs().max().item() + 1e-6
+        close(rows_, want_rows, rtol=1e-2, atol=2e-2 * scale_ + 0.05 * HW**0.5 * 2**-8, name='gn per-image column sums')
+        tot = want_rows.sum(0)
+        atol_t = 2e-2 * tot.abs().max().item() + 0.05 * (B * HW)**0.5 * 2**-8
+        close(c1 - 3.0, tot, rtol=1e-2, atol=atol_t, name='gn column sums (dest 1, accumulated)')
+        close(c2, tot, rtol=1e-2, atol=atol_t, name='gn column sums (dest 2)')
+        close(dg2, gamma.grad, rtol=1e-2, atol=1e-2 * gamma.grad.abs().max().item(), name='gn dgamma (emitting)')
 
 
 @pytest.mark.parametrize('rows,Cc', [(16384, 320), (4096, 640), (1024, 1280), (2048, 64), (32, 256), (231, 320), (77, 640), (5, 1280),

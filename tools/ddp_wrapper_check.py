@@ -124,7 +124,9 @@ def main():
         print('cosine engine vs ddp+AdamW: %.6f, engine vs ddp+FusedAdamW: %.6f' % (cos_ab, cos_ac))
         print('microbatch accumulation under DDP no_sync + ddp_compat: cosine vs explicit average %.6f' % cos_mb)
         ok = all(v < 1e-6 for v in res.values()) and cos_ab > 0.995 and cos_ac > 0.995 and cos_mb > 0.9999
-        print('DDP ROUTES OK' if ok else 'DDP ROUTES MISMATCH')
+        print('DDP ROUTES OK' if ok else 'DDP ROUTES MISMATCH', flush=True)
+        if not ok:
+            os._exit(1)
     dist.destroy_process_group()
 
 
