@@ -216,7 +216,7 @@ class DryLib:
             if name == 'sd2_groupnorm_ws_floats':
                 return a[0] * 64 * a[1] * 3 + a[0] * 128
             if name == 'sd2_attn_bwd_ws_bytes':
-                return a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * ((a[2] + 127) // 128) * 256 * 4
+                return 8 * a[0] * a[2] * a[1] * 64 * 4 + a[0] * a[1] * ((a[2] + 127) // 128) * 256 * 4
             if name == 'sd2_layernorm_ws_floats':
                 return 148 * 4 * a[1] * 2
             if name == 'sd2_last_error':

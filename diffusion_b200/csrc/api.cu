@@ -258,6 +258,20 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     }
   }
 
+  // 2-CTA clusters sharing the B tile through TMA multicast: decided before the tensor maps are built, because a K-major B
+  // operand is then fetched as two half-height boxes (one per CTA of the cluster)
+  bool cluster;
+  {
+    const bool bmn = d->kind == SD2_GEMM_CONV_WGRAD ? true : d->B.mn_major != 0;
+    GemmKParams q = p;
+    q.mt = (int)((d->M + 127) / 128);
+    q.nt = (p.N + BN - 1) / BN;
+    q.splits = splits;
+    q.batches = d->kind == SD2_GEMM_PLAIN ? (d->batch > 0 ? d->batch : 1) : (d->kind == SD2_GEMM_CONV_WGRAD ? d->conv.ntaps : 1);
+    cluster = gemm_use_cluster(q, BN, bmn, ctx->num_sms);
+  }
+  const int b_box_rows = cluster ? BN / 2 : BN;
+
   if (d->kind == SD2_GEMM_PLAIN) {
     a_mn = d->A.mn_major != 0;
     b_mn = d->B.mn_major != 0;
@@ -267,7 +281,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     p.b_batched = d->B.nb0 > 0;
     p.a_nb0 = d->A.nb0 > 0 ? d->A.nb0 : 1;
     p.b_nb0 = d->B.nb0 > 0 ? d->B.nb0 : 1;
-    if (!plain_tmap(&tmA, d->A, 128, &err) || !plain_tmap(&tmB, d->B, BN, &err)) return fail(ctx, "sd2_gemm plain: " + err);
+    if (!plain_tmap(&tmA, d->A, 128, &err) || !plain_tmap(&tmB, d->B, b_box_rows, &err)) return fail(ctx, "sd2_gemm plain: " + err);
   } else if (d->kind == SD2_GEMM_CONV) {
     const sd2_conv_geom& g = d->conv;
     a_mn = false;
@@ -294,7 +308,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     sd2_operand w = d->B;
     w.nb0 = 9;
     w.nb1 = 1;
-    if (!plain_tmap(&tmB, w, BN, &err)) return fail(ctx, "sd2_gemm conv B: " + err);
+    if (!plain_tmap(&tmB, w, b_box_rows, &err)) return fail(ctx, "sd2_gemm conv B: " + err);
   } else if (d->kind == SD2_GEMM_CONV_WGRAD) {
     const sd2_conv_geom& g = d->conv;
     a_mn = true;
@@ -356,7 +370,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     pp.residual = nullptr;
     if (!out_tmap(&tmO, d->workspace, true, 32, p.N, d->M, p.N, splits, 1, (long long)d->M * p.N, 0, &err))
       return fail(ctx, "sd2_gemm split-K workspace map: " + err);
-    e = launch_gemm_tc(tmA, tmB, tmO, pp, BN, a_mn, b_mn, ctx->num_sms, stream);
+    e = launch_gemm_tc(tmA, tmB, tmO, pp, BN, a_mn, b_mn, cluster, ctx->num_sms, stream);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm launch: ") + cudaGetErrorString(e));
     e = launch_splitk_finalize(reinterpret_cast<const float*>(d->workspace), splits, d->M, p.N, d->alpha, d->bias,
                                d->rowbias, p.rows_per_group, d->ld_rowbias, p.residual, d->ldr, d->out, d->ldo,
@@ -380,7 +394,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     if (!out_tmap(&tmO, d->out, f32, f32 ? 32 : gemm_out_chunk(BN), p.N, d->M, d->ldo, nb0, nb1, d->out_bs0, d->out_bs1, &err))
       return fail(ctx, "sd2_gemm output map: " + err);
   }
-  e = launch_gemm_tc(tmA, tmB, tmO, p, BN, a_mn, b_mn, ctx->num_sms, stream);
+  e = launch_gemm_tc(tmA, tmB, tmO, p, BN, a_mn, b_mn, cluster, ctx->num_sms, stream);
   if (e != cudaSuccess) return fail(ctx, std::string("sd2_gemm launch: ") + cudaGetErrorString(e));
   ctx->launches += 1;
   return 0;

@@ -365,17 +365,24 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, long long ldo, 
   }
 }
 
-// dst[r][0..cols) bf16 (row stride ldd) = src[r][0..cols) fp32 (dense)
+// dst[r][0..cols) bf16 (row stride ldd) = sum over `nparts` fp32 partials (dense [rows][cols] each, `part_stride` floats
+// apart, added in index order)
 __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long ldd, long long rows,
-                                       int cols) {
+                                       int cols, int nparts, long long part_stride) {
   pdl_grid_sync();
   const int V = cols / 8;
   const long long n = rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / V;
     const int v = (int)(i % V);
-    const float4 a = *reinterpret_cast<const float4*>(src + r * cols + v * 8);
-    const float4 b = *reinterpret_cast<const float4*>(src + r * cols + v * 8 + 4);
+    float4 a = *reinterpret_cast<const float4*>(src + r * cols + v * 8);
+    float4 b = *reinterpret_cast<const float4*>(src + r * cols + v * 8 + 4);
+    for (int pi = 1; pi < nparts; ++pi) {
+      const float4 a2 = *reinterpret_cast<const float4*>(src + pi * part_stride + r * cols + v * 8);
+      const float4 b2 = *reinterpret_cast<const float4*>(src + pi * part_stride + r * cols + v * 8 + 4);
+      a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+      b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+    }
     uint4 u;
     u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
     *reinterpret_cast<uint4*>(dst + r * ldd + v * 8) = u;
@@ -393,7 +400,7 @@ static constexpr int AT_BWD_THREADS = 64 + AT_BWD_CWARPS * 32;  // warp 0 TMA, w
 template <bool DIRECT>
 __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_stg, const void* my_stg_g, int lane, float scale,
                                                   uint64_t* dq_empty, const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h,
-                                                  int b, bf16* dq, long long lddq) {
+                                                  int b, bf16* dq, long long lddq, bool one_q_tile, bool first_kt) {
   uint32_t rq[16];
   tmem_ld_32x32b_x16(taddr, rq);
   tmem_wait_ld();
@@ -418,6 +425,11 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
     if (lane == 0) {
       mbar_arrive(dq_empty);
       bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
+      // Fixed summation order: the previous contribution to THESE dQ rows (same query tile, previous key tile = nqt tiles
+      // ago) must have landed before this one is issued.  With several query tiles only the most recent reduce-add (other
+      // rows) may still be in flight.
+      if (one_q_tile) bulk_wait<0>();
+      else bulk_wait<1>();
     }
     __syncwarp();
     const uint32_t bufp = my_stg + lane * 64;  // 64 B rows, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
@@ -428,46 +440,61 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if (row0 < Nq) tma_reduce_add_4d(tmDQ, my_stg_g, col0, row0, h, b);
+      if (row0 < Nq) {  // the first key tile of this CTA's range initialises its partial (no memset), the others add to it
+        if (first_kt) tma_store_4d(tmDQ, my_stg_g, col0, row0, h, b);
+        else tma_reduce_add_4d(tmDQ, my_stg_g, col0, row0, h, b);
+      }
       bulk_commit();
     }
   }
 }
 
+// One CTA owns the key tiles [kt0, kt1) of one (image, head) and walks them sequentially (outer loop), each against all
+// query tiles (inner loop): dK / dV of a key tile accumulate in tensor memory over the inner loop, and every dQ tile
+// receives this CTA's contributions in a FIXED order (same thread, same address, one reduce-add after the other) - the
+// gradient is bit-reproducible run to run.  gridDim.x > 1 splits the key range over several CTAs when (images x heads) alone
+// cannot fill the GPU; each split accumulates into its own fp32 partial and the cast pass adds the partials in order.
 template <bool DIRECT>
 __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + AT_TILE;
-  uint8_t* sQ = sV + AT_TILE;        // [2]
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
+  uint8_t* sKV = smem;               // [2 buffers][K tile | V tile]
+  uint8_t* sQ = sKV + 4 * AT_TILE;   // [2]
   uint8_t* sdO = sQ + 2 * AT_TILE;   // [2]
   uint8_t* sdS = sdO + 2 * AT_TILE;  // dS^T : [2 buffers] x 2 query chunks x [128 key rows][128 B]
   uint8_t* stg = sdS + 4 * AT_TILE;  // 16 warps x 2 KB fp32 staging for the dQ reduce-add (DIRECT: unused)
   float* sStat = reinterpret_cast<float*>(stg + AT_BWD_CWARPS * 2048);  // [2 stages][lse 128 | D 128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 512);
-  uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* dp_full = bars + 7;
-  uint64_t* dp_empty = bars + 8;
-  uint64_t* pds_full = bars + 9;
-  uint64_t* pt_empty = bars + 10;   // P^T (tensor memory) consumed by dV
-  uint64_t* dq_full = bars + 11;
-  uint64_t* dq_empty = bars + 12;
-  uint64_t* dkv_full = bars + 13;
-  uint64_t* ds_empty = bars + 14;   // [2] dS^T smem buffer consumed by dK and dQ
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* kv_full = bars;        // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* qdo_full = bars + 4;   // [2]
+  uint64_t* qdo_empty = bars + 6;  // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* s_empty = bars + 9;
+  uint64_t* dp_full = bars + 10;
+  uint64_t* dp_empty = bars + 11;
+  uint64_t* pds_full = bars + 12;
+  uint64_t* pt_empty = bars + 13;   // P^T (tensor memory) consumed by dV
+  uint64_t* dq_full = bars + 14;
+  uint64_t* dq_empty = bars + 15;
+  uint64_t* dkv_full = bars + 16;   // dV / dK of a key tile complete
+  uint64_t* dkv_empty = bars + 17;  // ... and drained from tensor memory
+  uint64_t* ds_empty = bars + 18;   // [2] dS^T smem buffer consumed by dK and dQ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nqt = (p.Nq + 127) / 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nqt = (p.Nq + 127) / 128, nkt = (p.Nk + 127) / 128;
+  const int kt0 = (int)(((long long)blockIdx.x * nkt) / gridDim.x), kt1 = (int)(((long long)(blockIdx.x + 1) * nkt) / gridDim.x);
+  const int nk = kt1 - kt0;
+  const int ntiles = nk * nqt;
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("sd2: attn_bwd dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -477,10 +504,12 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
   }
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(kv_full, 1);
       for (int s = 0; s < 2; ++s) {
+        mbar_init(&kv_full[s], 1);
+        mbar_init(&kv_empty[s], 1);
         mbar_init(&qdo_full[s], 1);
         mbar_init(&qdo_empty[s], 1);
+        mbar_init(&ds_empty[s], 1);
       }
       mbar_init(s_full, 1);
       mbar_init(s_empty, AT_BWD_CWARPS);
@@ -488,11 +517,10 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
       mbar_init(dp_empty, AT_BWD_CWARPS);
       mbar_init(pds_full, AT_BWD_CWARPS);
       mbar_init(pt_empty, 1);
-      mbar_init(&ds_empty[0], 1);
-      mbar_init(&ds_empty[1], 1);
       mbar_init(dq_full, 1);
       mbar_init(dq_empty, AT_BWD_CWARPS);
       mbar_init(dkv_full, 1);
+      mbar_init(dkv_empty, AT_BWD_CWARPS);
       fence_mbar_init();
     }
     __syncwarp();
@@ -510,215 +538,246 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (elect_one()) {
-      mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
-      tma_load_4d(sK, &tmK, kv_full, 0, kt * 128, h, b);
-      tma_load_4d(sV, &tmV, kv_full, 0, kt * 128, h, b);
-    }
-    __syncwarp();
     const float* st_bh = p.stats + ((long long)b * p.heads + h) * nqt * 256;
-    for (int i = 0; i < nqt; ++i) {
-      const int s = i & 1;
-      mbar_wait(&qdo_empty[s], (uint32_t)((i >> 1) & 1) ^ 1u);
+    int t = 0;
+    for (int kk = 0; kk < nk; ++kk) {
+      const int sk = kk & 1;
+      mbar_wait(&kv_empty[sk], (uint32_t)((kk >> 1) & 1) ^ 1u);  // every MMA of the key tile that used this buffer is done
       if (elect_one()) {
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * AT_TILE + 1024);
-        tma_load_4d(sQ + s * AT_TILE, &tmQ, &qdo_full[s], 0, i * 128, h, b);
-        tma_load_4d(sdO + s * AT_TILE, &tmdO, &qdo_full[s], 0, i * 128, h, b);
-        bulk_load_1d(sStat + s * 256, st_bh + (long long)i * 256, 1024, &qdo_full[s]);
+        mbar_arrive_expect_tx(&kv_full[sk], 2 * AT_TILE);
+        tma_load_4d(sKV + sk * 2 * AT_TILE, &tmK, &kv_full[sk], 0, (kt0 + kk) * 128, h, b);
+        tma_load_4d(sKV + sk * 2 * AT_TILE + AT_TILE, &tmV, &kv_full[sk], 0, (kt0 + kk) * 128, h, b);
       }
       __syncwarp();
+      for (int i = 0; i < nqt; ++i, ++t) {
+        const int s = t & 1;
+        mbar_wait(&qdo_empty[s], (uint32_t)((t >> 1) & 1) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&qdo_full[s], 2 * AT_TILE + 1024);
+          tma_load_4d(sQ + s * AT_TILE, &tmQ, &qdo_full[s], 0, i * 128, h, b);
+          tma_load_4d(sdO + s * AT_TILE, &tmdO, &qdo_full[s], 0, i * 128, h, b);
+          bulk_load_1d(sStat + s * 256, st_bh + (long long)i * 256, 1024, &qdo_full[s]);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    // Tensor-pipe order per query tile i:  [dV, dK, dQ of tile i-1]  S^T(i+1)  dP^T(i+1)  - the score tile of the next
-    // iteration is issued as soon as the compute warps hold S^T(i) in registers (s_empty, early in their iteration), the
-    // dP^T one when dP^T(i) has been read (late), so both are complete long before tile i+1 needs them.
+    // Tensor-pipe order per tile t:  [dV, dK, dQ of tile t-1]  S^T(t+1)  dP^T(t+1)  - the score tile of the next iteration
+    // (possibly the first query tile of the NEXT key tile, whose K / V were prefetched into the other buffer) is issued as
+    // soon as the compute warps hold S^T(t) in registers, the dP^T one when dP^T(t) has been read.
     constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T : A K-major, B K-major
     constexpr uint32_t id_kn = umma_idesc_bf16(128, 64, 0, 1);   // dV, dK    : A K-major (TMEM P^T / smem dS^T), B MN-major
     constexpr uint32_t id_mn = umma_idesc_bf16(128, 64, 1, 1);   // dQ        : A MN-major (dS), B MN-major (K)
-    const uint64_t aK = umma_desc_sw128(smem_u32(sK), 16, 1024), aV = umma_desc_sw128(smem_u32(sV), 16, 1024);
+    constexpr uint64_t TS = AT_TILE >> 4;
+    const uint64_t aK0 = umma_desc_sw128(smem_u32(sKV), 16, 1024), aV0 = aK0 + TS;
     const uint64_t bQ0 = umma_desc_sw128(smem_u32(sQ), 16, 1024), bdO0 = umma_desc_sw128(smem_u32(sdO), 16, 1024);
     const uint64_t adS = umma_desc_sw128(smem_u32(sdS), 16, 1024);
     const uint64_t bQ0mn = umma_desc_sw128(smem_u32(sQ), 8192, 1024), bdO0mn = umma_desc_sw128(smem_u32(sdO), 8192, 1024);
     const uint64_t adSmn = umma_desc_sw128(smem_u32(sdS), 16384, 1024);  // M chunks (64 queries) 16 KB apart
-    const uint64_t bKmn = umma_desc_sw128(smem_u32(sK), 8192, 1024);
-    constexpr uint64_t TS = AT_TILE >> 4;
-    mbar_wait(kv_full, 0);
+    const uint64_t bKmn0 = umma_desc_sw128(smem_u32(sKV), 8192, 1024);
+    mbar_wait(&kv_full[0], 0);
     mbar_wait(&qdo_full[0], 0);
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK + 2 * ks, bQ0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK0 + 2 * ks, bQ0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
       tc_commit(s_full);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV + 2 * ks, bdO0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+      for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV0 + 2 * ks, bdO0 + 2 * ks, id_s, ks != 0 ? 1u : 0u);
       tc_commit(dp_full);
     }
     __syncwarp();
-    for (int i = 0; i < nqt; ++i) {
-      const int s = i & 1;
-      if (i + 1 < nqt) {
-        const int s1 = (i + 1) & 1;
-        const uint64_t bQ = bQ0 + (uint64_t)s1 * TS, bdO = bdO0 + (uint64_t)s1 * TS;
-        mbar_wait(s_empty, (uint32_t)(i & 1));
-        mbar_wait(&qdo_full[s1], (uint32_t)(((i + 1) >> 1) & 1));
+    int t = 0;
+    for (int kk = 0; kk < nk; ++kk) {
+      const uint64_t kvb = (uint64_t)(kk & 1) * 2 * TS;  // K / V buffer of this key tile
+      for (int i = 0; i < nqt; ++i, ++t) {
+        const int s = t & 1;
+        if (t + 1 < ntiles) {
+          const int s1 = (t + 1) & 1;
+          const uint64_t bQ = bQ0 + (uint64_t)s1 * TS, bdO = bdO0 + (uint64_t)s1 * TS;
+          uint64_t kvn = kvb;
+          if (i == nqt - 1) {  // the next tile belongs to the next key tile: its K / V arrive in the other buffer
+            kvn = (uint64_t)((kk + 1) & 1) * 2 * TS;
+            mbar_wait(&kv_full[(kk + 1) & 1], (uint32_t)(((kk + 1) >> 1) & 1));
+          }
+          mbar_wait(s_empty, (uint32_t)(t & 1));
+          mbar_wait(&qdo_full[s1], (uint32_t)(((t + 1) >> 1) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK0 + kvn + 2 * ks, bQ + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+            tc_commit(s_full);
+          }
+          __syncwarp();
+          mbar_wait(dp_empty, (uint32_t)(t & 1));
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV0 + kvn + 2 * ks, bdO + 2 * ks, id_s, ks != 0 ? 1u : 0u);
+            tc_commit(dp_full);
+          }
+          __syncwarp();
+        }
+        mbar_wait(pds_full, (uint32_t)(t & 1));
+        if (i == 0 && kk > 0) mbar_wait(dkv_empty, (uint32_t)((kk - 1) & 1));  // dV / dK of the previous key tile drained
+        tc_fence_after();
+        const uint64_t bQ = bQ0mn + (uint64_t)s * TS, bdO = bdO0mn + (uint64_t)s * TS;
+        const uint64_t dsb = (uint64_t)s * 2 * TS;  // dS^T buffer of this tile
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // K = 128 queries, 16 per step = 8 TMEM columns of P^T
+            tc_mma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), bdO + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
+          tc_commit(pt_empty);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // dS^T from smem: chunk ks>>2 (16 KB apart), 32 B per K step inside
+            const uint64_t a = adS + dsb + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
+            tc_mma_bf16(tdK, a, bQ + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (t > 0) mbar_wait(dq_empty, (uint32_t)((t - 1) & 1));  // dQ of the previous tile has left tensor memory
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tST, aK + 2 * ks, bQ + 2 * ks, id_s, ks != 0 ? 1u : 0u);
-          tc_commit(s_full);
+          for (int ks = 0; ks < 8; ++ks)  // K = 128 keys: 16 key rows (2048 B) per step in both operands
+            tc_mma_bf16(tdQ, adSmn + dsb + (uint64_t)ks * 128, bKmn0 + kvb + (uint64_t)ks * 128, id_mn, ks != 0 ? 1u : 0u);
+          tc_commit(&ds_empty[s]);
+          tc_commit(dq_full);
+          tc_commit(&qdo_empty[s]);
+          if (i == nqt - 1) {
+            tc_commit(dkv_full);
+            tc_commit(&kv_empty[kk & 1]);
+          }
         }
         __syncwarp();
-        mbar_wait(dp_empty, (uint32_t)(i & 1));
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tdPT, aV + 2 * ks, bdO + 2 * ks, id_s, ks != 0 ? 1u : 0u);
-          tc_commit(dp_full);
-        }
-        __syncwarp();
       }
-      mbar_wait(pds_full, (uint32_t)(i & 1));
-      tc_fence_after();
-      const uint64_t bQ = bQ0mn + (uint64_t)s * TS, bdO = bdO0mn + (uint64_t)s * TS;
-      const uint64_t dsb = (uint64_t)s * 2 * TS;  // dS^T buffer of this tile
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // K = 128 queries, 16 per step = 8 TMEM columns of P^T
-          tc_mma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), bdO + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
-        tc_commit(pt_empty);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // dS^T from smem: chunk ks>>2 (16 KB apart), 32 B per K step inside
-          const uint64_t a = adS + dsb + (uint64_t)(ks >> 2) * TS + 2 * (ks & 3);
-          tc_mma_bf16(tdK, a, bQ + (uint64_t)ks * 128, id_kn, (i | ks) != 0 ? 1u : 0u);
-        }
-      }
-      __syncwarp();
-      if (i > 0) mbar_wait(dq_empty, (uint32_t)((i - 1) & 1));  // dQ_{i-1} has left tensor memory (drained right after pds_full)
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)  // K = 128 keys: 16 key rows (2048 B) per step in both operands
-          tc_mma_bf16(tdQ, adSmn + dsb + (uint64_t)ks * 128, bKmn + (uint64_t)ks * 128, id_mn, ks != 0 ? 1u : 0u);
-        tc_commit(&ds_empty[s]);
-        tc_commit(dq_full);
-        tc_commit(&qdo_empty[s]);
-        if (i == nqt - 1) tc_commit(dkv_full);
-      }
-      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- compute warps
     // Four threads per key row: thread (r, hq) owns query columns hq*32 .. +31 of S^T / dP^T (16 bf16-pair columns of
     // P^T, four 16-byte groups of a dS^T row) and output columns hq*16 .. +15 of dQ, dV and dK.  Four warps per SM
     // sub-partition keep the MUFU / FMA pipes busy across each other's TMEM-load and barrier latencies.
+    // Padding key rows of the last key tile need no masking: their K rows are zero-filled by TMA, so they add nothing to
+    // dQ = dS K, and their dV / dK rows are never stored.
     const int q = warp & 3;
     const int hq = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const int key = kt * 128 + r;
-    const bool key_ok = key < p.Nk;
-    // Padding key rows of the last key tile need no masking: their K rows are zero-filled by TMA, so they add nothing to
-    // dQ = dS K, and their dV / dK rows are never stored.
     const uint32_t ds_row0 = smem_u32(sdS) + (uint32_t)(hq >> 1) * AT_TILE + r * 128;
     const int dsg0 = (hq & 1) * 4;  // first 16-byte group of this thread inside the 128-byte dS^T row
     const uint32_t stat0 = smem_u32(sStat) + hq * 128;  // this thread's 32 queries of the lse block; D block 512 B further
     const uint8_t* my_stg_g = stg + (size_t)(warp - 2) * 2048;
     const uint32_t my_stg = smem_u32(my_stg_g);
     const float c2 = p.c2;
-    for (int i = 0; i < nqt; ++i) {
-      const uint32_t stat = stat0 + (uint32_t)(i & 1) * 1024;
-      const uint32_t ds_row = ds_row0 + (uint32_t)(i & 1) * 2 * AT_TILE;
-      mbar_wait(&qdo_full[i & 1], (uint32_t)((i >> 1) & 1));  // the statistics block of this query tile has landed
-      mbar_wait(s_full, (uint32_t)(i & 1));
+    const int bq = DIRECT ? b : (int)blockIdx.x * p.B + b;  // image index inside the (per key-range split) fp32 dQ accumulator
+
+    auto drain_dkv = [&](int kt, int kk) {  // dV, dK of key tile kt (this thread's 16 columns of each) -> bf16, global
+      mbar_wait(dkv_full, (uint32_t)(kk & 1));
       tc_fence_after();
-      uint32_t rs[32];
-      tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hq * 32), rs);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);  // S^T is in registers: the tensor pipe may overwrite it with tile i+1
-      // P^T = exp2(S^T c2 - lse), kept in fp32 for dS and packed to bf16 pairs for the dV operand
-      uint32_t pk[16];
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 l = lds128f(stat + g * 16);
-        const float e0 = ex2(fmaf(__uint_as_float(rs[g * 4 + 0]), c2, -l.x));
-        const float e1 = ex2(fmaf(__uint_as_float(rs[g * 4 + 1]), c2, -l.y));
-        const float e2 = ex2(fmaf(__uint_as_float(rs[g * 4 + 2]), c2, -l.z));
-        const float e3 = ex2(fmaf(__uint_as_float(rs[g * 4 + 3]), c2, -l.w));
-        rs[g * 4 + 0] = __float_as_uint(e0); rs[g * 4 + 1] = __float_as_uint(e1);
-        rs[g * 4 + 2] = __float_as_uint(e2); rs[g * 4 + 3] = __float_as_uint(e3);
-        pk[g * 2] = pack_bf16x2(e0, e1);
-        pk[g * 2 + 1] = pack_bf16x2(e2, e3);
-      }
-      mbar_wait(pt_empty, (uint32_t)(i & 1) ^ 1u);  // P^T of the previous tile consumed by its dV MMAs (first in their order)
-      tc_fence_after();
-      tmem_st_32x32b_x16(tPT + lane_off + (uint32_t)(hq * 16), pk);
-      // dS^T = P^T (dP^T - D)   (the 1/sqrt(d) factor is applied when dQ / dK are drained)
-      mbar_wait(dp_full, (uint32_t)(i & 1));
-      tc_fence_after();
-      uint32_t rd[32];
-      tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(hq * 32), rd);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dp_empty);
-      mbar_wait(&ds_empty[i & 1], (uint32_t)((i >> 1) & 1) ^ 1u);  // this dS^T buffer was read by the MMAs of tile i-2
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4 d0 = lds128f(stat + 512 + g * 32), d1 = lds128f(stat + 512 + g * 32 + 16);
-        const int e = g * 8;
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(rs[e + 0]) * (__uint_as_float(rd[e + 0]) - d0.x),
-                          __uint_as_float(rs[e + 1]) * (__uint_as_float(rd[e + 1]) - d0.y));
-        u.y = pack_bf16x2(__uint_as_float(rs[e + 2]) * (__uint_as_float(rd[e + 2]) - d0.z),
-                          __uint_as_float(rs[e + 3]) * (__uint_as_float(rd[e + 3]) - d0.w));
-        u.z = pack_bf16x2(__uint_as_float(rs[e + 4]) * (__uint_as_float(rd[e + 4]) - d1.x),
-                          __uint_as_float(rs[e + 5]) * (__uint_as_float(rd[e + 5]) - d1.y));
-        u.w = pack_bf16x2(__uint_as_float(rs[e + 6]) * (__uint_as_float(rd[e + 6]) - d1.z),
-                          __uint_as_float(rs[e + 7]) * (__uint_as_float(rd[e + 7]) - d1.w));
-        sts128(ds_row + (uint32_t)(((dsg0 + g) ^ (r & 7)) << 4), u);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      if (i > 0) {  // dQ_{i-1} (rows = queries): its MMAs were issued a whole tile of math ago
-        mbar_wait(dq_full, (uint32_t)((i - 1) & 1));
-        tc_fence_after();
-        attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
-                                  (i - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
-      }
-    }
-    {  // last tile's dQ
-      mbar_wait(dq_full, (uint32_t)((nqt - 1) & 1));
-      tc_fence_after();
-      attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
-                                (nqt - 1) * 128 + q * 32, p.Nq, h, b, p.dq, p.lddq);
-    }
-    // dV, dK of this key tile (this thread's 16 columns of each)
-    mbar_wait(dkv_full, 0);
-    tc_fence_after();
+      const int key = kt * 128 + r;
 #pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      bf16* dst = (t == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (t == 0 ? p.lddv : p.lddk) + h * 64 + hq * 16;
-      const float mul = t == 0 ? 1.f : p.scale;
-      uint32_t rr[16];
-      tmem_ld_32x32b_x16((t == 0 ? tdV : tdK) + lane_off + (uint32_t)(hq * 16), rr);
-      tmem_wait_ld();
-      if (key_ok) {
+      for (int tt = 0; tt < 2; ++tt) {
+        bf16* dst = (tt == 0 ? p.dv : p.dk) + ((long long)b * p.Nk + key) * (tt == 0 ? p.lddv : p.lddk) + h * 64 + hq * 16;
+        const float mul = tt == 0 ? 1.f : p.scale;
+        uint32_t rr[16];
+        tmem_ld_32x32b_x16((tt == 0 ? tdV : tdK) + lane_off + (uint32_t)(hq * 16), rr);
+        tmem_wait_ld();
+        if (key < p.Nk) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(rr[g * 8 + 0]) * mul, __uint_as_float(rr[g * 8 + 1]) * mul);
-          u.y = pack_bf16x2(__uint_as_float(rr[g * 8 + 2]) * mul, __uint_as_float(rr[g * 8 + 3]) * mul);
-          u.z = pack_bf16x2(__uint_as_float(rr[g * 8 + 4]) * mul, __uint_as_float(rr[g * 8 + 5]) * mul);
-          u.w = pack_bf16x2(__uint_as_float(rr[g * 8 + 6]) * mul, __uint_as_float(rr[g * 8 + 7]) * mul);
-          *reinterpret_cast<uint4*>(dst + g * 8) = u;
+          for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(rr[g * 8 + 0]) * mul, __uint_as_float(rr[g * 8 + 1]) * mul);
+            u.y = pack_bf16x2(__uint_as_float(rr[g * 8 + 2]) * mul, __uint_as_float(rr[g * 8 + 3]) * mul);
+            u.z = pack_bf16x2(__uint_as_float(rr[g * 8 + 4]) * mul, __uint_as_float(rr[g * 8 + 5]) * mul);
+            u.w = pack_bf16x2(__uint_as_float(rr[g * 8 + 6]) * mul, __uint_as_float(rr[g * 8 + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + g * 8) = u;
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkv_empty);
+    };
+
+    int t = 0;
+    for (int kk = 0; kk < nk; ++kk) {
+      for (int i = 0; i < nqt; ++i, ++t) {
+        const uint32_t stat = stat0 + (uint32_t)(t & 1) * 1024;
+        const uint32_t ds_row = ds_row0 + (uint32_t)(t & 1) * 2 * AT_TILE;
+        mbar_wait(&qdo_full[t & 1], (uint32_t)((t >> 1) & 1));  // the statistics block of this query tile has landed
+        mbar_wait(s_full, (uint32_t)(t & 1));
+        tc_fence_after();
+        uint32_t rs[32];
+        tmem_ld_32x32b_x32(tST + lane_off + (uint32_t)(hq * 32), rs);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);  // S^T is in registers: the tensor pipe may overwrite it with the next tile
+        // P^T = exp2(S^T c2 - lse), kept in fp32 for dS and packed to bf16 pairs for the dV operand
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 l = lds128f(stat + g * 16);
+          const float e0 = ex2(fmaf(__uint_as_float(rs[g * 4 + 0]), c2, -l.x));
+          const float e1 = ex2(fmaf(__uint_as_float(rs[g * 4 + 1]), c2, -l.y));
+          const float e2 = ex2(fmaf(__uint_as_float(rs[g * 4 + 2]), c2, -l.z));
+          const float e3 = ex2(fmaf(__uint_as_float(rs[g * 4 + 3]), c2, -l.w));
+          rs[g * 4 + 0] = __float_as_uint(e0); rs[g * 4 + 1] = __float_as_uint(e1);
+          rs[g * 4 + 2] = __float_as_uint(e2); rs[g * 4 + 3] = __float_as_uint(e3);
+          pk[g * 2] = pack_bf16x2(e0, e1);
+          pk[g * 2 + 1] = pack_bf16x2(e2, e3);
+        }
+        // dV / dK of the previous key tile: complete since its last tile's MMAs, drained here (one exp phase later)
+        if (i == 0 && kk > 0) drain_dkv(kt0 + kk - 1, kk - 1);
+        mbar_wait(pt_empty, (uint32_t)(t & 1) ^ 1u);  // P^T of the previous tile consumed by its dV MMAs (first in their order)
+        tc_fence_after();
+        tmem_st_32x32b_x16(tPT + lane_off + (uint32_t)(hq * 16), pk);
+        // dS^T = P^T (dP^T - D)   (the 1/sqrt(d) factor is applied when dQ / dK are drained)
+        mbar_wait(dp_full, (uint32_t)(t & 1));
+        tc_fence_after();
+        uint32_t rd[32];
+        tmem_ld_32x32b_x32(tdPT + lane_off + (uint32_t)(hq * 32), rd);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_empty);
+        mbar_wait(&ds_empty[t & 1], (uint32_t)((t >> 1) & 1) ^ 1u);  // this dS^T buffer was read by the MMAs of tile t-2
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 d0 = lds128f(stat + 512 + g * 32), d1 = lds128f(stat + 512 + g * 32 + 16);
+          const int e = g * 8;
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(rs[e + 0]) * (__uint_as_float(rd[e + 0]) - d0.x),
+                            __uint_as_float(rs[e + 1]) * (__uint_as_float(rd[e + 1]) - d0.y));
+          u.y = pack_bf16x2(__uint_as_float(rs[e + 2]) * (__uint_as_float(rd[e + 2]) - d0.z),
+                            __uint_as_float(rs[e + 3]) * (__uint_as_float(rd[e + 3]) - d0.w));
+          u.z = pack_bf16x2(__uint_as_float(rs[e + 4]) * (__uint_as_float(rd[e + 4]) - d1.x),
+                            __uint_as_float(rs[e + 5]) * (__uint_as_float(rd[e + 5]) - d1.y));
+          u.w = pack_bf16x2(__uint_as_float(rs[e + 6]) * (__uint_as_float(rd[e + 6]) - d1.z),
+                            __uint_as_float(rs[e + 7]) * (__uint_as_float(rd[e + 7]) - d1.w));
+          sts128(ds_row + (uint32_t)(((dsg0 + g) ^ (r & 7)) << 4), u);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        if (t > 0) {  // dQ of the previous tile (rows = queries): its MMAs were issued a whole tile of math ago
+          const int ip = i > 0 ? i - 1 : nqt - 1;
+          mbar_wait(dq_full, (uint32_t)((t - 1) & 1));
+          tc_fence_after();
+          attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ,
+                                    hq * 16, ip * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, t - 1 < nqt);
+        }
+      }
+    }
+    if (ntiles > 0) {  // last tile's dQ, last key tile's dV / dK
+      mbar_wait(dq_full, (uint32_t)((ntiles - 1) & 1));
+      tc_fence_after();
+      attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
+                                (nqt - 1) * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, ntiles - 1 < nqt);
+      drain_dkv(kt1 - 1, nk - 1);
     }
     if (!DIRECT) {
       if (lane == 0) bulk_wait_read<0>();
@@ -783,9 +842,30 @@ int sd2_attn_fwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   return check_launch(ctx, "attn_fwd");
 }
 
+// Key-range splits per (image, head).  One CTA per SM: the grid runs in waves of 148, so few (image, head) pairs leave
+// the last wave (or the whole GPU) partly idle; splitting the key range over 2 / 4 / 8 CTAs fills it at the price of one
+// fp32 dQ partial per split (written by the kernel, summed in order by the cast pass).  Small cost model: waves x tiles per
+// CTA x ~2 us per tile + partial traffic at ~6 TB/s.
+static int attn_bwd_ksplit(int B, int heads, int Nq, int nkt) {
+  const double bh = (double)B * heads;
+  const int nqt = (Nq + 127) / 128;
+  const double part_bytes = bh * Nq * 64.0 * 4.0;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ks = 1; ks <= 8 && ks <= nkt; ks *= 2) {
+    const double cost = ceil(bh * ks / 148.0) * ceil((double)nkt / ks) * nqt * 2.0e-6 + ks * part_bytes / 6.0e12;
+    if (cost < best_cost * 0.97) {
+      best_cost = cost;
+      best = ks;
+    }
+  }
+  return best;
+}
+
 long long sd2_attn_bwd_ws_bytes(int B, int heads, int Nq) {
   const long long nqt = (Nq + 127) / 128;
-  return (long long)B * Nq * heads * 64 * 4 + (long long)B * heads * nqt * 256 * 4;
+  const int ks = attn_bwd_ksplit(B, heads, Nq, (int)nqt);  // self-attention (Nk = Nq) is the case that needs the accumulator
+  return (long long)ks * B * Nq * heads * 64 * 4 + (long long)B * heads * nqt * 256 * 4;
 }
 
 int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
@@ -801,15 +881,20 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   const int C = heads * 64;
   const int nqt = (Nq + 127) / 128, nkt = (Nk + 127) / 128;
   const bool direct = nkt == 1;  // one key tile: every dQ tile has a single contribution and is written as bf16 directly
-  float* dq32 = reinterpret_cast<float*>(ws);      // [B*Nq][C] fp32 accumulation of dQ (several key tiles only)
-  float* stats = dq32 + (long long)B * Nq * C;     // [B*heads][nqt][lse 128 | D 128]
+  // the workspace (sd2_attn_bwd_ws_bytes knows B, heads, Nq only) holds attn_bwd_ksplit(B, heads, nqt) partials
+  const int ks_ws = attn_bwd_ksplit(B, heads, Nq, nqt);
+  int ksplit = direct ? 1 : attn_bwd_ksplit(B, heads, Nq, nkt);
+  if (ksplit > ks_ws) ksplit = ks_ws;
+  const long long part = (long long)B * Nq * C;
+  float* dq32 = reinterpret_cast<float*>(ws);                                    // [ksplit][B*Nq][C] fp32 dQ partials
+  float* stats = dq32 + (long long)ks_ws * part;                                // [B*heads][nqt][lse 128 | D 128]
   CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
   std::string err;
   if (!head_tmap(&tmQ, q, ldq, Nq, heads, B, &err) || !head_tmap(&tmK, k, ldk, Nk, heads, B, &err) ||
       !head_tmap(&tmV, v, ldv, Nk, heads, B, &err) || !head_tmap(&tmdO, d_o, lddo, Nq, heads, B, &err))
     return fail(ctx, "sd2_attn_bwd: " + err);
-  // fp32 dQ accumulator as [B][heads][Nq][64]-strided view, box = 32 rows x 16 columns (64-byte rows, SWIZZLE_64B)
-  if (!out_tmap(&tmDQ, dq32, true, 16, 64, Nq, C, heads, B, 64, (long long)Nq * C, &err))
+  // fp32 dQ partials as a [ksplit * B][heads][Nq][64]-strided view, box = 32 rows x 16 columns (64-byte rows, SWIZZLE_64B)
+  if (!out_tmap(&tmDQ, dq32, true, 16, 64, Nq, C, heads, (long long)B * ksplit, 64, (long long)Nq * C, &err))
     return fail(ctx, "sd2_attn_bwd dq map: " + err);
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -828,11 +913,7 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   launch_k(attn_bwd_prep_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(o), ldo,
            reinterpret_cast<const bf16*>(d_o), lddo, lse, stats, B, heads, Nq, nqt);
   cudaError_t e;
-  if (!direct) {
-    e = cudaMemsetAsync(dq32, 0, (size_t)B * Nq * C * 4, stream);
-    if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
-  }
-  const size_t smem = 10 * AT_TILE + AT_BWD_CWARPS * 2048 + 512 * 4 + 17 * 8 + 16 + 1024;
+  const size_t smem = 12 * AT_TILE + AT_BWD_CWARPS * 2048 + 512 * 4 + 20 * 8 + 16;
   static bool attr = false;
   if (!attr) {
     e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -841,13 +922,14 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
     attr = true;
   }
   if (direct) {
-    e = launch_k(attn_bwd_kernel<true>, dim3(nkt, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
+    e = launch_k(attn_bwd_kernel<true>, dim3(1, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd launch: ") + cudaGetErrorString(e));
     return check_launch(ctx, "attn_bwd", 2);
   }
-  attn_bwd_kernel<false><<<dim3(nkt, heads, B), AT_BWD_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+  e = launch_k(attn_bwd_kernel<false>, dim3(ksplit, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
+  if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd launch: ") + cudaGetErrorString(e));
   launch_k(cast2d_f32_bf16_kernel, dim3(grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream,
-           (const float*)dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
+           (const float*)dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C, ksplit, part);
   return check_launch(ctx, "attn_bwd", 3);
 }
 

@@ -10,6 +10,10 @@
 //                 tcgen05.ld 32x32b -> registers -> alpha / bias / per-image bias / residual -> swizzled smem
 //                 staging -> TMA store (bf16 / fp32) or TMA reduce-add (fp32 weight gradients, split-K sums); every
 //                 global write is a full coalesced row segment issued by the copy engine, no per-thread stores or atomics
+// CL = 2: the kernel runs as thread-block clusters of two CTAs that work on the two M tiles of a pair with the SAME B tile:
+// each CTA fetches half of B and TMA-multicasts it into both CTAs' shared memory, so the operand traffic L2 -> SM per
+// k-block drops from A + B to A + B/2 (the 128 x 256 tile is L2-fabric bound at ~2/3 of the tensor peak otherwise: 48 KB
+// of operands per 512 tensor-pipe cycles on each of 148 SMs).  A stage is released by both CTAs' MMA warps (multicast commit).
 // Operands can be K-major (forward, activations x weights) or MN-major (dgrad reads the weights transposed, wgrad
 // contracts over pixels) - the same TMA boxes serve both, only the UMMA descriptors differ.
 //
@@ -49,19 +53,20 @@ int gemm_out_chunk(int BN) { return (BN % 128 == 0) ? 64 : 32; }
 struct WorkItem {
   int m_tile, n_tile, split, batch, kb0, nkb;
 };
-__device__ __forceinline__ WorkItem decode_item(const GemmKParams& p, int item) {
+// mt = number of M work units: M tiles, or pairs of M tiles when the kernel runs as 2-CTA clusters (m_tile then counts pairs)
+__device__ __forceinline__ WorkItem decode_item(const GemmKParams& p, int item, int mt) {
   WorkItem w;
   int t;
   if (p.raster == 1) {
     w.n_tile = item % p.nt;
     t = item / p.nt;
-    w.m_tile = t % p.mt;
-    t /= p.mt;
+    w.m_tile = t % mt;
+    t /= mt;
     w.split = t % p.splits;
     w.batch = t / p.splits;
   } else {
-    w.m_tile = item % p.mt;
-    t = item / p.mt;
+    w.m_tile = item % mt;
+    t = item / mt;
     w.n_tile = t % p.nt;
     t /= p.nt;
     if (p.raster == 2) {
@@ -184,12 +189,13 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmO, const GemmKParams p, const int stages) {
   using Cfg = TileCfg<BN>;
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide chunks");
+  static_assert(CL == 1 || (B_MN ? BN % 128 == 0 : BN % 16 == 0), "2-CTA clusters split the B tile in two halves");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stg_base = smem + (size_t)stages * Cfg::STAGE_BYTES;
@@ -200,7 +206,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.mt * p.nt * p.splits * p.batches;
+  // work units: one M tile (CL = 1) or a pair of M tiles, one per CTA of the cluster (CL = 2; an odd tile count leaves the
+  // last pair's second CTA with an out-of-range tile: its loads are zero-filled, its stores clipped)
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int mtd = CL == 2 ? (p.mt + 1) / 2 : p.mt;
+  const int n_items = mtd * p.nt * p.splits * p.batches;
+  const int unit0 = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[s], CL);  // one MMA-warp commit per CTA of the cluster
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full_bar[a], 1);
@@ -224,7 +236,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_grid_sync();  // everything above is input-independent and overlaps the previous kernel's tail
@@ -237,8 +250,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int s = 0;
     uint32_t ph = 0;
     const int bpi = p.cnb == 1 ? (p.cH / p.cth) * p.cws : 1;  // pixel blocks (M tiles or wgrad k-blocks) per image
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const WorkItem w = decode_item(p, item);
+    constexpr int BH = BN / 2;                          // rows of B this CTA fetches for the cluster (K-major B)
+    constexpr int NCH = BN / 64, NCH_CL = NCH / CL;     // 64-wide chunks of an MN-major B tile: all / per CTA
+    const int j0 = crank * NCH_CL;
+    for (int item = unit0; item < n_items; item += unit_step) {
+      WorkItem w = decode_item(p, item, mtd);
+      if (CL == 2) w.m_tile = 2 * w.m_tile + crank;
       const int n_off = w.n_tile * BN, m_off = w.m_tile * BM;
       const int ab0 = p.a_batched ? w.batch % p.a_nb0 : 0, ab1 = p.a_batched ? w.batch / p.a_nb0 : 0;
       const int bb0 = p.b_batched ? w.batch % p.b_nb0 : 0, bb1 = p.b_batched ? w.batch / p.b_nb0 : 0;
@@ -283,7 +300,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
           if (p.kind == KIND_CONV) {
             tma_load_4d(a_dst, &tmA, fb, cb * 64, cw0 + dw, ch0 + dh, cn0 + dn);
-            if (!B_MN) {
+            if (CL == 2) {  // this CTA's half of the B tile, multicast to both CTAs of the cluster
+              if (!B_MN) {
+                tma_load_4d_mc(b_dst + crank * (BH * 128), &tmB, fb, cb * 64, n_off + crank * BH, tw, 0, 3);
+              } else {
+#pragma unroll
+                for (int j = 0; j < NCH_CL; ++j)
+                  tma_load_4d_mc(b_dst + (j0 + j) * CHUNK_BYTES, &tmB, fb, n_off + 64 * (j0 + j), cb * 64, tw, 0, 3);
+              }
+            } else if (!B_MN) {
               tma_load_4d(b_dst, &tmB, fb, cb * 64, n_off, tw, 0);
             } else {
 #pragma unroll
@@ -297,16 +322,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               for (int j = 0; j < 2; ++j) tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, fb, m_off + 64 * j, kcol, ab0, ab1);
             }
             if (p.kind == KIND_PLAIN) {
-              if (!B_MN) {
+              if (CL == 2) {
+                if (!B_MN) {
+                  tma_load_4d_mc(b_dst + crank * (BH * 128), &tmB, fb, kcol, n_off + crank * BH, bb0, bb1, 3);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < NCH_CL; ++j)
+                    tma_load_4d_mc(b_dst + (j0 + j) * CHUNK_BYTES, &tmB, fb, n_off + 64 * (j0 + j), kcol, bb0, bb1, 3);
+                }
+              } else if (!B_MN) {
                 tma_load_4d(b_dst, &tmB, fb, kcol, n_off, bb0, bb1);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, kcol, bb0, bb1);
               }
             } else if (B_MN) {  // KIND_CONV_WGRAD: B = activations shifted by the tap, k-block = 64 pixels
+              if (CL == 2) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, dw, wh + dh, wn + dn);
+                for (int j = 0; j < NCH_CL; ++j)
+                  tma_load_4d_mc(b_dst + (j0 + j) * CHUNK_BYTES, &tmB, fb, n_off + 64 * (j0 + j), dw, wh + dh, wn + dn, 3);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, dw, wh + dh, wn + dn);
+              }
             }
           }
         }
@@ -357,8 +396,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint32_t ph = 0;
     uint64_t ad = adesc0, bd = bdesc0;
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const WorkItem w = decode_item(p, item);
+    for (int item = unit0; item < n_items; item += unit_step, ++it) {
+      const WorkItem w = decode_item(p, item, mtd);
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator buffer
@@ -372,7 +411,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           tc_mma_bf16(d_tmem, ad + A_KSTEP, bd + B_KSTEP, idesc, 1u);
           tc_mma_bf16(d_tmem, ad + 2 * A_KSTEP, bd + 2 * B_KSTEP, idesc, 1u);
           tc_mma_bf16(d_tmem, ad + 3 * A_KSTEP, bd + 3 * B_KSTEP, idesc, 1u);
-          tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
+          if (CL == 2) tc_commit_mc(&empty_bar[s], 3);  // the stage is shared: both CTAs' producers wait for both MMA warps
+          else tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
           if (i == w.nkb - 1) tc_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
         __syncwarp();
@@ -401,8 +441,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     st.c1 = hh == 0 ? HALF : NCH_ALL;
     int it = 0;
     const bool raw = p.out_mode == OUT_F32_PARTIAL;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const WorkItem w = decode_item(p, item);
+    for (int item = unit0; item < n_items; item += unit_step, ++it) {
+      WorkItem w = decode_item(p, item, mtd);
+      if (CL == 2) w.m_tile = 2 * w.m_tile + crank;
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       EpiTile t;
@@ -449,7 +490,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     __syncwarp();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -498,28 +540,79 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int splits,
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
                               int grid, int stages, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + STG_TOTAL + (2 * stages + 4) * 8 + 16 + 1024;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmO, p, stages);
+  if (CL == 1) return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmO, p, stages);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, p, stages);
+}
+
+// Should this launch run as 2-CTA clusters (B tile shared through TMA multicast)?  Measured per shape at the bench geometry
+// (tools/gemm_shapes.py, SD2_GEMM_CLUSTER=0 vs 2, profiles/r02_gemm_cluster_ab.md): the implicit-GEMM convolutions (forward
+// and dgrad) gain up to 17 %, the weight gradients lose 10-80 % (their M dimension is Cout: 3 or 5 tiles pair badly, and
+// both operands are streamed), the linears are a wash.  Default policy: convolution forward / dgrad only, even M-tile
+// count or many tiles.  SD2_GEMM_CLUSTER=0 disables clusters, =2 enables them wherever the kernel supports it.
+bool gemm_use_cluster(const GemmKParams& p, int BN, bool b_mn, int num_sms) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SD2_GEMM_CLUSTER");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode == 0) return false;
+  if (b_mn && BN < 128) return false;  // an MN-major B tile needs two 64-wide chunks to split
+  if (p.mt < 2) return false;
+  const long long pair_items = (long long)((p.mt + 1) / 2) * p.nt * p.splits * p.batches;
+  if (pair_items < num_sms / 2) return false;
+  if (mode == 2) return true;
+  return p.kind == KIND_CONV && (p.mt % 2 == 0 || p.mt >= 32);
 }
 
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
-                           int BN, bool a_mn, bool b_mn, int num_sms, cudaStream_t stream) {
+                           int BN, bool a_mn, bool b_mn, bool cluster, int num_sms, cudaStream_t stream) {
+  const int st = gemm_stages(BN);
+  if (cluster) {
+    const long long items = (long long)((p.mt + 1) / 2) * p.nt * p.splits * p.batches;
+    const int ncl = (int)(items < num_sms / 2 ? items : num_sms / 2);
+    const int grid = 2 * ncl;
+#define SD2_GEMM_CASE(bn, amn, bmn) \
+  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn, 2>(tmA, tmB, tmO, p, grid, st, stream);
+    SD2_GEMM_CASE(256, false, false) SD2_GEMM_CASE(160, false, false) SD2_GEMM_CASE(128, false, false)
+    SD2_GEMM_CASE(64, false, false)
+    SD2_GEMM_CASE(256, false, true) SD2_GEMM_CASE(128, false, true)
+    SD2_GEMM_CASE(256, true, false) SD2_GEMM_CASE(160, true, false) SD2_GEMM_CASE(128, true, false)
+    SD2_GEMM_CASE(64, true, false)
+    SD2_GEMM_CASE(256, true, true) SD2_GEMM_CASE(128, true, true)
+#undef SD2_GEMM_CASE
+    return cudaErrorInvalidValue;
+  }
   const long long items = (long long)p.mt * p.nt * p.splits * p.batches;
   const int grid = (int)(items < num_sms ? items : num_sms);
-  const int st = gemm_stages(BN);
 #define SD2_GEMM_CASE(bn, amn, bmn) \
-  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn>(tmA, tmB, tmO, p, grid, st, stream);
+  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn, 1>(tmA, tmB, tmO, p, grid, st, stream);
   SD2_GEMM_CASE(256, false, false) SD2_GEMM_CASE(160, false, false) SD2_GEMM_CASE(128, false, false)
   SD2_GEMM_CASE(64, false, false)
   SD2_GEMM_CASE(256, false, true) SD2_GEMM_CASE(128, false, true) SD2_GEMM_CASE(64, false, true)

@@ -376,14 +376,6 @@ __global__ void __launch_bounds__(256) gn_colsum_finalize_kernel(const float* __
 // x and dy cross HBM exactly once.
 static constexpr int GNC_NSUB = 4;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // Split second barrier of the cluster kernels: a CTA may exit only after every peer has read its gpart.  Peers read it right
 // after the first barrier, so each CTA ARRIVES (relaxed: no memory to publish) as soon as its own remote reads are done and
 // WAITS only at the very end - by then everybody has long arrived, and the arrive no longer fences the apply pass's global

@@ -33,7 +33,7 @@ def test_sd2_base_train_step_parity(B, R):
     assert torch.equal(out_g[1], res['out'][1]) and torch.equal(out_g[2], res['out'][2])
     assert abs(loss_g - res['loss_product']) <= 1e-4 * abs(res['loss_product'])
     worst = min(parity._cos(g1[n], g2[n]) for n in g1 if g1[n].norm().item() > 0)
-    assert worst > 0.9995, worst
+    assert worst > 0.999999, worst
 
 
 @pytest.mark.parametrize('B,R', [(2, 32), (3, 16), (2, 64)])
@@ -43,9 +43,10 @@ def test_tiny_train_step_parity(B, R):
 
 
 def test_forward_is_bit_deterministic_and_gradients_repeat():
-    """Two runs of the same step: identical prediction bits; gradients agree to cosine > 0.9995 per tensor (the fp32 dQ /
-    split-K sums are reduce-adds in arrival order: after the bf16 cast of dQ a last-bit difference is amplified by the
-    depth of the backward pass, see DESIGN.md "Determinism")."""
+    """Two runs of the same step: identical prediction bits; gradients agree to cosine > 0.999999 per tensor.  Every bf16
+    activation gradient is bit-reproducible (the attention backward adds the key tiles' dQ contributions in a fixed order);
+    only fp32 parameter-gradient sums (split-K / weight-gradient reduce-adds, norm affine gradients) depend on arrival order,
+    at the 1e-7 level, and nothing is computed from them (DESIGN.md "Determinism")."""
     from oracle.unet import SD2_BASE_UNET_CONFIG
     oracle, model, batch = parity.make_pair(SD2_BASE_UNET_CONFIG, 2, 32)
     del oracle
@@ -54,4 +55,4 @@ def test_forward_is_bit_deterministic_and_gradients_repeat():
     _, out2, g2 = parity.product_step(model, batch)
     assert torch.equal(pred1.view(torch.int16), out2[0].view(torch.int16))
     worst = min(parity._cos(g1[n], g2[n]) for n in g1 if g1[n].norm().item() > 0)
-    assert worst > 0.9995, worst
+    assert worst > 0.999999, worst
