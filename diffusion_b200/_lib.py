@@ -96,7 +96,7 @@ class GemmDesc(C.Structure):
                 ('residual', C.c_void_p), ('ldr', C.c_longlong), ('bias', C.c_void_p), ('rowbias', C.c_void_p),
                 ('rows_per_group', C.c_int), ('ld_rowbias', C.c_longlong), ('alpha', C.c_float),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_longlong), ('max_splits', C.c_int), ('force_bn', C.c_int),
-                ('force_splits', C.c_int)]
+                ('force_splits', C.c_int), ('gn_partial', C.c_void_p), ('gn_slab', C.c_int)]
 
 
 GEMM_PLAIN, GEMM_CONV, GEMM_CONV_WGRAD = 0, 1, 2
@@ -123,6 +123,7 @@ SIGNATURES = {
     'sd2_gemm': (_i, [_vp, C.POINTER(GemmDesc), _vp]),
     'sd2_groupnorm_ws_floats': (_ll, [_i, _i]),
     'sd2_groupnorm_fwd': (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'sd2_groupnorm_fwd_fused': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'sd2_groupnorm_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _i, _i, _i,
                                _i, _i, _vp, _vp, _vp, _vp]),
     'sd2_layernorm_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),

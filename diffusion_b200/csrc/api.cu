@@ -218,6 +218,16 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   p.out_nb0 = d->out_nb0 > 0 ? d->out_nb0 : 1;
   p.out_bs0 = d->out_bs0;
   p.out_bs1 = d->out_bs1;
+  const bool gn = d->gn_partial != nullptr;
+  if (gn) {
+    if (d->out_mode != SD2_OUT_BF16) return fail(ctx, "sd2_gemm: gn_partial needs a bf16 output");
+    if (d->gn_slab != 16 && d->gn_slab != 32) return fail(ctx, "sd2_gemm: gn_slab must be 16 or 32");
+    if (d->kind == SD2_GEMM_CONV_WGRAD || (d->kind == SD2_GEMM_PLAIN && d->batch > 1))
+      return fail(ctx, "sd2_gemm: gn_partial is for single-batch forward GEMMs / convolutions");
+    if (d->M % d->gn_slab != 0) return fail(ctx, "sd2_gemm: gn_slab must divide M");
+    p.gn_part = d->gn_partial;
+    p.gn_slab = d->gn_slab;
+  }
 
   bool a_mn, b_mn;
   int batches = 1;
@@ -241,7 +251,9 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
       bmn = true;
     }
     if (kb < 1 || nbatch < 1) return fail(ctx, "sd2_gemm: empty contraction / batch");
-    plan_gemm(ctx, d, p.N, kb, nbatch, bmn, direct_store, &BN, &splits);
+    sd2_gemm_desc dd = *d;
+    if (gn) dd.max_splits = 1;  // the statistics come from the epilogue that writes the final values
+    plan_gemm(ctx, &dd, p.N, kb, nbatch, bmn, direct_store, &BN, &splits);
     // measured plan (tools/autotune_gemm.py -> diffusion_b200/gemm_plans.json) overrides the cycle model
     if (d->force_bn == 256 || d->force_bn == 128 || d->force_bn == 64 || (d->force_bn == 160 && !bmn)) BN = d->force_bn;
     if (d->force_splits > 0) {
@@ -256,6 +268,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
       if (smax < 1) smax = 1;
       splits = d->force_splits < smax ? d->force_splits : (int)smax;
     }
+    if (gn) splits = 1;
   }
 
   // 2-CTA clusters sharing the B tile through TMA multicast: decided before the tensor maps are built, because a K-major B

@@ -90,6 +90,8 @@ struct EpiTile {  // per work item, per thread (thread = one output row of the 3
   bool has_bias;
   float alpha;
   float bv[8];      // bias of tile columns lane*8 .. lane*8+7
+  float* gn_part;   // GroupNorm partial sums of the output (or null), see GemmKParams
+  int gn_slab;
 };
 struct EpiPre {  // residual of one 32-column chunk, fetched one chunk ahead (the per-image bias rows are tiny and
   uint4 rs[4];    // L1-resident: they are read in place)
@@ -107,6 +109,65 @@ __device__ __forceinline__ void epi_prefetch(const EpiTile& t, int c, EpiPre& pr
 }
 
 // One 32-column chunk of the accumulator: TMEM -> registers -> (+bias +rowbias +residual) -> swizzled staging -> TMA.
+// GroupNorm statistics of one staged bf16 tile (32 rows x OUT_CH columns, swizzled as the TMA store expects it): every lane
+// owns one 32-bit word (two columns) and walks the rows: per column sum and sum of squares of the rounded values, kept
+// apart for rows 0-15 / 16-31 (two 16-row slabs) or added (one 32-row slab).  With 32-column tiles the two half-warps split
+// the rows.  Conflict-free: in every row the 32 lanes read 32 different banks.
+template <int OUT_CH>
+__device__ __forceinline__ void epi_gn_stats(const EpiTile& t, uint32_t buf_s, int col0, int lane) {
+  float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [row half][column of the pair]
+  const int rows_ok = t.M - t.row0;  // rows of this 32-row slab inside the matrix
+  if (OUT_CH == 64) {
+    const int c = lane >> 2, w = lane & 3;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+      for (int k = hf * 16; k < hf * 16 + 16; ++k) {
+        uint32_t u;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(buf_s + k * 128 + ((c ^ (k & 7)) << 4) + w * 4) : "memory");
+        if (k < rows_ok) {
+          const float2 x = unpack_bf16x2(u);
+          s[hf][0] += x.x; q[hf][0] = fmaf(x.x, x.x, q[hf][0]);
+          s[hf][1] += x.y; q[hf][1] = fmaf(x.y, x.y, q[hf][1]);
+        }
+      }
+    const int col = col0 + 2 * lane;
+    if (col < t.N) {
+      if (t.gn_slab == 32) {
+        float* o = t.gn_part + ((long long)(t.row0 >> 5) * t.N + col) * 2;
+        *reinterpret_cast<float4*>(o) = make_float4(s[0][0] + s[1][0], q[0][0] + q[1][0], s[0][1] + s[1][1], q[0][1] + q[1][1]);
+      } else {
+        float* o = t.gn_part + ((long long)(t.row0 >> 4) * t.N + col) * 2;
+        *reinterpret_cast<float4*>(o) = make_float4(s[0][0], q[0][0], s[0][1], q[0][1]);
+        if (rows_ok > 16) *reinterpret_cast<float4*>(o + 2 * (long long)t.N) = make_float4(s[1][0], q[1][0], s[1][1], q[1][1]);
+      }
+    }
+  } else {  // 32 columns: 16 words per row, half-warp hf = lane >> 4 takes rows hf*16 .. hf*16+15
+    const int hf = lane >> 4, j = lane & 15, c = j >> 2, w = j & 3;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int row = hf * 16 + k;
+      uint32_t u;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(buf_s + row * 64 + ((c ^ ((row >> 1) & 3)) << 4) + w * 4) : "memory");
+      if (row < rows_ok) {
+        const float2 x = unpack_bf16x2(u);
+        s0 += x.x; q0 = fmaf(x.x, x.x, q0);
+        s1 += x.y; q1 = fmaf(x.y, x.y, q1);
+      }
+    }
+    const int col = col0 + 2 * j;
+    if (t.gn_slab == 32) {  // one slab: add the two halves (lane j + lane j+16)
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+      if (hf == 0 && col < t.N)
+        *reinterpret_cast<float4*>(t.gn_part + ((long long)(t.row0 >> 5) * t.N + col) * 2) = make_float4(s0, q0, s1, q1);
+    } else if (col < t.N && hf * 16 < rows_ok) {
+      *reinterpret_cast<float4*>(t.gn_part + ((long long)((t.row0 >> 4) + hf) * t.N + col) * 2) = make_float4(s0, q0, s1, q1);
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c, const EpiPre& cur, EpiPre& nxt,
                                           uint32_t t_addr, uint8_t* stg, int lane, const CUtensorMap* tmO,
@@ -186,6 +247,8 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
         tma_store_4d(tmO, buf, col0, t.row0, t.o2, t.o3);
     }
     if (lane == 0) bulk_commit();
+    // GroupNorm statistics of the tile just handed to the copy engine (it only reads the staging buffer, as we do)
+    if (!f32_out && t.gn_part != nullptr && t.row0 < t.M && col0 < t.N) epi_gn_stats<OUT_CH>(t, buf_s, col0, lane);
   }
 }
 
@@ -467,6 +530,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       t.N = p.N;
       t.M = p.M;
       t.out_mode = p.out_mode;
+      t.gn_part = p.gn_part;
+      t.gn_slab = p.gn_slab;
 #pragma unroll
       for (int e = 0; e < 8; ++e) t.bv[e] = 0.f;
       if (t.has_bias && lane * 8 < BN && t.n_tile0 + lane * 8 < p.N) {

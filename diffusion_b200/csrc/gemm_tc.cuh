@@ -48,6 +48,11 @@ struct GemmKParams {
   int rows_per_group;
   long long ld_rowbias;
   float alpha;
+  // GroupNorm statistics of the OUTPUT, taken in the epilogue (bf16 outputs only): per slab of gn_slab (16 or 32) consecutive
+  // rows and per column the sum and the sum of squares of the stored (bf16-rounded) values -> gn_part[row / gn_slab][N][2].
+  // The consuming GroupNorm combines them per (image, group) and is then a pure streaming apply pass.
+  float* gn_part;
+  int gn_slab;
 };
 
 }  // namespace sd2

@@ -363,6 +363,72 @@ __global__ void __launch_bounds__(256) gn_colsum_finalize_kernel(const float* __
   }
 }
 
+// ---- GroupNorm forward on statistics taken by the producing GEMM's epilogue (gemm_tc.cu::epi_gn_stats)
+// part[slab][C][2] = (sum, sum of squares) of every column over `slab` consecutive rows; NS = HW / slab slabs per image.
+// grid (B), block 256: one warp per group (round-robin), lanes over (slab, channel of the group) -> stats[b][g] = (mean, rstd)
+__global__ void __launch_bounds__(256) gn_part_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int NS,
+                                                               int HW, int C, int G, float eps) {
+  pdl_grid_sync();
+  const int b = blockIdx.x, cpg = C / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* pb = part + (long long)b * NS * C * 2;
+  const int n = NS * cpg;
+  for (int g = warp; g < G; g += 8) {
+    float s = 0.f, q = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const int sl = i / cpg, cl = i % cpg;
+      const float2 t = *reinterpret_cast<const float2*>(pb + ((long long)sl * C + g * cpg + cl) * 2);
+      s += t.x;
+      q += t.y;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      const float cnt = (float)cpg * (float)HW;
+      const float mean = s / cnt;
+      const float var = fmaxf(q / cnt - mean * mean, 0.f);
+      *reinterpret_cast<float2*>(stats + ((long long)b * G + g) * 2) = make_float2(mean, rsqrtf(var + eps));
+    }
+  }
+}
+
+// grid (P, B): y = [silu](x * scale + shift) with the per-(image, channel) scale / shift from stats - one streaming pass
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_stats_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                                     const float* __restrict__ stats, int HW, int C, int G,
+                                                                     int silu) {
+  pdl_grid_sync();
+  const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G;
+  const int V = C / 8, R = GN_THREADS / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  if (r >= R) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e, g = c / cpg;
+    const float2 t = *reinterpret_cast<const float2*>(stats + ((long long)b * G + g) * 2);
+    sc[e] = gamma[c] * t.y;
+    sh[e] = beta[c] - t.x * sc[e];
+  }
+  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  const bf16* xb = x + ((long long)b * HW) * C + v * 8;
+  bf16* yb = y + ((long long)b * HW) * C + v * 8;
+#pragma unroll 4
+  for (int row = row0 + r; row < row1; row += R) {
+    float f[8];
+    const uint4 u = ldg_stream16(xb + (long long)row * C);
+    const float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), dd = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = bb.x; f[3] = bb.y; f[4] = cc.x; f[5] = cc.y; f[6] = dd.x; f[7] = dd.y;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float z = fmaf(f[e], sc[e], sh[e]);
+      f[e] = silu ? silu_f(z) : z;
+    }
+    store8(yb + (long long)row * C, f);
+  }
+}
+
 // ---- single-pass GroupNorm backward: one thread-block CLUSTER per image
 // The two-kernel path above reads x and dy twice from HBM/L2 and evaluates the SiLU derivative twice; at the UNet's
 // shapes it ran at 1.5-2.5 TB/s and was half instruction-issue bound.  Here a cluster of NC CTAs owns one image: each
@@ -1153,6 +1219,28 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
   launch_k(gn_apply_kernel, dim3(grid), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(x), ldx, gamma, beta,
                                                    reinterpret_cast<bf16*>(y), ldy, stats, ws, HW, C, G, eps, silu);
   return check_launch(ctx, "groupnorm_fwd", 2);
+}
+
+int sd2_groupnorm_fwd_fused(sd2_ctx* ctx, const void* x, const float* gn_partial, int slab, const float* gamma,
+                            const float* beta, void* y, float* stats, float* ws, int B, int HW, int C, int G, float eps,
+                            int silu, sd2_stream stream_) {
+  if (!ctx) return 1;
+  (void)ws;
+  if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_fwd_fused: unsupported C/G");
+  if ((slab != 16 && slab != 32) || HW % slab != 0) return fail(ctx, "sd2_groupnorm_fwd_fused: slab must be 16 or 32 and divide HW");
+  if (!gn_partial) return fail(ctx, "sd2_groupnorm_fwd_fused: no partial statistics");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  launch_k(gn_part_finalize_kernel, dim3(B), dim3(256), 0, stream, gn_partial, stats, HW / slab, HW, C, G, eps);
+  // enough blocks for ~4 per SM; every thread keeps >= 4 rows in flight
+  const int R = GN_THREADS / (C / 8);
+  int P = (4 * ctx->num_sms + B - 1) / B;
+  const int pmax = HW / (4 * (R > 0 ? R : 1));
+  if (P > pmax) P = pmax;
+  if (P > GN_MAXP) P = GN_MAXP;
+  if (P < 1) P = 1;
+  launch_k(gn_apply_stats_kernel, dim3(P, B), dim3(GN_THREADS), 0, stream, reinterpret_cast<const bf16*>(x), gamma, beta,
+           reinterpret_cast<bf16*>(y), (const float*)stats, HW, C, G, silu);
+  return check_launch(ctx, "groupnorm_fwd_fused", 2);
 }
 
 int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,

@@ -31,10 +31,10 @@ _GEMM_FUNCS = (ops.linear_fwd, ops.linear_dgrad, ops.linear_wgrad, ops.conv3x3_f
 # Output operands of every recorded op: (positional indices after ctx, keyword names).  Every other tensor argument is
 # an input.  The two-stream scheduler derives read / write address ranges from this table.
 _OP_WRITES = {
-    'linear_fwd': ((2,), ('workspace',)), 'linear_dgrad': ((2,), ('workspace',)), 'linear_wgrad': ((2,), ()),
-    'conv3x3_fwd': ((5,), ('workspace',)), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
+    'linear_fwd': ((2,), ('workspace', 'gn_partial')), 'linear_dgrad': ((2,), ('workspace',)), 'linear_wgrad': ((2,), ()),
+    'conv3x3_fwd': ((5,), ('workspace', 'gn_partial')), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
     'attn_fwd': ((3, 4), ()), 'attn_bwd': ((6, 7, 8, 9), ()),
-    'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ('drowsum', 'dcolsum', 'dcolsum2')),
+    'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_fwd_fused': ((5, 6, 7), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ('drowsum', 'dcolsum', 'dcolsum2')),
     'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ('dcolsum',)),
     'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ('dbias',)), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
     'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
@@ -78,7 +78,7 @@ def _overlap(xs, ys):
 class Node:
     """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
     __slots__ = ('data', 'grad', 'gw', 'M', 'C', 'writes', 'last_writer', 'writes_at_norm', 'reads', 'bias_names', 'rowsum',
-                 'claimed')
+                 'claimed', 'producer')
 
     def __init__(self, data):
         self.data, self.grad, self.gw = data, None, False
@@ -91,6 +91,9 @@ class Node:
         #   claimed    - a GroupNorm is the node's FIRST forward consumer, hence the last writer of its gradient: its
         #                backward kernel emits those sums and the producer skips its own pass.
         self.reads, self.bias_names, self.rowsum, self.claimed = 0, [], None, False
+        # the recorded forward GEMM / conv op (a functools.partial) that writes this node as a whole bf16 tensor: a GroupNorm
+        # that consumes the node asks that op's epilogue for the statistics (Engine.groupnorm)
+        self.producer = None
 
 
 def _align(n, a=64):
@@ -208,6 +211,9 @@ class Engine:
         self.fwd, self.bwd, self._bwd_builders = [], [], []
         self._touched, self.grad_ready = set(), {}
         self._norm_emitted = set()  # bias parameters whose gradient a GroupNorm backward produced
+        import os
+        self.fuse_gn_stats = os.environ.get('SD2_NO_GN_FUSION') != '1'  # A/B switch of the epilogue GroupNorm statistics
+        self.gn_part = None  # scratch of those statistics: written by a producer's epilogue, read by the norm right behind it
         reuse = shared is not None and getattr(shared, 'ws', None) is not None
         self.ws = shared.ws if reuse else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         self.G = self.cfg['norm_num_groups']
@@ -279,10 +285,12 @@ class Engine:
         """Record a forward op.  side=True: the op is off the critical path (it only feeds later ops) and may run on the
         side stream, concurrently with the main chain; the scheduler inserts the dependencies."""
         self._attach_plan(fn, a, k)
-        self.fwd.append(partial(fn, self.ctx, *a, **k))
+        op = partial(fn, self.ctx, *a, **k)
+        self.fwd.append(op)
         self.fwd_is_gemm.append(fn in _GEMM_FUNCS)
         self.fwd_side.append(bool(side))
         self._count_flops(fn, a)
+        return op
 
     def b(self, fn, *a, side=None, **k):
         """Record a backward op.  Weight-gradient GEMMs and bias-gradient column sums write only parameter gradients,
@@ -348,8 +356,10 @@ class Engine:
         self._use(x, residual)
         if bname and not bias_grad_elsewhere:
             out.bias_names = [bname]
-        self.f(ops.linear_fwd, x.data, w, out.data, bias=bias, residual=residual.data if residual else None,
-               workspace=self.ws_side if side else self.ws, side=side)
+        op = self.f(ops.linear_fwd, x.data, w, out.data, bias=bias, residual=residual.data if residual else None,
+                    workspace=self.ws_side if side else self.ws, side=side)
+        if not side:
+            out.producer = op
 
         def bwd():
             g = out.grad
@@ -394,6 +404,11 @@ class Engine:
         self._bwd_builders.append(bwd)
         return out
 
+    def _gn_part_floats(self):
+        # largest [rows / 16][C][2] any level can ask for: rows * C is largest at the top level (C0 channels, or 2*C0 never
+        # fused: concatenations have no producing GEMM)
+        return (self.B * self.H * self.W // 16) * self.cfg['block_out_channels'][0] * 2
+
     def _use(self, *nodes):
         for n in nodes:
             if n is not None:
@@ -417,7 +432,23 @@ class Engine:
         if x.reads == 0 and (x.bias_names or x.rowsum is not None) and len(x.bias_names) <= 2 and not self.forward_only:
             x.claimed = True
         self._use(x)
-        self.f(ops.groupnorm_fwd, x.data, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
+        # GroupNorm fused with the producing conv / linear: that op's epilogue takes the per-slab column sums of the tensor it
+        # writes, this norm only combines them and streams the apply(+SiLU) pass (north_star: GroupNorm in the conv epilogue)
+        slab = 32 if HW % 32 == 0 else (16 if HW % 16 == 0 else 0)
+        fuse = x.producer is not None and slab and 'gn_partial' not in x.producer.keywords and self.fuse_gn_stats
+        if fuse:  # the statistics scratch is shared: nothing recorded since the producer may write it
+            at = next(i for i in range(len(self.fwd) - 1, -1, -1) if self.fwd[i] is x.producer)
+            fuse = not any('gn_partial' in op.keywords for op in self.fwd[at + 1:])
+        if fuse:
+            need = (x.M // slab) * x.C * 2
+            if self.gn_part is None or self.gn_part.numel() < need:
+                self.gn_part = torch.empty(max(need, self._gn_part_floats()), dtype=torch.float32, device=self.dev)
+            part = self.gn_part[:need].view(x.M // slab, x.C, 2)
+            x.producer.keywords['gn_partial'] = part
+            x.producer.keywords['gn_slab'] = slab
+            self.f(ops.groupnorm_fwd_fused, x.data, part, slab, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
+        else:
+            self.f(ops.groupnorm_fwd, x.data, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
 
         def bwd():
             assert y.gw
@@ -471,8 +502,8 @@ class Engine:
         out.rowsum = rowsum
         B = self.B
         self._use(x, residual)
-        self.f(ops.conv3x3_fwd, x.data, B, Hc, Wc, w, out.data, bias=bias, rowbias=rowbias,
-               residual=residual.data if residual else None, workspace=self.ws)
+        out.producer = self.f(ops.conv3x3_fwd, x.data, B, Hc, Wc, w, out.data, bias=bias, rowbias=rowbias,
+                              residual=residual.data if residual else None, workspace=self.ws)
 
         def bwd():
             g = out.grad
@@ -504,7 +535,8 @@ class Engine:
         taps = ops.taps_stride2(B)
         self._use(x)
         self.f(ops.phase_split, x.data, planes, B, Hc, Wc)
-        self.f(ops.conv3x3_fwd, planes, B, Ho, Wo, w, out.data, bias=bias, taps=taps, n_planes=4 * B, workspace=self.ws)
+        out.producer = self.f(ops.conv3x3_fwd, planes, B, Ho, Wo, w, out.data, bias=bias, taps=taps, n_planes=4 * B,
+                              workspace=self.ws)
 
         def bwd():
             g = out.grad
@@ -693,7 +725,8 @@ class Engine:
         x8 = Node(self.in_x8)
         x = self.node(M, boc[0])
         x.bias_names = ['conv_in.bias']
-        self.f(ops.conv3x3_fwd, x8.data, B, H, W, self.w_in16, x.data, bias=self.p32('conv_in.bias'), workspace=self.ws)
+        x.producer = self.f(ops.conv3x3_fwd, x8.data, B, H, W, self.w_in16, x.data, bias=self.p32('conv_in.bias'),
+                            workspace=self.ws)
         gw_in = self.buf(9, boc[0], 8, dtype=torch.float32)
         x0 = x  # `x` is rebound below; the closure must keep conv_in's own output node
 

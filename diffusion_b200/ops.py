@@ -182,9 +182,15 @@ def gemm_plans():
     return _PLANS
 
 
+def _gn_stats(d, gn_partial, gn_slab):
+    if gn_partial is not None:
+        d.gn_partial, d.gn_slab = gn_partial.data_ptr(), int(gn_slab)
+
+
 def linear_fwd(ctx, x, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, alpha=1.0, out_f32=False,
-               workspace=None, plan=None):
-    """out[M,N] = alpha * x[M,K] @ w[N,K]^T (+bias +rowbias +residual). x, w bf16 with unit inner stride."""
+               workspace=None, plan=None, gn_partial=None, gn_slab=32):
+    """out[M,N] = alpha * x[M,K] @ w[N,K]^T (+bias +rowbias +residual). x, w bf16 with unit inner stride.
+    gn_partial: fp32 [M / gn_slab, N, 2] receiving the GroupNorm partial statistics of `out` from the epilogue."""
     M, K = x.shape
     N = w.shape[0]
     d = L.GemmDesc()
@@ -193,6 +199,9 @@ def linear_fwd(ctx, x, w, out, bias=None, residual=None, rowbias=None, rows_per_
     d.B = _operand(w, 0, K, N, w.stride(0))
     _epilogue(d, out, out.stride(0), L.OUT_F32 if out_f32 else L.OUT_BF16, bias, rowbias, rows_per_group, residual,
               residual.stride(0) if residual is not None else 0, alpha, workspace)
+    _gn_stats(d, gn_partial, gn_slab)
+    if gn_partial is not None and plan is not None:
+        plan = (plan[0], 1)
     run_gemm(ctx, d, plan)
 
 
@@ -254,8 +263,9 @@ def taps_stride2_dgrad():
 
 
 def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None, taps=None, n_planes=None,
-                workspace=None, plan=None):
-    """x: bf16 [n_planes*H*W, Cin] NHWC; w9: bf16 [9, Cout, Cin]; out: bf16 [B*H*W, Cout]."""
+                workspace=None, plan=None, gn_partial=None, gn_slab=32):
+    """x: bf16 [n_planes*H*W, Cin] NHWC; w9: bf16 [9, Cout, Cin]; out: bf16 [B*H*W, Cout].
+    gn_partial: fp32 [B*H*W / gn_slab, Cout, 2] receiving the GroupNorm partial statistics of `out` from the epilogue."""
     Cin, Cout = x.shape[1], w9.shape[1]
     d = L.GemmDesc()
     d.kind, d.M, d.N, d.K, d.batch = L.GEMM_CONV, B * H * W, Cout, 9 * Cin, 1
@@ -263,6 +273,9 @@ def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None
     d.B = _operand(w9, 0, Cin, Cout, w9.stride(1), bs0=w9.stride(0))
     _epilogue(d, out, out.stride(0), L.OUT_BF16, bias, rowbias, H * W, residual,
               residual.stride(0) if residual is not None else 0, 1.0, workspace)
+    _gn_stats(d, gn_partial, gn_slab)
+    if gn_partial is not None and plan is not None:
+        plan = (plan[0], 1)
     run_gemm(ctx, d, plan)
 
 
@@ -315,6 +328,15 @@ def groupnorm_fwd(ctx, x, gamma, beta, y, stats, ws, B, HW, G, eps, silu):
     ctx.check(
         ctx.lib.sd2_groupnorm_fwd(ctx.h, _p(x), x.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0), _p(stats), _p(ws), B,
                                   HW, Cc, G, float(eps), int(silu), _s()))
+
+
+def groupnorm_fwd_fused(ctx, x, gn_partial, gn_slab, gamma, beta, y, stats, ws, B, HW, G, eps, silu):
+    """GroupNorm(+SiLU) of a tensor whose partial statistics the producing GEMM's epilogue wrote into gn_partial."""
+    Cc = x.shape[1]
+    assert x.stride(0) == Cc and y.stride(0) == Cc
+    ctx.check(
+        ctx.lib.sd2_groupnorm_fwd_fused(ctx.h, _p(x), _p(gn_partial), int(gn_slab), _p(gamma), _p(beta), _p(y), _p(stats),
+                                        _p(ws), B, HW, Cc, G, float(eps), int(silu), _s()))
 
 
 def groupnorm_bwd(ctx, dy, x, gamma, beta, stats, dx, dgamma, dbeta, ws, B, HW, G, silu, dx_add=None, drowsum=None,

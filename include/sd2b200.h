@@ -105,6 +105,11 @@ typedef struct sd2_gemm_desc {
   int max_splits;       /* 0 = auto */
   int force_bn;         /* 0 = planner decides; else the tile width (256/160/128/64) from a measured plan table */
   int force_splits;     /* 0 = planner decides; else the K-split count (clamped to what the workspace / K allow) */
+  /* GroupNorm statistics of the output, taken in the epilogue (SD2_OUT_BF16, single batch; disables split-K): per slab of
+   * gn_slab (16 or 32; must divide the pixels per image) consecutive rows and per column the sum and sum of squares of the
+   * stored values -> gn_partial[M / gn_slab][round8(N)][2] fp32.  Consumed by sd2_groupnorm_fwd_fused.  Null = off. */
+  float* gn_partial;
+  int gn_slab;
 } sd2_gemm_desc;
 
 int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream);
@@ -117,6 +122,12 @@ long long sd2_groupnorm_ws_floats(int B, int C);
 int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* gamma, const float* beta, void* y,
                       long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
                       sd2_stream stream);
+/* GroupNorm(+SiLU) of a tensor whose statistics were taken by the epilogue of the GEMM / conv that produced it
+ * (sd2_gemm_desc.gn_partial: [B*HW / slab][C][2]): combines the partials per (image, group), writes stats [B][G][2] and
+ * applies y = [silu]((x - mean) * rstd * gamma + beta) in one streaming pass - x crosses HBM once, no statistics pass. */
+int sd2_groupnorm_fwd_fused(sd2_ctx* ctx, const void* x, const float* gn_partial, int slab, const float* gamma,
+                            const float* beta, void* y, float* stats, float* ws, int B, int HW, int C, int G, float eps,
+                            int silu, sd2_stream stream);
 /* dx = d(loss)/dx (+ dx_add if non-null); dgamma/dbeta accumulated (+=) in fp32.
  * Optional column sums of the dx this call writes (it is then the complete output gradient of the conv / linear that
  * produced x, so these are that layer's bias gradients - no separate pass over dx): drowsum fp32 [B][C] overwritten with

@@ -146,6 +146,54 @@ def test_conv3x3_fwd(ctx, B, H, W, Cin, Cout):
     close(out, ref, name='conv fwd')
 
 
+@pytest.mark.parametrize('B,H,W,Cin,Cout,silu', [(4, 32, 32, 64, 320, 1), (3, 16, 16, 128, 640, 0), (9, 4, 4, 64, 1280, 1),
+                                                  (2, 8, 8, 320, 256, 1), (5, 16, 16, 64, 192, 1), (3, 4, 8, 64, 96, 0)])
+def test_groupnorm_statistics_from_the_conv_epilogue(ctx, B, H, W, Cin, Cout, silu):
+    """GroupNorm fused with its producer: the conv epilogue emits per-slab column sums of the bf16 tensor it stores, the norm
+    combines them and applies in one streaming pass.  Checked against F.group_norm of the stored conv output."""
+    from diffusion_b200 import ops
+    HW, M = H * W, B * H * W
+    x = bf(M, Cin, seed=1)
+    w9 = bf(9, Cout, Cin, scale=(9 * Cin)**-0.5, seed=2)
+    bias = torch.randn(Cout, device='cuda')
+    res = bf(M, Cout, seed=3)
+    out = torch.empty(M, Cout, dtype=torch.bfloat16, device='cuda')
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+    slab = 32 if HW % 32 == 0 else 16
+    part = torch.full((M // slab, Cout, 2), float('nan'), device='cuda')
+    ops.conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=bias, residual=res, workspace=ws, gn_partial=part, gn_slab=slab)
+    ref = conv_ref(x, w9, B, H, W) + bias[None, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(M, Cout) + res.float()
+    close(out, ref, name='conv fwd (with statistics)')
+    o32 = out.float().view(M // slab, slab, Cout)
+    close(part[..., 0], o32.sum(1), rtol=1e-4, atol=1e-3, name='epilogue column sums')
+    close(part[..., 1], (o32 * o32).sum(1), rtol=1e-4, atol=1e-3, name='epilogue column sums of squares')
+    G, eps = 32, 1e-5
+    gamma = torch.randn(Cout, device='cuda') * 0.2 + 1
+    beta = torch.randn(Cout, device='cuda') * 0.2
+    y = torch.empty_like(out)
+    stats = torch.empty(B, G, 2, device='cuda')
+    gws = ops.groupnorm_ws(ctx, B, Cout, out.device)
+    ops.groupnorm_fwd_fused(ctx, out, part, slab, gamma, beta, y, stats, gws, B, HW, G, eps, silu)
+    xr = out.float().view(B, HW, Cout).permute(0, 2, 1)
+    yr = F.group_norm(xr, G, gamma, beta, eps)
+    if silu:
+        yr = F.silu(yr)
+    close(y.view(B, HW, Cout), yr.permute(0, 2, 1), rtol=1e-2, atol=2e-2, name='fused gn fwd')
+    xg = xr.reshape(B, G, -1)
+    close(stats[..., 0], xg.mean(-1), rtol=1e-3, atol=1e-3, name='gn mean')
+    close(stats[..., 1], (xg.var(-1, unbiased=False) + eps).rsqrt(), rtol=2e-3, atol=1e-3, name='gn rstd')
+    # and through a linear layer's epilogue (proj_out -> next ResNet's norm1)
+    wl = bf(Cout, Cin, scale=Cin**-0.5, seed=7)
+    out2 = torch.empty(M, Cout, dtype=torch.bfloat16, device='cuda')
+    part2 = torch.full((M // slab, Cout, 2), float('nan'), device='cuda')
+    ops.linear_fwd(ctx, x, wl, out2, bias=bias, residual=res, workspace=ws, gn_partial=part2, gn_slab=slab)
+    o32 = out2.float().view(M // slab, slab, Cout)
+    close(out2, x.float() @ wl.float().t() + bias + res.float(), name='linear fwd (with statistics)')
+    close(part2[..., 0], o32.sum(1), rtol=1e-4, atol=1e-3, name='linear epilogue column sums')
+    close(part2[..., 1], (o32 * o32).sum(1), rtol=1e-4, atol=1e-3, name='linear epilogue column sums of squares')
+
+
 @pytest.mark.parametrize('B,H,W,Cin,Cout', CONV_SHAPES)
 def test_conv3x3_dgrad_wgrad(ctx, B, H, W, Cin, Cout):
     from diffusion_b200 import ops
