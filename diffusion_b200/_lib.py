@@ -123,6 +123,7 @@ SIGNATURES = {
     'sd2_gemm': (_i, [_vp, C.POINTER(GemmDesc), _vp]),
     'sd2_groupnorm_ws_floats': (_ll, [_i, _i]),
     'sd2_groupnorm_fwd': (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'sd2_concat_stats': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'sd2_groupnorm_fwd_fused': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'sd2_groupnorm_bwd': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _i, _i, _i,
                                _i, _i, _vp, _vp, _vp, _vp]),

@@ -363,6 +363,46 @@ __global__ void __launch_bounds__(256) gn_colsum_finalize_kernel(const float* __
   }
 }
 
+// ---- skip concatenation that also takes the GroupNorm statistics of what it writes
+// out[row] = [a[row] | b[row]] (the up-path torch.cat of the running tensor and the skip); the kernel streams both halves
+// anyway, so it accumulates per column the sum and sum of squares of its pixel chunk: part[(img * P + p)][Ca + Cb][2].
+// The norm1 behind it (fused path, slab = HW / P) then needs no statistics pass.  grid (P, B), block GN_THREADS.
+__global__ void __launch_bounds__(GN_THREADS, 2) concat_stats_kernel(const bf16* __restrict__ a, long long lda,
+                                                                   const bf16* __restrict__ bsrc, long long ldb,
+                                                                   bf16* __restrict__ out, float* __restrict__ part, int HW,
+                                                                   int Ca, int Cb) {
+  pdl_grid_sync();
+  extern __shared__ float sm[];  // [R][C][2] + [C][2]
+  const int P = gridDim.x, p = blockIdx.x, b = blockIdx.y;
+  const int C = Ca + Cb, V = C / 8, Va = Ca / 8, R = GN_THREADS / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  const int row0 = (int)((long long)p * HW / P), row1 = (int)((long long)(p + 1) * HW / P);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  if (r < R) {
+    const bf16* src = v < Va ? a + ((long long)b * HW) * lda + v * 8 : bsrc + ((long long)b * HW) * ldb + (v - Va) * 8;
+    const long long lds = v < Va ? lda : ldb;
+    bf16* dst = out + ((long long)b * HW) * C + v * 8;
+#pragma unroll 4
+    for (int row = row0 + r; row < row1; row += R) {
+      const uint4 u = ldg_stream16(src + (long long)row * lds);
+      *reinterpret_cast<uint4*>(dst + (long long)row * C) = u;
+      const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+      const float f[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += f[e];
+        q[e] = fmaf(f[e], f[e], q[e]);
+      }
+    }
+  }
+  gn_block_reduce(sm, s, q, C, R, v, r);
+  const float* red = sm + (size_t)R * C * 2;
+  float* o = part + (((long long)b * P + p) * C) * 2;
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) o[i] = red[i];
+}
+
 // ---- GroupNorm forward on statistics taken by the producing GEMM's epilogue (gemm_tc.cu::epi_gn_stats)
 // part[slab][C][2] = (sum, sum of squares) of every column over `slab` consecutive rows; NS = HW / slab slabs per image.
 // grid (B), block 256: one warp per group (round-robin), lanes over (slab, channel of the group) -> stats[b][g] = (mean, rstd)
@@ -1221,13 +1261,34 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
   return check_launch(ctx, "groupnorm_fwd", 2);
 }
 
+int sd2_concat_stats(sd2_ctx* ctx, const void* a, long long lda, const void* b, long long ldb, void* out, float* part, int B,
+                     int HW, int Ca, int Cb, int P, sd2_stream stream_) {
+  if (!ctx) return 1;
+  const int C = Ca + Cb;
+  if (Ca % 8 || Cb % 8 || lda % 8 || ldb % 8 || C / 8 > GN_THREADS) return fail(ctx, "sd2_concat_stats: channel counts / strides % 8");
+  if (P < 1 || P > GN_MAXP || HW % P != 0) return fail(ctx, "sd2_concat_stats: P must divide HW (1..64)");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const size_t smem = ((size_t)(GN_THREADS / (C / 8)) * C * 2 + (size_t)C * 2) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool opted = false;
+    if (!opted) {
+      if (cudaFuncSetAttribute(concat_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        return fail(ctx, "sd2_concat_stats: cannot raise the shared-memory limit");
+      opted = true;
+    }
+  }
+  launch_k(concat_stats_kernel, dim3(P, B), dim3(GN_THREADS), smem, stream, reinterpret_cast<const bf16*>(a), lda,
+           reinterpret_cast<const bf16*>(b), ldb, reinterpret_cast<bf16*>(out), part, HW, Ca, Cb);
+  return check_launch(ctx, "concat_stats");
+}
+
 int sd2_groupnorm_fwd_fused(sd2_ctx* ctx, const void* x, const float* gn_partial, int slab, const float* gamma,
                             const float* beta, void* y, float* stats, float* ws, int B, int HW, int C, int G, float eps,
                             int silu, sd2_stream stream_) {
   if (!ctx) return 1;
   (void)ws;
   if (C % 8 != 0 || C % G != 0 || G > 64 || C / 8 > GN_THREADS) return fail(ctx, "sd2_groupnorm_fwd_fused: unsupported C/G");
-  if ((slab != 16 && slab != 32) || HW % slab != 0) return fail(ctx, "sd2_groupnorm_fwd_fused: slab must be 16 or 32 and divide HW");
+  if (slab < 1 || HW % slab != 0) return fail(ctx, "sd2_groupnorm_fwd_fused: slab must divide HW");
   if (!gn_partial) return fail(ctx, "sd2_groupnorm_fwd_fused: no partial statistics");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   launch_k(gn_part_finalize_kernel, dim3(B), dim3(256), 0, stream, gn_partial, stats, HW / slab, HW, C, G, eps);

@@ -37,7 +37,7 @@ _OP_WRITES = {
     'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_fwd_fused': ((5, 6, 7), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ('drowsum', 'dcolsum', 'dcolsum2')),
     'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ('dcolsum',)),
     'geglu_fwd': ((1,), ()), 'geglu_bwd': ((2,), ('dbias',)), 'silu_fwd': ((1,), ()), 'silu_bwd': ((2,), ()),
-    'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
+    'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'concat_stats': ((2, 3), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
     'phase_split': ((1,), ()), 'phase_merge': ((1,), ()), 'colsum': ((1,), ()), 'cast_f32_to_bf16': ((1,), ()),
     'pad_cast_rows': ((2,), ()), 'unpad_accum_rows': ((2,), ()), 'fill_f32': ((0,), ()),
 }
@@ -78,7 +78,7 @@ def _overlap(xs, ys):
 class Node:
     """An activation [M, C] (bf16) with its lazily allocated gradient buffer."""
     __slots__ = ('data', 'grad', 'gw', 'M', 'C', 'writes', 'last_writer', 'writes_at_norm', 'reads', 'bias_names', 'rowsum',
-                 'claimed', 'producer')
+                 'claimed', 'producer', 'gn_part')
 
     def __init__(self, data):
         self.data, self.grad, self.gw = data, None, False
@@ -94,6 +94,7 @@ class Node:
         # the recorded forward GEMM / conv op (a functools.partial) that writes this node as a whole bf16 tensor: a GroupNorm
         # that consumes the node asks that op's epilogue for the statistics (Engine.groupnorm)
         self.producer = None
+        self.gn_part = None  # (partials, slab) when the op that wrote this node already took the GroupNorm statistics
 
 
 def _align(n, a=64):
@@ -409,6 +410,11 @@ class Engine:
         # fused: concatenations have no producing GEMM)
         return (self.B * self.H * self.W // 16) * self.cfg['block_out_channels'][0] * 2
 
+    def _gn_scratch(self, need):
+        if self.gn_part is None or self.gn_part.numel() < need:
+            self.gn_part = torch.empty(max(need, self._gn_part_floats()), dtype=torch.float32, device=self.dev)
+        return self.gn_part[:need]
+
     def _use(self, *nodes):
         for n in nodes:
             if n is not None:
@@ -435,18 +441,21 @@ class Engine:
         # GroupNorm fused with the producing conv / linear: that op's epilogue takes the per-slab column sums of the tensor it
         # writes, this norm only combines them and streams the apply(+SiLU) pass (north_star: GroupNorm in the conv epilogue)
         slab = 32 if HW % 32 == 0 else (16 if HW % 16 == 0 else 0)
-        fuse = x.producer is not None and slab and 'gn_partial' not in x.producer.keywords and self.fuse_gn_stats
-        if fuse:  # the statistics scratch is shared: nothing recorded since the producer may write it
+        fused_args = None
+        if x.gn_part is not None and self.fwd and self.fwd[-1].func is ops.concat_stats:
+            fused_args = x.gn_part  # the skip concatenation recorded right before this norm took the statistics
+        elif x.producer is not None and slab and 'gn_partial' not in x.producer.keywords and self.fuse_gn_stats:
+            # the statistics scratch is shared: nothing recorded since the producer may write it
             at = next(i for i in range(len(self.fwd) - 1, -1, -1) if self.fwd[i] is x.producer)
-            fuse = not any('gn_partial' in op.keywords for op in self.fwd[at + 1:])
-        if fuse:
-            need = (x.M // slab) * x.C * 2
-            if self.gn_part is None or self.gn_part.numel() < need:
-                self.gn_part = torch.empty(max(need, self._gn_part_floats()), dtype=torch.float32, device=self.dev)
-            part = self.gn_part[:need].view(x.M // slab, x.C, 2)
-            x.producer.keywords['gn_partial'] = part
-            x.producer.keywords['gn_slab'] = slab
-            self.f(ops.groupnorm_fwd_fused, x.data, part, slab, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
+            if not any('gn_partial' in op.keywords or op.func is ops.concat_stats for op in self.fwd[at + 1:]):
+                need = (x.M // slab) * x.C * 2
+                part = self._gn_scratch(need).view(x.M // slab, x.C, 2)
+                x.producer.keywords['gn_partial'] = part
+                x.producer.keywords['gn_slab'] = slab
+                fused_args = (part, slab)
+        if fused_args is not None:
+            self.f(ops.groupnorm_fwd_fused, x.data, fused_args[0], fused_args[1], gamma, beta, y.data, stats, self.gn_ws, self.B,
+                   HW, self.G, eps, silu)
         else:
             self.f(ops.groupnorm_fwd, x.data, gamma, beta, y.data, stats, self.gn_ws, self.B, HW, self.G, eps, silu)
 
@@ -577,8 +586,18 @@ class Engine:
     def concat(self, a, b_):
         out = self.node(a.M, a.C + b_.C)
         self._use(a, b_)
-        self.f(ops.copy2d, a.data, out.data[:, :a.C], a.M, a.C)
-        self.f(ops.copy2d, b_.data, out.data[:, a.C:], a.M, b_.C)
+        HW = a.M // self.B
+        if self.fuse_gn_stats and (a.C + b_.C) // 8 <= 512:
+            # one kernel copies both halves and takes the GroupNorm statistics of the result (its consumer is a ResNet norm1)
+            P = 1
+            while self.B * P < 4 * self.ctx.num_sms and P * 2 <= max(1, HW // 16) and P < 64:
+                P *= 2
+            part = self._gn_scratch(self.B * P * out.C * 2).view(self.B * P, out.C, 2)
+            self.f(ops.concat_stats, a.data, b_.data, out.data, part, self.B, HW, P)
+            out.gn_part = (part, HW // P)
+        else:
+            self.f(ops.copy2d, a.data, out.data[:, :a.C], a.M, a.C)
+            self.f(ops.copy2d, b_.data, out.data[:, a.C:], a.M, b_.C)
 
         def bwd():
             assert out.gw

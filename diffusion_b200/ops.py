@@ -330,6 +330,12 @@ def groupnorm_fwd(ctx, x, gamma, beta, y, stats, ws, B, HW, G, eps, silu):
                                   HW, Cc, G, float(eps), int(silu), _s()))
 
 
+def concat_stats(ctx, a, b, out, part, B, HW, P):
+    """out = [a | b] along channels + GroupNorm partial statistics of out over P pixel chunks per image (see sd2b200.h)."""
+    ctx.check(ctx.lib.sd2_concat_stats(ctx.h, _p(a), a.stride(0), _p(b), b.stride(0), _p(out), _p(part), B, HW, a.shape[1],
+                                       b.shape[1], int(P), _s()))
+
+
 def groupnorm_fwd_fused(ctx, x, gn_partial, gn_slab, gamma, beta, y, stats, ws, B, HW, G, eps, silu):
     """GroupNorm(+SiLU) of a tensor whose partial statistics the producing GEMM's epilogue wrote into gn_partial."""
     Cc = x.shape[1]

@@ -123,8 +123,13 @@ int sd2_groupnorm_fwd(sd2_ctx* ctx, const void* x, long long ldx, const float* g
                       long long ldy, float* stats, float* ws, int B, int HW, int C, int G, float eps, int silu,
                       sd2_stream stream);
 /* GroupNorm(+SiLU) of a tensor whose statistics were taken by the epilogue of the GEMM / conv that produced it
- * (sd2_gemm_desc.gn_partial: [B*HW / slab][C][2]): combines the partials per (image, group), writes stats [B][G][2] and
+ * (sd2_gemm_desc.gn_partial: [B*HW / slab][C][2]; slab = any divisor of HW) or by sd2_concat_stats: combines the partials per (image, group), writes stats [B][G][2] and
  * applies y = [silu]((x - mean) * rstd * gamma + beta) in one streaming pass - x crosses HBM once, no statistics pass. */
+/* Skip concatenation out[B*HW][Ca+Cb] = [a | b] (diffusers' torch.cat in the up blocks) that also takes the GroupNorm
+ * partial statistics of what it writes: part[(image * P + chunk)][Ca+Cb][2] over P pixel chunks per image (P divides HW);
+ * feed them to sd2_groupnorm_fwd_fused with slab = HW / P. */
+int sd2_concat_stats(sd2_ctx* ctx, const void* a, long long lda, const void* b, long long ldb, void* out, float* part, int B,
+                     int HW, int Ca, int Cb, int P, sd2_stream stream);
 int sd2_groupnorm_fwd_fused(sd2_ctx* ctx, const void* x, const float* gn_partial, int slab, const float* gamma,
                             const float* beta, void* y, float* stats, float* ws, int B, int HW, int C, int G, float eps,
                             int silu, sd2_stream stream);

@@ -196,9 +196,9 @@ def test_schedule_builds_and_covers_every_parameter(dry, cfg, B, R):
     eng.run_forward()
     eng.run_backward()
     calls = eng.ctx.lib.calls
-    # 61 GroupNorms: the 49 whose input a conv / linear epilogue produces take their statistics from that epilogue, the 12
-    # that read a skip concatenation (norm1 of the up-path ResNets) run the stand-alone kernel
-    assert calls['sd2_groupnorm_fwd_fused'] == 49 and calls['sd2_groupnorm_fwd'] == 12
+    # 61 GroupNorms, none with a statistics pass of its own: 49 get them from the epilogue of the conv / linear that produced
+    # their input, the 12 that read a skip concatenation (norm1 of the up-path ResNets) from the concatenation kernel
+    assert calls['sd2_groupnorm_fwd_fused'] == 61 and calls['sd2_concat_stats'] == 12 and 'sd2_groupnorm_fwd' not in calls
     assert calls['sd2_layernorm_fwd'] == 48 and calls['sd2_attn_fwd'] == 32 and calls['sd2_attn_bwd'] == 32
     # buckets tile the arena exactly, in completion order
     lo = sorted(b[0] for b in eng.buckets)

@@ -194,6 +194,30 @@ def test_groupnorm_statistics_from_the_conv_epilogue(ctx, B, H, W, Cin, Cout, si
     close(part2[..., 1], (o32 * o32).sum(1), rtol=1e-4, atol=1e-3, name='linear epilogue column sums of squares')
 
 
+@pytest.mark.parametrize('B,HW,Ca,Cb,P', [(4, 1024, 320, 320, 8), (3, 256, 640, 320, 4), (9, 16, 1280, 1280, 1), (2, 64, 64, 128, 2),
+                                          (5, 4, 128, 64, 1)])
+def test_concat_with_groupnorm_statistics(ctx, B, HW, Ca, Cb, P):
+    from diffusion_b200 import ops
+    a, b = bf(B * HW, Ca, seed=1), bf(B * HW, Cb, seed=2)
+    Cc = Ca + Cb
+    out = torch.empty(B * HW, Cc, dtype=torch.bfloat16, device='cuda')
+    part = torch.full((B * P, Cc, 2), float('nan'), device='cuda')
+    ops.concat_stats(ctx, a, b, out, part, B, HW, P)
+    ref = torch.cat([a, b], 1)
+    assert torch.equal(out, ref)
+    o32 = ref.float().view(B * P, HW // P, Cc)
+    close(part[..., 0], o32.sum(1), rtol=1e-4, atol=1e-3, name='concat column sums')
+    close(part[..., 1], (o32 * o32).sum(1), rtol=1e-4, atol=1e-3, name='concat column sums of squares')
+    G, eps = 32, 1e-5
+    gamma = torch.randn(Cc, device='cuda') * 0.2 + 1
+    beta = torch.randn(Cc, device='cuda') * 0.2
+    y = torch.empty_like(out)
+    stats = torch.empty(B, G, 2, device='cuda')
+    ops.groupnorm_fwd_fused(ctx, out, part, HW // P, gamma, beta, y, stats, ops.groupnorm_ws(ctx, B, Cc, out.device), B, HW, G, eps, 1)
+    yr = F.silu(F.group_norm(ref.float().view(B, HW, Cc).permute(0, 2, 1), G, gamma, beta, eps))
+    close(y.view(B, HW, Cc), yr.permute(0, 2, 1), rtol=1e-2, atol=2e-2, name='gn fwd on concat statistics')
+
+
 @pytest.mark.parametrize('B,H,W,Cin,Cout', CONV_SHAPES)
 def test_conv3x3_dgrad_wgrad(ctx, B, H, W, Cin, Cout):
     from diffusion_b200 import ops
