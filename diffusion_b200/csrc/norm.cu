@@ -325,13 +325,69 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_apply_kernel(const bf16*
   }
 }
 
-// Column sums emitted by the GroupNorm backward -> their consumers.  cs_ws[b*NP + i][C] (NP partial slabs per image):
-//   rowsum[b][c]  = sum_i cs_ws[b*NP+i][c]                 (overwritten; per-image sums = gradient of a per-image bias)
-//   dcs1/dcs2[c] += sum_b rowsum[b][c]                     (bias gradients)
+// Per-CTA partials of the GroupNorm backward -> their consumers, one launch.  Slab i = b*NP + r (NP partial slabs per image):
+//   dbeta[c] += sum_i ws[i][c][0],  dgamma[c] += sum_i ws[i][c][1]                    (affine gradients)
+//   rowsum[b][c]  = sum_r cs_ws[b*NP+r][c]   (overwritten; per-image column sums of dx = gradient of a per-image bias)
+//   dcs1/dcs2[c] += sum_b rowsum[b][c]       (bias gradients of the conv / linear that produced the norm's input)
 // grid (ceil(C/32), slices over images), block (32 channels, 8 image lanes).
-__global__ void __launch_bounds__(256) gn_colsum_finalize_kernel(const float* __restrict__ cs_ws, int B, int NP, int C,
-                                                                 float* __restrict__ rowsum, float* __restrict__ dcs1,
-                                                                 float* __restrict__ dcs2) {
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ cs_ws, int B,
+                                                              int NP, int C, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              float* __restrict__ rowsum, float* __restrict__ dcs1,
+                                                              float* __restrict__ dcs2) {
+  pdl_grid_sync();
+  __shared__ float sm[8][32][3];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float tot = 0.f, a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    for (int b = blockIdx.y * 8 + pl; b < B; b += 8 * gridDim.y) {
+      const float* src = cs_ws + ((long long)b * NP) * C + c;
+      const float* aff = ws + (((long long)b * NP) * C + c) * 2;
+      float t = 0.f;
+      int i = 0;
+      for (; i + 3 < NP; i += 4) {
+        const float t0 = src[(long long)i * C], t1 = src[(long long)(i + 1) * C], t2 = src[(long long)(i + 2) * C],
+                    t3 = src[(long long)(i + 3) * C];
+        const float2 g0 = *reinterpret_cast<const float2*>(aff + (long long)i * C * 2),
+                     g1 = *reinterpret_cast<const float2*>(aff + (long long)(i + 1) * C * 2),
+                     g2 = *reinterpret_cast<const float2*>(aff + (long long)(i + 2) * C * 2),
+                     g3 = *reinterpret_cast<const float2*>(aff + (long long)(i + 3) * C * 2);
+        t += (t0 + t1) + (t2 + t3);
+        a1 += (g0.x + g1.x) + (g2.x + g3.x);
+        a2 += (g0.y + g1.y) + (g2.y + g3.y);
+      }
+      for (; i < NP; ++i) {
+        t += src[(long long)i * C];
+        const float2 g = *reinterpret_cast<const float2*>(aff + (long long)i * C * 2);
+        a1 += g.x;
+        a2 += g.y;
+      }
+      if (rowsum != nullptr) rowsum[(long long)b * C + c] = t;
+      tot += t;
+    }
+  }
+  sm[pl][cl][0] = tot;
+  sm[pl][cl][1] = a1;
+  sm[pl][cl][2] = a2;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      tot += sm[j][cl][0];
+      a1 += sm[j][cl][1];
+      a2 += sm[j][cl][2];
+    }
+    atomicAdd(&dbeta[c], a1);
+    atomicAdd(&dgamma[c], a2);
+    if (dcs1 != nullptr) atomicAdd(&dcs1[c], tot);
+    if (dcs2 != nullptr) atomicAdd(&dcs2[c], tot);
+  }
+}
+
+// column sums only (two-pass fallback path: the affine gradients are produced by gn_bwd_reduce_kernel there)
+__global__ void __launch_bounds__(256) gn_colsum_only_kernel(const float* __restrict__ cs_ws, int B, int NP, int C,
+                                                             float* __restrict__ rowsum, float* __restrict__ dcs1,
+                                                             float* __restrict__ dcs2) {
   pdl_grid_sync();
   __shared__ float sm[8][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -341,13 +397,7 @@ __global__ void __launch_bounds__(256) gn_colsum_finalize_kernel(const float* __
     for (int b = blockIdx.y * 8 + pl; b < B; b += 8 * gridDim.y) {
       const float* src = cs_ws + ((long long)b * NP) * C + c;
       float t = 0.f;
-      int i = 0;
-      for (; i + 3 < NP; i += 4) {
-        const float t0 = src[(long long)i * C], t1 = src[(long long)(i + 1) * C], t2 = src[(long long)(i + 2) * C],
-                    t3 = src[(long long)(i + 3) * C];
-        t += (t0 + t1) + (t2 + t3);
-      }
-      for (; i < NP; ++i) t += src[(long long)i * C];
+      for (int i = 0; i < NP; ++i) t += src[(long long)i * C];
       if (rowsum != nullptr) rowsum[(long long)b * C + c] = t;
       tot += t;
     }
@@ -405,7 +455,7 @@ __global__ void __launch_bounds__(GN_THREADS, 2) concat_stats_kernel(const bf16*
 
 // ---- GroupNorm forward on statistics taken by the producing GEMM's epilogue (gemm_tc.cu::epi_gn_stats)
 // part[slab][C][2] = (sum, sum of squares) of every column over `slab` consecutive rows; NS = HW / slab slabs per image.
-// grid (B), block 256: one warp per group (round-robin), lanes over (slab, channel of the group) -> stats[b][g] = (mean, rstd)
+// grid (B, ceil(G / 8)), block 256: one warp per group, lanes over (slab, channel of the group) -> stats[b][g] = (mean, rstd)
 __global__ void __launch_bounds__(256) gn_part_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int NS,
                                                                int HW, int C, int G, float eps) {
   pdl_grid_sync();
@@ -413,7 +463,7 @@ __global__ void __launch_bounds__(256) gn_part_finalize_kernel(const float* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* pb = part + (long long)b * NS * C * 2;
   const int n = NS * cpg;
-  for (int g = warp; g < G; g += 8) {
+  for (int g = blockIdx.y * 8 + warp; g < G; g += 8 * gridDim.y) {
     float s = 0.f, q = 0.f;
     for (int i = lane; i < n; i += 32) {
       const int sl = i / cpg, cl = i % cpg;
@@ -1291,7 +1341,7 @@ int sd2_groupnorm_fwd_fused(sd2_ctx* ctx, const void* x, const float* gn_partial
   if (slab < 1 || HW % slab != 0) return fail(ctx, "sd2_groupnorm_fwd_fused: slab must divide HW");
   if (!gn_partial) return fail(ctx, "sd2_groupnorm_fwd_fused: no partial statistics");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  launch_k(gn_part_finalize_kernel, dim3(B), dim3(256), 0, stream, gn_partial, stats, HW / slab, HW, C, G, eps);
+  launch_k(gn_part_finalize_kernel, dim3(B, (G + 7) / 8), dim3(256), 0, stream, gn_partial, stats, HW / slab, HW, C, G, eps);
   // enough blocks for ~4 per SM; every thread keeps >= 4 rows in flight
   const int R = GN_THREADS / (C / 8);
   int P = (4 * ctx->num_sms + B - 1) / B;
@@ -1327,10 +1377,12 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
       else if (ap) e = launch_gn_bwd_cluster<false, true>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, cs_ws, HW, C, G);
       else e = launch_gn_bwd_cluster<false, false>(cc, B, stream, dyp, xp, gamma, beta, stats, ap, dxp, ws, cs_ws, HW, C, G);
       if (e != cudaSuccess) return fail(ctx, std::string("sd2_groupnorm_bwd (cluster): ") + cudaGetErrorString(e));
-      launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(B * cc.NC)), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta, nullptr, nullptr);
-      if (emit)
-        launch_k(gn_colsum_finalize_kernel, fin_grid, dim3(256), 0, stream, (const float*)cs_ws, B, cc.NC, C, drowsum, dcolsum1, dcolsum2);
-      return check_launch(ctx, "groupnorm_bwd", emit ? 3 : 2);
+      if (emit)  // affine gradients + the column sums of dx, one launch
+        launch_k(gn_bwd_finalize_kernel, fin_grid, dim3(256), 0, stream, (const float*)ws, (const float*)cs_ws, B, cc.NC, C, dgamma,
+                 dbeta, drowsum, dcolsum1, dcolsum2);
+      else
+        launch_k(affine_grad_reduce_kernel, dim3((C + 31) / 32, affine_slices(B * cc.NC)), dim3(256), 0, stream, ws, B * cc.NC, C, dgamma, dbeta, nullptr, nullptr);
+      return check_launch(ctx, "groupnorm_bwd", 2);
     }
   }
   const int P = gn_chunks(HW, B, C, ctx->num_sms);
@@ -1363,7 +1415,7 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
                                                        reinterpret_cast<const bf16*>(dx_add), ldadd,
                                                        reinterpret_cast<bf16*>(dx), lddx, cs_ws, HW, C, G, silu);
   if (emit)
-    launch_k(gn_colsum_finalize_kernel, fin_grid, dim3(256), 0, stream, (const float*)cs_ws, B, P, C, drowsum, dcolsum1, dcolsum2);
+    launch_k(gn_colsum_only_kernel, fin_grid, dim3(256), 0, stream, (const float*)cs_ws, B, P, C, drowsum, dcolsum1, dcolsum2);
   return check_launch(ctx, "groupnorm_bwd", emit ? 4 : 3);
 }
 
