@@ -96,7 +96,9 @@ class GemmDesc(C.Structure):
                 ('residual', C.c_void_p), ('ldr', C.c_longlong), ('bias', C.c_void_p), ('rowbias', C.c_void_p),
                 ('rows_per_group', C.c_int), ('ld_rowbias', C.c_longlong), ('alpha', C.c_float),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_longlong), ('max_splits', C.c_int), ('force_bn', C.c_int),
-                ('force_splits', C.c_int), ('gn_partial', C.c_void_p), ('gn_slab', C.c_int)]
+                ('force_splits', C.c_int), ('gn_partial', C.c_void_p), ('gn_slab', C.c_int),
+                ('mse_target', C.c_void_p), ('mse_dpred8', C.c_void_p), ('mse_acc', C.c_void_p), ('mse_dtype', C.c_int),
+                ('mse_hw', C.c_int)]
 
 
 GEMM_PLAIN, GEMM_CONV, GEMM_CONV_WGRAD = 0, 1, 2

@@ -218,6 +218,21 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
   p.out_nb0 = d->out_nb0 > 0 ? d->out_nb0 : 1;
   p.out_bs0 = d->out_bs0;
   p.out_bs1 = d->out_bs1;
+  const bool mse = d->mse_target != nullptr;
+  if (mse) {
+    if (d->kind != SD2_GEMM_CONV || d->out_mode != SD2_OUT_BF16 || d->N > 8 || d->N < 4)
+      return fail(ctx, "sd2_gemm: the MSE head belongs to a bf16 convolution with 4..8 output columns (conv_out)");
+    if (!d->mse_dpred8 || !d->mse_acc || d->mse_hw < 1 || d->M % d->mse_hw != 0)
+      return fail(ctx, "sd2_gemm: MSE head needs mse_dpred8, mse_acc and mse_hw dividing M");
+    if (d->mse_dtype != SD2_DT_F32 && d->mse_dtype != SD2_DT_BF16 && d->mse_dtype != SD2_DT_F16)
+      return fail(ctx, "sd2_gemm: mse_dtype");
+    p.mse_target = d->mse_target;
+    p.mse_dpred8 = reinterpret_cast<bf16*>(d->mse_dpred8);
+    p.mse_acc = d->mse_acc;
+    p.mse_dtype = d->mse_dtype;
+    p.mse_hw = d->mse_hw;
+    p.mse_k = 2.f / ((float)d->M * 4.f);
+  }
   const bool gn = d->gn_partial != nullptr;
   if (gn) {
     if (d->out_mode != SD2_OUT_BF16) return fail(ctx, "sd2_gemm: gn_partial needs a bf16 output");
@@ -252,7 +267,7 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     }
     if (kb < 1 || nbatch < 1) return fail(ctx, "sd2_gemm: empty contraction / batch");
     sd2_gemm_desc dd = *d;
-    if (gn) dd.max_splits = 1;  // the statistics come from the epilogue that writes the final values
+    if (gn || mse) dd.max_splits = 1;  // the statistics / the loss come from the epilogue that writes the final values
     plan_gemm(ctx, &dd, p.N, kb, nbatch, bmn, direct_store, &BN, &splits);
     // measured plan (tools/autotune_gemm.py -> diffusion_b200/gemm_plans.json) overrides the cycle model
     if (d->force_bn == 256 || d->force_bn == 128 || d->force_bn == 64 || (d->force_bn == 160 && !bmn)) BN = d->force_bn;
@@ -268,7 +283,8 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
       if (smax < 1) smax = 1;
       splits = d->force_splits < smax ? d->force_splits : (int)smax;
     }
-    if (gn) splits = 1;
+    if (gn || mse) splits = 1;
+    if (mse) BN = 64;
   }
 
   // 2-CTA clusters sharing the B tile through TMA multicast: decided before the tensor maps are built, because a K-major B

@@ -92,6 +92,8 @@ struct EpiTile {  // per work item, per thread (thread = one output row of the 3
   float bv[8];      // bias of tile columns lane*8 .. lane*8+7
   float* gn_part;   // GroupNorm partial sums of the output (or null), see GemmKParams
   int gn_slab;
+  long long row;    // this thread's output row
+  bool row_ok;
 };
 struct EpiPre {  // residual of one 32-column chunk, fetched one chunk ahead (the per-image bias rows are tiny and
   uint4 rs[4];    // L1-resident: they are read in place)
@@ -168,10 +170,16 @@ __device__ __forceinline__ void epi_gn_stats(const EpiTile& t, uint32_t buf_s, i
   }
 }
 
+__device__ __forceinline__ float mse_target_at(const void* tgt, int dtype, long long i) {
+  if (dtype == SD2_DT_F32) return reinterpret_cast<const float*>(tgt)[i];
+  if (dtype == SD2_DT_BF16) return __bfloat162float(reinterpret_cast<const bf16*>(tgt)[i]);
+  return __half2float(reinterpret_cast<const __half*>(tgt)[i]);
+}
+
 template <int BN>
 __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c, const EpiPre& cur, EpiPre& nxt,
                                           uint32_t t_addr, uint8_t* stg, int lane, const CUtensorMap* tmO,
-                                          uint64_t* tmem_empty) {
+                                          uint64_t* tmem_empty, const GemmKParams& p) {
   constexpr int OUT_CH = (BN % 128 == 0) ? 64 : 32;
   const bool f32_out = t.out_mode != OUT_BF16;
   uint32_t r[32];
@@ -212,6 +220,30 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
         v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
         v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
       }
+    }
+    if (BN == 64 && p.mse_target != nullptr && g == 0 && n_base == 0) {
+      // MSE head (conv_out): columns 0..3 of this row are the prediction of one pixel; compare the bf16-rounded values (the
+      // stored tensor, what F.mse_loss would read) with the target noise
+      float sq = 0.f;
+      if (t.row_ok) {
+        const long long b = t.row / p.mse_hw, hw = t.row % p.mse_hw;
+        float d[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float pr = __bfloat162float(__float2bfloat16_rn(v[ch]));
+          const float diff = pr - mse_target_at(p.mse_target, p.mse_dtype, (b * 4 + ch) * p.mse_hw + hw);
+          sq = fmaf(diff, diff, sq);
+          d[ch] = p.mse_k * diff;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(d[0], d[1]);
+        o.y = pack_bf16x2(d[2], d[3]);
+        o.z = 0u;
+        o.w = 0u;
+        *reinterpret_cast<uint4*>(p.mse_dpred8 + t.row * 8) = o;
+      }
+      sq = warp_sum(sq);
+      if (lane == 0) atomicAdd(p.mse_acc, sq);
     }
     if (new_buf && !waited) {  // the staging buffer was handed to the copy engine by the previous store of this warp
       if (lane == 0) bulk_wait_read<0>();
@@ -316,6 +348,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     constexpr int BH = BN / 2;                          // rows of B this CTA fetches for the cluster (K-major B)
     constexpr int NCH = BN / 64, NCH_CL = NCH / CL;     // 64-wide chunks of an MN-major B tile: all / per CTA
     const int j0 = crank * NCH_CL;
+    bool first_tile = true;
     for (int item = unit0; item < n_items; item += unit_step) {
       WorkItem w = decode_item(p, item, mtd);
       if (CL == 2) w.m_tile = 2 * w.m_tile + crank;
@@ -360,7 +393,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* a_dst = smem + (size_t)s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
           uint64_t* fb = &full_bar[s];
-          mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+          const bool load_b = CL == 2 || !p.b_resident || first_tile;  // B-resident: the weight tile is already in this stage
+          mbar_arrive_expect_tx(fb, load_b ? Cfg::STAGE_BYTES : A_BYTES);
           if (p.kind == KIND_CONV) {
             tma_load_4d(a_dst, &tmA, fb, cb * 64, cw0 + dw, ch0 + dh, cn0 + dn);
             if (CL == 2) {  // this CTA's half of the B tile, multicast to both CTAs of the cluster
@@ -384,7 +418,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
               for (int j = 0; j < 2; ++j) tma_load_4d(a_dst + j * CHUNK_BYTES, &tmA, fb, m_off + 64 * j, kcol, ab0, ab1);
             }
-            if (p.kind == KIND_PLAIN) {
+            if (p.kind == KIND_PLAIN && load_b) {
               if (CL == 2) {
                 if (!B_MN) {
                   tma_load_4d_mc(b_dst + crank * (BH * 128), &tmB, fb, kcol, n_off + crank * BH, bb0, bb1, 3);
@@ -399,7 +433,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) tma_load_4d(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * j, kcol, bb0, bb1);
               }
-            } else if (B_MN) {  // KIND_CONV_WGRAD: B = activations shifted by the tap, k-block = 64 pixels
+            } else if (p.kind != KIND_PLAIN && B_MN) {  // KIND_CONV_WGRAD: B = activations shifted by the tap, k-block = 64 pixels
               if (CL == 2) {
 #pragma unroll
                 for (int j = 0; j < NCH_CL; ++j)
@@ -442,6 +476,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           ph ^= 1u;
         }
       }
+      first_tile = false;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -532,6 +567,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       t.out_mode = p.out_mode;
       t.gn_part = p.gn_part;
       t.gn_slab = p.gn_slab;
+      t.row = row;
+      t.row_ok = row_ok;
 #pragma unroll
       for (int e = 0; e < 8; ++e) t.bv[e] = 0.f;
       if (t.has_bias && lane * 8 < BN && t.n_tile0 + lane * 8 < p.N) {
@@ -547,8 +584,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
 #pragma unroll 1
       for (int c = st.c0; c < st.c1; c += 2) {
-        epi_chunk<BN>(t, st, c, pa, pb, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
-        if (c + 1 < st.c1) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc]);
+        epi_chunk<BN>(t, st, c, pa, pb, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc], p);
+        if (c + 1 < st.c1) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc], p);
       }
     }
     if (lane == 0) bulk_wait_read<0>();  // staging smem no longer read by the copy engine; the writes complete with the grid
@@ -675,9 +712,25 @@ cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     return cudaErrorInvalidValue;
   }
   const long long items = (long long)p.mt * p.nt * p.splits * p.batches;
-  const int grid = (int)(items < num_sms ? items : num_sms);
+  int grid = (int)(items < num_sms ? items : num_sms);
+  int st_run = st;
+  GemmKParams pr = p;
+  {  // B-resident mode, see GemmKParams::b_resident.  SD2_GEMM_BRES=0 disables it (A/B measurements).
+    static int bres = -1;
+    if (bres < 0) {
+      const char* e = getenv("SD2_GEMM_BRES");
+      bres = e ? atoi(e) : 1;
+    }
+    const int g_nt = p.nt > 0 ? (num_sms / p.nt) * p.nt : 0;  // a grid that is a multiple of nt keeps n_tile fixed per CTA
+    if (bres && p.kind == KIND_PLAIN && p.total_kb <= st && p.total_kb >= 3 && p.splits == 1 && p.batches == 1 && p.raster == 1 &&
+        g_nt > 0 && items >= 2LL * g_nt && g_nt * 100 >= num_sms * 94) {
+      pr.b_resident = 1;
+      grid = g_nt;
+      st_run = p.total_kb;  // ring length = k-blocks per tile: stage s <-> k-block s
+    }
+  }
 #define SD2_GEMM_CASE(bn, amn, bmn) \
-  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn, 1>(tmA, tmB, tmO, p, grid, st, stream);
+  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn, 1>(tmA, tmB, tmO, pr, grid, st_run, stream);
   SD2_GEMM_CASE(256, false, false) SD2_GEMM_CASE(160, false, false) SD2_GEMM_CASE(128, false, false)
   SD2_GEMM_CASE(64, false, false)
   SD2_GEMM_CASE(256, false, true) SD2_GEMM_CASE(128, false, true) SD2_GEMM_CASE(64, false, true)

@@ -53,6 +53,20 @@ struct GemmKParams {
   // The consuming GroupNorm combines them per (image, group) and is then a pure streaming apply pass.
   float* gn_part;
   int gn_slab;
+  // B-resident mode (set by launch_gemm_tc): the K loop has exactly as many k-blocks as the ring has stages and every work
+  // item of a CTA has the same n tile, so stage s always holds k-block s of the SAME weight tile: the producer fetches B with
+  // the CTA's first tile only and streams A alone afterwards (K = 320 linears: 100 KB of weights per 128 x 160 tile no longer
+  // re-read from L2 for each of the ~28 tiles a CTA computes).
+  int b_resident;
+  // MSE head in the epilogue of the final conv (conv_out: 4 prediction channels in an 8-wide bf16 tensor): against the target
+  // noise (NCHW, mse_dtype = SD2_DT_*), the epilogue thread of a pixel adds sum((pred - noise)^2) over the 4 channels to
+  // mse_acc[0] (one atomic per warp) and writes dL/dpred = 2 (pred - noise) / count as the bf16 NHWC8 row of mse_dpred8 -
+  // the loss and the first gradient of the backward pass without a pass over the prediction.
+  const void* mse_target;
+  bf16* mse_dpred8;
+  float* mse_acc;
+  int mse_dtype, mse_hw;
+  float mse_k;  // 2 / (pixels * 4)
 };
 
 }  // namespace sd2

@@ -32,7 +32,7 @@ _GEMM_FUNCS = (ops.linear_fwd, ops.linear_dgrad, ops.linear_wgrad, ops.conv3x3_f
 # an input.  The two-stream scheduler derives read / write address ranges from this table.
 _OP_WRITES = {
     'linear_fwd': ((2,), ('workspace', 'gn_partial')), 'linear_dgrad': ((2,), ('workspace',)), 'linear_wgrad': ((2,), ()),
-    'conv3x3_fwd': ((5,), ('workspace', 'gn_partial')), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
+    'conv3x3_fwd': ((5,), ('workspace', 'gn_partial', 'mse_dpred8', 'mse_acc')), 'conv3x3_dgrad': ((5,), ('workspace',)), 'conv3x3_wgrad': ((5,), ()),
     'attn_fwd': ((3, 4), ()), 'attn_bwd': ((6, 7, 8, 9), ()),
     'groupnorm_fwd': ((3, 4, 5), ()), 'groupnorm_fwd_fused': ((5, 6, 7), ()), 'groupnorm_bwd': ((5, 6, 7, 8), ('drowsum', 'dcolsum', 'dcolsum2')),
     'layernorm_fwd': ((3, 4), ()), 'layernorm_bwd': ((4, 5, 6, 7), ('dcolsum',)),
@@ -236,6 +236,12 @@ class Engine:
         self.pred8 = None
         self.dpred8 = torch.zeros(B * H * W, 8, dtype=BF16, device=dev)
         self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        # MSE head in conv_out's epilogue (training engines): the target noise lives in a static buffer that K1 writes and the
+        # epilogue reads; its dtype is fixed by the first training forward (before graph capture).  mse_generation = the
+        # forward whose loss sum / dL/dpred the epilogue produced.
+        self.noise_target = None
+        self.mse_generation = -1
+        self._conv_out_op = None
         self.forward_only = forward_only  # sampling / eval: no backward schedule, no gradient buffers
         self._build()
         self.graph_fwd = self.graph_bwd = None
@@ -243,6 +249,26 @@ class Engine:
 
     def params_bound(self):
         return self.arena.bound()
+
+    def fused_mse_target(self, like):
+        """The static noise buffer the conv_out epilogue compares the prediction with, or None when the MSE head cannot be in
+        the epilogue for this call (forward-only engine, another latent dtype than the one the schedule was set up for, graphs
+        already captured without it).  The first training forward decides the dtype and arms the recorded conv_out launch."""
+        if self.forward_only or self._conv_out_op is None:
+            return None
+        if self.noise_target is None:
+            if self.graph_fwd is not None:
+                return None
+            self.noise_target = torch.zeros(self.B, 4, self.H, self.W, dtype=like.dtype, device=self.dev)
+            self.loss_acc[1] = float(self.B * 4 * self.H * self.W)
+            self._conv_out_op.keywords.update(mse_target=self.noise_target, mse_dpred8=self.dpred8, mse_acc=self.loss_acc)
+            # the loss sum is cleared at the start of every forward (first recorded op)
+            self.fwd.insert(0, partial(ops.fill_f32, self.ctx, self.loss_acc[0:1], 0.0))
+            self.fwd_is_gemm.insert(0, False)
+            self.fwd_side.insert(0, False)
+        if like.dtype != self.noise_target.dtype or tuple(like.shape) != tuple(self.noise_target.shape):
+            return None
+        return self.noise_target
 
     def prepare_inputs(self, sample, timestep, enc):
         """Inputs of a plain `unet(sample, timestep, encoder_hidden_states)` call -> the static input buffers."""
@@ -794,7 +820,7 @@ class Engine:
         w_out = self.w16('conv_out.weight')  # [9, 4, C0]
         if self.pred8 is None:
             self.pred8 = self.buf(M, 8)
-        self.f(ops.conv3x3_fwd, n.data, B, H, W, w_out, self.pred8, bias=self.b_out8, workspace=self.ws)
+        self._conv_out_op = self.f(ops.conv3x3_fwd, n.data, B, H, W, w_out, self.pred8, bias=self.b_out8, workspace=self.ws)
         gb8 = self.buf(8, dtype=torch.float32)
 
         def head_bwd():

@@ -141,13 +141,16 @@ class DDIMScheduler:
 
 
 class _FusedMSE(torch.autograd.Function):
-    """loss = mean((pred - noise)^2) computed by the fused head kernel from the engine's pred8 buffer; the same
-    launch writes dL/dpred so that backward starts without an elementwise pass."""
+    """loss = mean((pred - noise)^2).  Training forwards produce the sum of squares and dL/dpred in the epilogue of conv_out
+    itself (the target noise sits in the engine's static buffer, csrc/gemm_tc.cu MSE head): this node then only divides;
+    otherwise the stand-alone head kernel computes both from the engine's pred8 buffer."""
 
     @staticmethod
     def forward(ctx_, pred, noise, eng):
-        ops.fill_f32(eng.ctx, eng.loss_acc, 0.0)
-        ops.mse_head(eng.ctx, eng.pred8, noise.contiguous(), None, eng.dpred8, eng.loss_acc, 1.0, eng.B, eng.H, eng.W)
+        in_epilogue = eng.mse_generation == eng.generation and noise is eng.noise_target
+        if not in_epilogue:  # the conv_out epilogue did not see this target (other dtype / tensor): stand-alone head kernel
+            ops.fill_f32(eng.ctx, eng.loss_acc, 0.0)
+            ops.mse_head(eng.ctx, eng.pred8, noise.contiguous(), None, eng.dpred8, eng.loss_acc, 1.0, eng.B, eng.H, eng.W)
         ctx_.eng = eng
         ctx_.shape = pred.shape
         return (eng.loss_acc[0] / eng.loss_acc[1]).to(torch.float32)
@@ -279,12 +282,15 @@ class StableDiffusion(ComposerModel):
         gen = torch.cuda.default_generators[latents.device.index]
         seed, offset = gen.initial_seed(), gen.get_offset()
         ac = self.noise_scheduler.alphas_cumprod_on(latents.device)
+        target = eng.fused_mse_target(latents) if (torch.is_grad_enabled() and self.loss_fn is F.mse_loss) else None
         timesteps, noise, _, _, _, used = ops.noise_sched_fwd(eng.ctx, latents, ac, seed, offset, eng.in_temb.shape[1],
-                                                              out_nhwc8=eng.in_x8, out_temb=eng.in_temb)
+                                                              out_nhwc8=eng.in_x8, out_temb=eng.in_temb, out_noise=target)
         gen.set_offset(offset + used)
         eng.set_context(conditioning)
         from diffusion_b200.engine import unet_apply
         pred = unet_apply(self.unet, latents, timesteps, conditioning, prepared=True)
+        if target is not None:
+            eng.mse_generation = eng.generation  # conv_out's epilogue compared this forward's prediction with `noise`
         return pred, noise, timesteps
 
     # -- reference stable_diffusion.py:185-187 -----------------------------------------------------------------

@@ -72,14 +72,16 @@ _DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F
 
 # ------------------------------------------------------------------------------------------------- K1
 def noise_sched_fwd(ctx, latents, alphas_cumprod, seed, offset, temb_dim, want_noised_nchw=False, out_nhwc8=None,
-                    out_temb=None):
+                    out_temb=None, out_noise=None):
     """Returns (timesteps i64[B], noise like latents, noised_nhwc8 bf16 [B,H,W,8], temb bf16 [B,temb_dim],
-    noised_nchw or None, philox offset consumed)."""
+    noised_nchw or None, philox offset consumed).  out_noise: a buffer like `latents` to receive the noise (the engine's
+    static target buffer, read by the MSE head in conv_out's epilogue)."""
     B, Cc, H, W = latents.shape
     assert Cc == 4 and latents.is_contiguous()
     dev = latents.device
     ts = torch.empty(B, dtype=torch.int64, device=dev)
-    noise = torch.empty_like(latents)
+    noise = out_noise if out_noise is not None else torch.empty_like(latents)
+    assert noise.shape == latents.shape and noise.dtype == latents.dtype and noise.is_contiguous()
     nhwc8 = out_nhwc8 if out_nhwc8 is not None else torch.empty(B, H, W, 8, dtype=torch.bfloat16, device=dev)
     temb = out_temb if out_temb is not None else torch.empty(B, temb_dim, dtype=torch.bfloat16, device=dev)
     nchw = torch.empty_like(latents) if want_noised_nchw else None
@@ -263,9 +265,11 @@ def taps_stride2_dgrad():
 
 
 def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None, taps=None, n_planes=None,
-                workspace=None, plan=None, gn_partial=None, gn_slab=32):
+                workspace=None, plan=None, gn_partial=None, gn_slab=32, mse_target=None, mse_dpred8=None, mse_acc=None):
     """x: bf16 [n_planes*H*W, Cin] NHWC; w9: bf16 [9, Cout, Cin]; out: bf16 [B*H*W, Cout].
-    gn_partial: fp32 [B*H*W / gn_slab, Cout, 2] receiving the GroupNorm partial statistics of `out` from the epilogue."""
+    gn_partial: fp32 [B*H*W / gn_slab, Cout, 2] receiving the GroupNorm partial statistics of `out` from the epilogue.
+    mse_target (noise [B,4,H,W]) + mse_dpred8 (bf16 [B*H*W, 8]) + mse_acc (fp32 [>=1]): the MSE head in the epilogue of
+    conv_out - loss sum added to mse_acc[0], dL/dpred written to mse_dpred8 (see sd2b200.h)."""
     Cin, Cout = x.shape[1], w9.shape[1]
     d = L.GemmDesc()
     d.kind, d.M, d.N, d.K, d.batch = L.GEMM_CONV, B * H * W, Cout, 9 * Cin, 1
@@ -276,6 +280,11 @@ def conv3x3_fwd(ctx, x, B, H, W, w9, out, bias=None, rowbias=None, residual=None
     _gn_stats(d, gn_partial, gn_slab)
     if gn_partial is not None and plan is not None:
         plan = (plan[0], 1)
+    if mse_target is not None:
+        assert mse_target.is_contiguous() and tuple(mse_target.shape) == (B, 4, H, W)
+        d.mse_target, d.mse_dpred8, d.mse_acc = mse_target.data_ptr(), mse_dpred8.data_ptr(), mse_acc.data_ptr()
+        d.mse_dtype, d.mse_hw = _DT[mse_target.dtype], H * W
+        plan = None
     run_gemm(ctx, d, plan)
 
 

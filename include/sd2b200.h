@@ -110,6 +110,15 @@ typedef struct sd2_gemm_desc {
    * stored values -> gn_partial[M / gn_slab][round8(N)][2] fp32.  Consumed by sd2_groupnorm_fwd_fused.  Null = off. */
   float* gn_partial;
   int gn_slab;
+  /* MSE noise-prediction loss + its backward in the epilogue of the final conv (SD2_GEMM_CONV, bf16 output of <= 8 columns of
+   * which the first 4 are the prediction): mse_target = the noise [B][4][H][W] in mse_dtype (SD2_DT_*), mse_hw = H*W;
+   * mse_acc[0] += sum((pred - noise)^2) over the 4 channels of every pixel; mse_dpred8 = bf16 [M][8] rows
+   * 2 (pred - noise) / (M * 4) (columns 4..7 zero).  Replaces F.mse_loss + its backward, reference stable_diffusion.py:185-187.
+   * Null = off. */
+  const void* mse_target;
+  void* mse_dpred8;
+  float* mse_acc;
+  int mse_dtype, mse_hw;
 } sd2_gemm_desc;
 
 int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream);

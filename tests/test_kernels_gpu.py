@@ -518,6 +518,36 @@ def test_casts_and_mse(ctx):
         assert float(dpred[:, 4:].abs().max()) == 0
 
 
+@pytest.mark.parametrize('B,H,W,Cin,dt', [(16, 32, 32, 320, torch.bfloat16), (3, 8, 8, 64, torch.float32), (5, 16, 16, 128, torch.float16)])
+def test_mse_head_in_the_conv_out_epilogue(ctx, B, H, W, Cin, dt):
+    """conv_out (Cin -> 4 prediction channels in an 8-wide tensor) with the MSE head in its epilogue: same loss sum and
+    dL/dpred as the stand-alone head kernel on the stored prediction (north_star: loss + backward fused into the final conv)."""
+    from diffusion_b200 import ops
+    M = B * H * W
+    x = bf(M, Cin, seed=1)
+    w9 = bf(9, 4, Cin, scale=(9 * Cin)**-0.5, seed=2)
+    bias8 = torch.zeros(8, device='cuda')
+    bias8[:4] = torch.randn(4, device='cuda')
+    noise = torch.randn(B, 4, H, W, device='cuda').to(dt)
+    pred8 = torch.empty(M, 8, dtype=torch.bfloat16, device='cuda')
+    dpred = torch.full((M, 8), 7.0, dtype=torch.bfloat16, device='cuda')
+    acc = torch.zeros(2, device='cuda')
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+    ops.conv3x3_fwd(ctx, x, B, H, W, w9, pred8, bias=bias8, workspace=ws, mse_target=noise, mse_dpred8=dpred, mse_acc=acc)
+    # the plain launch gives the same prediction bits
+    pred8_plain = torch.empty_like(pred8)
+    ops.conv3x3_fwd(ctx, x, B, H, W, w9, pred8_plain, bias=bias8, workspace=ws)
+    assert torch.equal(pred8.view(torch.int16), pred8_plain.view(torch.int16))
+    dref = torch.empty_like(pred8)
+    acc_ref = torch.zeros(2, device='cuda')
+    ops.mse_head(ctx, pred8, noise, None, dref, acc_ref, 1.0, B, H, W)
+    assert abs(acc[0].item() - acc_ref[0].item()) <= 1e-5 * abs(acc_ref[0].item()), (acc, acc_ref)
+    assert torch.equal(dpred.view(torch.int16), dref.view(torch.int16))
+    p = pred8[:, :4].float().view(B, H, W, 4).permute(0, 3, 1, 2)
+    loss_ref = F.mse_loss(p, noise.float())
+    assert abs(acc[0].item() / (M * 4) - loss_ref.item()) < 1e-4 * loss_ref.item()
+
+
 def test_fused_adamw_matches_torch(ctx):
     """sd2_adamw_step vs torch.optim.AdamW (reference train.py:33 / yaml :55-58) over 4 steps, incl. the bf16 shadow
     and the in-kernel gradient reset."""
