@@ -181,11 +181,12 @@ def load(auto_build=True):
     global _lib
     if _lib is not None:
         return _lib
-    if auto_build and _stale():
+    path = os.environ.get('SD2_LIB') or LIB_PATH  # SD2_LIB: another build of the same ABI (kernel A/B measurements on one box)
+    if path == LIB_PATH and auto_build and _stale():
         build()
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"`')
-    lib = C.CDLL(LIB_PATH)
+    if not os.path.exists(path):
+        raise RuntimeError(f'{path} is missing: run `python -c "import __graft_entry__ as g; g.build()"`')
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         if not hasattr(lib, name):
             raise RuntimeError(f'{LIB_PATH} does not export {name}')
