@@ -152,10 +152,17 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_apply_kernel(const bf16* __r
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm bwd
-__device__ __forceinline__ float silu_grad(float z) {
-  const float s = sigmoid_f(z);
-  return s * (1.f + z * (1.f - s));
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+// d/dz [z * sigmoid(z)] = s + z*s*(1-s), sigmoid through one MUFU.TANH
+__device__ __forceinline__ float silu_grad_fast(float z) {
+  const float s = fmaf(tanh_approx(0.5f * z), 0.5f, 0.5f);
+  return fmaf(z, fmaf(-s, s, s), s);
+}
+__device__ __forceinline__ float silu_grad(float z) { return silu_grad_fast(z); }
 
 // grid (P, B): per-channel partial sums of dyh and dyh * xhat -> ws[b][p][C][2]
 __global__ void __launch_bounds__(GN_THREADS, 1) gn_bwd_stats_kernel(const bf16* __restrict__ dy, long long lddy,
@@ -544,16 +551,6 @@ __device__ __forceinline__ float2 ld_dsmem_f2(const void* local_smem, uint32_t r
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
   asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
   return v;
-}
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// d/dz [z * sigmoid(z)] = s + z*s*(1-s), sigmoid through one MUFU.TANH
-__device__ __forceinline__ float silu_grad_fast(float z) {
-  const float s = fmaf(tanh_approx(0.5f * z), 0.5f, 0.5f);
-  return fmaf(z, fmaf(-s, s, s), s);
 }
 
 struct GnClusterCfg {
@@ -1364,7 +1361,8 @@ int sd2_groupnorm_bwd(sd2_ctx* ctx, const void* dy, long long lddy, const void* 
   const bool emit = drowsum != nullptr || dcolsum1 != nullptr || dcolsum2 != nullptr;
   float* cs_ws = emit ? ws + (long long)B * GN_MAXP * C * 2 + (long long)B * 64 * 2 : nullptr;
   const dim3 fin_grid((C + 31) / 32, B >= 64 ? 8 : (B >= 8 ? 2 : 1));
-  if (ldx == C && lddy == C && lddx == C && (dx_add == nullptr || ldadd == C)) {
+  static const int force_two_pass = getenv("SD2_GN_BWD_TWOPASS") ? atoi(getenv("SD2_GN_BWD_TWOPASS")) : 0;  // A/B switch
+  if (!force_two_pass && ldx == C && lddy == C && lddx == C && (dx_add == nullptr || ldadd == C)) {
     const GnClusterCfg cc = gn_cluster_cfg(HW, C, 2);
     if (cc.ok) {  // single-pass cluster kernel + the dgamma/dbeta reduction over the B * NC per-CTA slabs
       const bf16* dyp = reinterpret_cast<const bf16*>(dy);
