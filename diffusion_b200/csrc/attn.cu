@@ -35,6 +35,7 @@ struct AttnParams {
   bf16* dq;            // backward, single key tile: dQ is written directly
   long long lddq;
   float* dq32;         // backward, several key tiles: fp32 dQ accumulator [B*Nq][heads*64]
+  int unordered;       // measurement only (SD2_ATTN_UNORDERED=1): skip the waits that fix the dQ summation order
   bf16* dk;
   long long lddk;
   bf16* dv;
@@ -400,7 +401,7 @@ static constexpr int AT_BWD_THREADS = 64 + AT_BWD_CWARPS * 32;  // warp 0 TMA, w
 template <bool DIRECT>
 __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_stg, const void* my_stg_g, int lane, float scale,
                                                   uint64_t* dq_empty, const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h,
-                                                  int b, bf16* dq, long long lddq, bool one_q_tile, bool first_kt) {
+                                                  int b, bf16* dq, long long lddq, bool one_q_tile, bool first_kt, int flags) {
   uint32_t rq[16];
   tmem_ld_32x32b_x16(taddr, rq);
   tmem_wait_ld();
@@ -428,8 +429,10 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
       // Fixed summation order: the previous contribution to THESE dQ rows (same query tile, previous key tile = nqt tiles
       // ago) must have landed before this one is issued.  With several query tiles only the most recent reduce-add (other
       // rows) may still be in flight.
-      if (one_q_tile) bulk_wait<0>();
-      else bulk_wait<1>();
+      if (!(flags & 1)) {
+        if (one_q_tile) bulk_wait<0>();
+        else bulk_wait<1>();
+      }
     }
     __syncwarp();
     const uint32_t bufp = my_stg + lane * 64;  // 64 B rows, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
@@ -768,7 +771,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
           mbar_wait(dq_full, (uint32_t)((t - 1) & 1));
           tc_fence_after();
           attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ,
-                                    hq * 16, ip * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, t - 1 < nqt);
+                                    hq * 16, ip * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, t - 1 < nqt, p.unordered);
         }
       }
     }
@@ -776,7 +779,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
       mbar_wait(dq_full, (uint32_t)((ntiles - 1) & 1));
       tc_fence_after();
       attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
-                                (nqt - 1) * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, ntiles - 1 < nqt);
+                                (nqt - 1) * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, ntiles - 1 < nqt, p.unordered);
       drain_dkv(kt1 - 1, nk - 1);
     }
     if (!DIRECT) {
@@ -905,6 +908,12 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.dq = reinterpret_cast<bf16*>(dq);
   p.lddq = lddq;
   p.dq32 = dq32;
+  {
+    static const int unordered = getenv("SD2_ATTN_UNORDERED") ? atoi(getenv("SD2_ATTN_UNORDERED")) : 0;
+    p.unordered = unordered;
+    static const int force_ks = getenv("SD2_ATTN_KSPLIT") ? atoi(getenv("SD2_ATTN_KSPLIT")) : 0;
+    if (force_ks > 0 && !direct && force_ks <= ks_ws && force_ks <= nkt) ksplit = force_ks;
+  }
   p.dk = reinterpret_cast<bf16*>(dk);
   p.lddk = lddk;
   p.dv = reinterpret_cast<bf16*>(dv);
