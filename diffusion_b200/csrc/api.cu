@@ -35,7 +35,8 @@ bool encode_tmap_4d(CUtensorMap* out, int dtype, int swizzle_bytes, const void* 
     bx[i] = box[i];
   }
   for (int i = 0; i < 3; ++i) gstr[i] = strides_bytes[i];
-  const CUtensorMapDataType dt = dtype == SD2_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = dtype == SD2_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == SD2_DT_U64_INTERNAL ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;

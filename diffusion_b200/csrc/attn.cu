@@ -17,6 +17,8 @@
 //   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - D) scale (bf16, smem)
 //   dV += P^T dO, dK += dS^T Q (accumulate in TMEM over the loop), dQ_i = dS K (TMEM -> smem -> TMA reduce-add fp32)
 //   The same smem image of a [128 x 64] tile serves as K-major operand of one GEMM and MN-major operand of another.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -36,6 +38,7 @@ struct AttnParams {
   long long lddq;
   float* dq32;         // backward, several key tiles: fp32 dQ accumulator [B*Nq][heads*64]
   int unordered;       // measurement only (SD2_ATTN_UNORDERED=1): skip the waits that fix the dQ summation order
+  long long* dq64;     // backward, FX variant: 64-bit fixed-point dQ accumulator [B*Nq][heads*64]
   bf16* dk;
   long long lddk;
   bf16* dv;
@@ -390,6 +393,31 @@ __global__ void cast2d_f32_bf16_kernel(const float* __restrict__ src, bf16* __re
   }
 }
 
+// dQ accumulates in 64-bit fixed point (2^-40 units): integer sums do not depend on the order in which the key tiles' CTAs
+// add their contributions, so the result is bit-reproducible although the reduce-adds land in arrival order.
+static constexpr float AT_FX_SCALE = 1099511627776.f;       // 2^40
+static constexpr float AT_FX_INV = 1.f / 1099511627776.f;   // |dQ| < 2^23, resolution 9e-13
+
+// dst[r][0..cols) bf16 (row stride ldd) = src[r][0..cols) fixed point (dense)
+__global__ void cast2d_fx64_bf16_kernel(const long long* __restrict__ src, bf16* __restrict__ dst, long long ldd, long long rows,
+                                        int cols) {
+  pdl_grid_sync();
+  const int V = cols / 8;
+  const long long n = rows * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / V;
+    const int v = (int)(i % V);
+    const longlong2* p = reinterpret_cast<const longlong2*>(src + r * cols + v * 8);
+    const longlong2 a = p[0], b = p[1], c = p[2], d = p[3];
+    uint4 u;
+    u.x = pack_bf16x2((float)a.x * AT_FX_INV, (float)a.y * AT_FX_INV);
+    u.y = pack_bf16x2((float)b.x * AT_FX_INV, (float)b.y * AT_FX_INV);
+    u.z = pack_bf16x2((float)c.x * AT_FX_INV, (float)c.y * AT_FX_INV);
+    u.w = pack_bf16x2((float)d.x * AT_FX_INV, (float)d.y * AT_FX_INV);
+    *reinterpret_cast<uint4*>(dst + r * ldd + v * 8) = u;
+  }
+}
+
 static constexpr int AT_BWD_CWARPS = 16;                       // compute warps: four threads per key row
 static constexpr int AT_BWD_THREADS = 64 + AT_BWD_CWARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..17 compute
 
@@ -398,7 +426,7 @@ static constexpr int AT_BWD_THREADS = 64 + AT_BWD_CWARPS * 32;  // warp 0 TMA, w
 // sends whole 64-byte row segments to the L2 reduction units.  A single key tile (cross-attention over 77 tokens,
 // self-attention over <= 128 tokens): the tile is complete, it goes to the bf16 gradient directly (no accumulator, no
 // memset, no cast pass).
-template <bool DIRECT>
+template <bool DIRECT, bool FX>
 __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_stg, const void* my_stg_g, int lane, float scale,
                                                   uint64_t* dq_empty, const CUtensorMap* tmDQ, int col0, int row0, int Nq, int h,
                                                   int b, bf16* dq, long long lddq, bool one_q_tile, bool first_kt, int flags) {
@@ -421,6 +449,30 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
         u.w = pack_bf16x2(__uint_as_float(rq[g * 8 + 6]) * scale, __uint_as_float(rq[g * 8 + 7]) * scale);
         *reinterpret_cast<uint4*>(dst + g * 8) = u;
       }
+    }
+  } else if (FX) {
+    // Shared accumulator in 64-bit fixed point: staging = one [32 rows][16 x 8 B] box per warp (128-byte rows, SWIZZLE_128B),
+    // integer TMA reduce-add; no ordering needed (integer sums are order-independent)
+    if (lane == 0) {
+      mbar_arrive(dq_empty);
+      bulk_wait_read<0>();  // the staging buffer was handed to the copy engine one iteration ago
+    }
+    __syncwarp();
+    const float fx = scale * AT_FX_SCALE;
+    const uint32_t bufp = my_stg + lane * 128;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const long long a = __float2ll_rn(__uint_as_float(rq[2 * g]) * fx), c = __float2ll_rn(__uint_as_float(rq[2 * g + 1]) * fx);
+      uint4 u;
+      u.x = (uint32_t)(unsigned long long)a; u.y = (uint32_t)((unsigned long long)a >> 32);
+      u.z = (uint32_t)(unsigned long long)c; u.w = (uint32_t)((unsigned long long)c >> 32);
+      sts128(bufp + (uint32_t)((g ^ (lane & 7)) << 4), u);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (row0 < Nq) tma_reduce_add_4d(tmDQ, my_stg_g, col0, row0, h, b);
+      bulk_commit();
     }
   } else {
     if (lane == 0) {
@@ -457,18 +509,24 @@ __device__ __forceinline__ void attn_bwd_drain_dq(uint32_t taddr, uint32_t my_st
 // receives this CTA's contributions in a FIXED order (same thread, same address, one reduce-add after the other) - the
 // gradient is bit-reproducible run to run.  gridDim.x > 1 splits the key range over several CTAs when (images x heads) alone
 // cannot fill the GPU; each split accumulates into its own fp32 partial and the cast pass adds the partials in order.
-template <bool DIRECT>
+// FX = true (long sequences): one key tile per CTA (gridDim.x = key tiles), all key-tile CTAs of an (image, head) add into ONE
+// dQ accumulator in 64-bit fixed point - integer sums are order-independent, so the result is still bit-reproducible, and
+// the CTAs of an (image, head) are adjacent in launch order, so their reduce-adds meet in L2 (the sequential walk re-touches a
+// 1 MB fp32 dQ slice per key tile from each of 148 CTAs: 148 MB live at N = 4096, past the 126 MB L2).
+template <bool DIRECT, bool FX>
 __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
-  uint8_t* sKV = smem;               // [2 buffers][K tile | V tile]
-  uint8_t* sQ = sKV + 4 * AT_TILE;   // [2]
+  constexpr int KVB = FX ? 1 : 2;              // K / V buffers (FX: one key tile per CTA, nothing to prefetch)
+  constexpr int STG_W = FX ? 4096 : 2048;      // dQ staging bytes per compute warp (FX: 16 x int64 per row)
+  uint8_t* sKV = smem;                         // [KVB buffers][K tile | V tile]
+  uint8_t* sQ = sKV + 2 * KVB * AT_TILE;       // [2]
   uint8_t* sdO = sQ + 2 * AT_TILE;   // [2]
   uint8_t* sdS = sdO + 2 * AT_TILE;  // dS^T : [2 buffers] x 2 query chunks x [128 key rows][128 B]
-  uint8_t* stg = sdS + 4 * AT_TILE;  // 16 warps x 2 KB fp32 staging for the dQ reduce-add (DIRECT: unused)
-  float* sStat = reinterpret_cast<float*>(stg + AT_BWD_CWARPS * 2048);  // [2 stages][lse 128 | D 128]
+  uint8_t* stg = sdS + 4 * AT_TILE;  // per compute warp: staging for the dQ reduce-add (DIRECT: unused)
+  float* sStat = reinterpret_cast<float*>(stg + AT_BWD_CWARPS * STG_W);  // [2 stages][lse 128 | D 128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 512);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
@@ -544,8 +602,8 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     const float* st_bh = p.stats + ((long long)b * p.heads + h) * nqt * 256;
     int t = 0;
     for (int kk = 0; kk < nk; ++kk) {
-      const int sk = kk & 1;
-      mbar_wait(&kv_empty[sk], (uint32_t)((kk >> 1) & 1) ^ 1u);  // every MMA of the key tile that used this buffer is done
+      const int sk = KVB == 2 ? (kk & 1) : 0;
+      mbar_wait(&kv_empty[sk], (uint32_t)((KVB == 2 ? (kk >> 1) : kk) & 1) ^ 1u);  // the MMAs that used this buffer are done
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[sk], 2 * AT_TILE);
         tma_load_4d(sKV + sk * 2 * AT_TILE, &tmK, &kv_full[sk], 0, (kt0 + kk) * 128, h, b);
@@ -593,7 +651,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     __syncwarp();
     int t = 0;
     for (int kk = 0; kk < nk; ++kk) {
-      const uint64_t kvb = (uint64_t)(kk & 1) * 2 * TS;  // K / V buffer of this key tile
+      const uint64_t kvb = KVB == 2 ? (uint64_t)(kk & 1) * 2 * TS : 0;  // K / V buffer of this key tile
       for (int i = 0; i < nqt; ++i, ++t) {
         const int s = t & 1;
         if (t + 1 < ntiles) {
@@ -601,8 +659,8 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
           const uint64_t bQ = bQ0 + (uint64_t)s1 * TS, bdO = bdO0 + (uint64_t)s1 * TS;
           uint64_t kvn = kvb;
           if (i == nqt - 1) {  // the next tile belongs to the next key tile: its K / V arrive in the other buffer
-            kvn = (uint64_t)((kk + 1) & 1) * 2 * TS;
-            mbar_wait(&kv_full[(kk + 1) & 1], (uint32_t)(((kk + 1) >> 1) & 1));
+            kvn = KVB == 2 ? (uint64_t)((kk + 1) & 1) * 2 * TS : 0;
+            mbar_wait(&kv_full[KVB == 2 ? ((kk + 1) & 1) : 0], (uint32_t)((KVB == 2 ? ((kk + 1) >> 1) : (kk + 1)) & 1));
           }
           mbar_wait(s_empty, (uint32_t)(t & 1));
           mbar_wait(&qdo_full[s1], (uint32_t)(((t + 1) >> 1) & 1));
@@ -650,7 +708,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
           tc_commit(&qdo_empty[s]);
           if (i == nqt - 1) {
             tc_commit(dkv_full);
-            tc_commit(&kv_empty[kk & 1]);
+            tc_commit(&kv_empty[KVB == 2 ? (kk & 1) : 0]);
           }
         }
         __syncwarp();
@@ -670,10 +728,10 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     const uint32_t ds_row0 = smem_u32(sdS) + (uint32_t)(hq >> 1) * AT_TILE + r * 128;
     const int dsg0 = (hq & 1) * 4;  // first 16-byte group of this thread inside the 128-byte dS^T row
     const uint32_t stat0 = smem_u32(sStat) + hq * 128;  // this thread's 32 queries of the lse block; D block 512 B further
-    const uint8_t* my_stg_g = stg + (size_t)(warp - 2) * 2048;
+    const uint8_t* my_stg_g = stg + (size_t)(warp - 2) * STG_W;
     const uint32_t my_stg = smem_u32(my_stg_g);
     const float c2 = p.c2;
-    const int bq = DIRECT ? b : (int)blockIdx.x * p.B + b;  // image index inside the (per key-range split) fp32 dQ accumulator
+    const int bq = (DIRECT || FX) ? b : (int)blockIdx.x * p.B + b;  // image index inside the (per key-range split) dQ partial
 
     auto drain_dkv = [&](int kt, int kk) {  // dV, dK of key tile kt (this thread's 16 columns of each) -> bf16, global
       mbar_wait(dkv_full, (uint32_t)(kk & 1));
@@ -770,7 +828,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
           const int ip = i > 0 ? i - 1 : nqt - 1;
           mbar_wait(dq_full, (uint32_t)((t - 1) & 1));
           tc_fence_after();
-          attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ,
+          attn_bwd_drain_dq<DIRECT, FX>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ,
                                     hq * 16, ip * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, t - 1 < nqt, p.unordered);
         }
       }
@@ -778,7 +836,7 @@ __global__ void __launch_bounds__(AT_BWD_THREADS, 1)
     if (ntiles > 0) {  // last tile's dQ, last key tile's dV / dK
       mbar_wait(dq_full, (uint32_t)((ntiles - 1) & 1));
       tc_fence_after();
-      attn_bwd_drain_dq<DIRECT>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
+      attn_bwd_drain_dq<DIRECT, FX>(tdQ + lane_off + (uint32_t)(hq * 16), my_stg, my_stg_g, lane, p.scale, dq_empty, &tmDQ, hq * 16,
                                 (nqt - 1) * 128 + q * 32, p.Nq, h, bq, p.dq, p.lddq, nqt == 1, ntiles - 1 < nqt, p.unordered);
       drain_dkv(kt1 - 1, nk - 1);
     }
@@ -865,10 +923,21 @@ static int attn_bwd_ksplit(int B, int heads, int Nq, int nkt) {
   return best;
 }
 
+// Which dQ accumulation scheme: the sequential walk (ordered fp32 partials) while its live dQ working set - one fp32 slice
+// of Nq x 64 per resident CTA - fits well inside the L2; beyond that one key tile per CTA on the shared fixed-point accumulator.
+// SD2_ATTN_FX=0/1 forces one of them (A/B measurements).
+static bool attn_bwd_use_fx(int Nq, int nkt) {
+  static const int forced = getenv("SD2_ATTN_FX") ? atoi(getenv("SD2_ATTN_FX")) : -1;
+  if (nkt <= 1) return false;
+  if (forced >= 0) return forced != 0;
+  return 148.0 * Nq * 64.0 * 4.0 > 64.0e6;  // N >= 2048
+}
+
 long long sd2_attn_bwd_ws_bytes(int B, int heads, int Nq) {
   const long long nqt = (Nq + 127) / 128;
-  const int ks = attn_bwd_ksplit(B, heads, Nq, (int)nqt);  // self-attention (Nk = Nq) is the case that needs the accumulator
-  return (long long)ks * B * Nq * heads * 64 * 4 + (long long)B * heads * nqt * 256 * 4;
+  const long long elems = (long long)B * Nq * heads * 64;
+  const long long acc = std::max(elems * 8, (long long)attn_bwd_ksplit(B, heads, Nq, (int)nqt) * elems * 4);  // either scheme
+  return acc + (long long)B * heads * nqt * 256 * 4;
 }
 
 int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
@@ -884,21 +953,32 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   const int C = heads * 64;
   const int nqt = (Nq + 127) / 128, nkt = (Nk + 127) / 128;
   const bool direct = nkt == 1;  // one key tile: every dQ tile has a single contribution and is written as bf16 directly
+  const bool fx = !direct && attn_bwd_use_fx(Nq, nkt);
   // the workspace (sd2_attn_bwd_ws_bytes knows B, heads, Nq only) holds attn_bwd_ksplit(B, heads, nqt) partials
   const int ks_ws = attn_bwd_ksplit(B, heads, Nq, nqt);
   int ksplit = direct ? 1 : attn_bwd_ksplit(B, heads, Nq, nkt);
   if (ksplit > ks_ws) ksplit = ks_ws;
   const long long part = (long long)B * Nq * C;
-  float* dq32 = reinterpret_cast<float*>(ws);                                    // [ksplit][B*Nq][C] fp32 dQ partials
-  float* stats = dq32 + (long long)ks_ws * part;                                // [B*heads][nqt][lse 128 | D 128]
+  const long long acc_bytes = std::max(part * 8, (long long)ks_ws * part * 4);
+  float* dq32 = reinterpret_cast<float*>(ws);                     // ordered scheme: [ksplit][B*Nq][C] fp32 dQ partials
+  long long* dq64 = reinterpret_cast<long long*>(ws);             // fixed-point scheme: [B*Nq][C] int64
+  float* stats = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + acc_bytes);  // [B*heads][nqt][lse 128 | D 128]
   CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
   std::string err;
   if (!head_tmap(&tmQ, q, ldq, Nq, heads, B, &err) || !head_tmap(&tmK, k, ldk, Nk, heads, B, &err) ||
       !head_tmap(&tmV, v, ldv, Nk, heads, B, &err) || !head_tmap(&tmdO, d_o, lddo, Nq, heads, B, &err))
     return fail(ctx, "sd2_attn_bwd: " + err);
-  // fp32 dQ partials as a [ksplit * B][heads][Nq][64]-strided view, box = 32 rows x 16 columns (64-byte rows, SWIZZLE_64B)
-  if (!out_tmap(&tmDQ, dq32, true, 16, 64, Nq, C, heads, (long long)B * ksplit, 64, (long long)Nq * C, &err))
-    return fail(ctx, "sd2_attn_bwd dq map: " + err);
+  if (fx) {  // accumulator as a [B][heads][Nq][64] view of 64-bit integers, box = 32 rows x 16 columns (128-byte rows, SWIZZLE_128B)
+    const uint64_t dims[4] = {64, (uint64_t)Nq, (uint64_t)heads, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 8, 64 * 8, (uint64_t)Nq * C * 8};
+    const uint32_t box[4] = {16, 32, 1, 1};
+    if (!encode_tmap_4d(&tmDQ, SD2_DT_U64_INTERNAL, 128, dq64, dims, strides, box, &err))
+      return fail(ctx, "sd2_attn_bwd dq map: " + err);
+  } else {
+    // fp32 dQ partials as a [ksplit * B][heads][Nq][64]-strided view, box = 32 rows x 16 columns (64-byte rows, SWIZZLE_64B)
+    if (!out_tmap(&tmDQ, dq32, true, 16, 64, Nq, C, heads, (long long)B * ksplit, 64, (long long)Nq * C, &err))
+      return fail(ctx, "sd2_attn_bwd dq map: " + err);
+  }
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.heads = heads; p.Nq = Nq; p.Nk = Nk;
@@ -908,6 +988,7 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   p.dq = reinterpret_cast<bf16*>(dq);
   p.lddq = lddq;
   p.dq32 = dq32;
+  p.dq64 = dq64;
   {
     static const int unordered = getenv("SD2_ATTN_UNORDERED") ? atoi(getenv("SD2_ATTN_UNORDERED")) : 0;
     p.unordered = unordered;
@@ -922,20 +1003,30 @@ int sd2_attn_bwd(sd2_ctx* ctx, const void* q, long long ldq, const void* k, long
   launch_k(attn_bwd_prep_kernel, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(o), ldo,
            reinterpret_cast<const bf16*>(d_o), lddo, lse, stats, B, heads, Nq, nqt);
   cudaError_t e;
+  // both layouts: 12 tiles + 32 KB staging (two K / V buffers) = 10 tiles + 64 KB staging (one K / V buffer, int64 staging)
   const size_t smem = 12 * AT_TILE + AT_BWD_CWARPS * 2048 + 512 * 4 + 20 * 8 + 16;
   static bool attr = false;
   if (!attr) {
-    e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd attr: ") + cudaGetErrorString(e));
     attr = true;
   }
   if (direct) {
-    e = launch_k(attn_bwd_kernel<true>, dim3(1, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
+    e = launch_k(attn_bwd_kernel<true, false>, dim3(1, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
     if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd launch: ") + cudaGetErrorString(e));
     return check_launch(ctx, "attn_bwd", 2);
   }
-  e = launch_k(attn_bwd_kernel<false>, dim3(ksplit, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
+  if (fx) {  // one key tile per CTA, shared fixed-point accumulator (cleared first: every CTA adds)
+    e = cudaMemsetAsync(dq64, 0, (size_t)part * 8, stream);
+    if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd memset: ") + cudaGetErrorString(e));
+    attn_bwd_kernel<false, true><<<dim3(nkt, heads, B), AT_BWD_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+    launch_k(cast2d_fx64_bf16_kernel, dim3(grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream,
+             (const long long*)dq64, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C);
+    return check_launch(ctx, "attn_bwd", 3);
+  }
+  e = launch_k(attn_bwd_kernel<false, false>, dim3(ksplit, heads, B), dim3(AT_BWD_THREADS), smem, stream, tmQ, tmK, tmV, tmdO, tmDQ, p);
   if (e != cudaSuccess) return fail(ctx, std::string("sd2_attn_bwd launch: ") + cudaGetErrorString(e));
   launch_k(cast2d_f32_bf16_kernel, dim3(grid_for((long long)B * Nq * (C / 8), 256, ctx->num_sms)), dim3(256), 0, stream,
            (const float*)dq32, reinterpret_cast<bf16*>(dq), lddq, (long long)B * Nq, C, ksplit, part);

@@ -35,7 +35,8 @@ EncodeTiledFn get_encode_tiled();
 bool encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                          const uint32_t box[4], std::string* err);
 
-// generic form: dtype SD2_DT_F32 / SD2_DT_BF16, swizzle_bytes 128 / 64 / 32 / 0 (inner box row must not exceed it)
+enum { SD2_DT_U64_INTERNAL = 100 };  // 64-bit integer elements (fixed-point accumulators), not part of the public ABI
+// generic form: dtype SD2_DT_F32 / SD2_DT_BF16 / SD2_DT_U64_INTERNAL, swizzle_bytes 128 / 64 / 32 / 0 (inner box row must not exceed it)
 bool encode_tmap_4d(CUtensorMap* out, int dtype, int swizzle_bytes, const void* ptr, const uint64_t dims[4],
                     const uint64_t strides_bytes[3], const uint32_t box[4], std::string* err);
 
