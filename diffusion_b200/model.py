@@ -380,10 +380,10 @@ class StableDiffusion(ComposerModel):
         with `self.vae` like the reference; 'latent' returns the final fp32 latents, which is all a model built without a
         VAE can return).  Per step: one timestep-embedding launch, the UNet forward graph on the (2x) batch, and ONE fused
         launch for classifier-free guidance + the DDIM update + the next UNet input (`sd2_cfg_ddim_step`)."""
-        _check_prompt_given(prompt, tokenized_prompts, prompt_embeds)
-        _check_prompt_lenths(prompt, negative_prompt)
-        _check_prompt_lenths(tokenized_prompts, tokenized_negative_prompts)
-        _check_prompt_lenths(prompt_embeds, negative_prompt_embeds)
+        _require_some_prompt(prompt, tokenized_prompts, prompt_embeds)
+        _require_matching_negatives(prompt, negative_prompt)
+        _require_matching_negatives(tokenized_prompts, tokenized_negative_prompts)
+        _require_matching_negatives(prompt_embeds, negative_prompt_embeds)
         if output_type not in ('image', 'latent'):
             raise ValueError("output_type must be 'image' or 'latent'")
         if output_type == 'image' and self.vae is None:
@@ -462,19 +462,26 @@ class StableDiffusion(ComposerModel):
         return text_embeddings.view(bs_embed * num_images_per_prompt, seq_len, -1)
 
 
-def _check_prompt_lenths(prompt, negative_prompt):
-    if prompt is None and negative_prompt is None:
+def _count(x):
+    """Number of prompts in a str / list of str / tensor argument."""
+    return 1 if isinstance(x, str) else len(x)
+
+
+def _require_matching_negatives(positive, negative):
+    """generate() accepts prompts, token ids or embeddings, each with an optional negative counterpart: when the negative is
+    given it needs one entry per positive one (same error type and wording as reference stable_diffusion.py:405-414)."""
+    if positive is None and negative is None:
         return
-    batch_size = 1 if isinstance(prompt, str) else len(prompt)
-    if negative_prompt is not None and len(negative_prompt) > 0:
-        negative_prompt_bs = 1 if isinstance(negative_prompt, str) else len(negative_prompt)
-        if negative_prompt_bs != batch_size:
-            raise ValueError('len(prompts) and len(negative_prompts) must be the same. '
-                             'A negative prompt must be provided for each given prompt.')
+    if negative is None or len(negative) == 0:
+        return
+    if _count(negative) != _count(positive):
+        raise ValueError('len(prompts) and len(negative_prompts) must be the same. '
+                         'A negative prompt must be provided for each given prompt.')
 
 
-def _check_prompt_given(prompt, tokenized_prompts, prompt_embeds):
-    if prompt is None and tokenized_prompts is None and prompt_embeds is None:
+def _require_some_prompt(*candidates):
+    """reference stable_diffusion.py:416-418: at least one way of giving the prompt."""
+    if all(c is None for c in candidates):
         raise ValueError('Must provide one of `prompt`, `tokenized_prompts`, or `prompt_embeds`')
 
 

@@ -170,14 +170,14 @@ def test_ddim_step_is_the_deterministic_ddim_update():
 
 
 def test_generate_argument_contract():
-    from diffusion_b200.model import DDIMScheduler, StableDiffusion, _check_prompt_given, _check_prompt_lenths
+    from diffusion_b200.model import DDIMScheduler, StableDiffusion, _require_some_prompt, _require_matching_negatives
     from diffusion_b200.unet import UNet2DConditionModel, UNetOutput
     from oracle.unet import TINY_UNET_CONFIG
     with pytest.raises(ValueError):
-        _check_prompt_given(None, None, None)
+        _require_some_prompt(None, None, None)
     with pytest.raises(ValueError):
-        _check_prompt_lenths(['a', 'b'], ['c'])
-    _check_prompt_lenths(['a'], None)
+        _require_matching_negatives(['a', 'b'], ['c'])
+    _require_matching_negatives(['a'], None)
     m = StableDiffusion(UNet2DConditionModel(**TINY_UNET_CONFIG), None, None, None, None, DDIMScheduler(), precomputed_latents=True)
     emb = torch.zeros(1, 77, 1024)
     with pytest.raises(ValueError):
