@@ -183,7 +183,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def measure_microbatch(model, opt, mb, device_batch, R, dev, steps, warmup, graphs):
+def measure_microbatch(model, opt, mb, device_batch, R, dev, steps, warmup, graphs, overlap=False):
     """The reference yaml's own schedule on one GPU: the device batch is cut into microbatches of `mb` images
     (SD-2-base-256.yaml:87 device_train_microbatch_size: 16; device batch 256 = global 2048 / 8 GPUs, :2), gradients accumulate
     over the microbatches (each loss scaled by its share, as Composer does) and the optimizer steps once per device batch.
@@ -195,12 +195,15 @@ def measure_microbatch(model, opt, mb, device_batch, R, dev, steps, warmup, grap
     n_mb = max(1, device_batch // mb)
 
     def opt_step():
-        for _ in range(n_mb):
+        for i in range(n_mb):
             loss = model.loss(model(batch), batch) * (1.0 / n_mb)
+            if overlap and i == n_mb - 1:
+                opt.arm()  # the update rides on the last microbatch's backward
             loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
 
+    opt_step()
     l0 = eng.ctx.launches
     opt_step()
     torch.cuda.synchronize()
@@ -263,12 +266,15 @@ def run_ours(args):
             ctx_d.copy_(ctx_h, non_blocking=True)
         out = model(batch)
         loss = model.loss(out, batch)
+        if args.optimizer_overlap:
+            opt.arm()  # AdamW per gradient bucket inside backward (FusedAdamW.arm); opt.step() then only counts the step
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss.item() if e2e else loss
 
     # eager warm-up (also counts our kernel launches per step), then CUDA-graph capture of the static schedules
+    step(False)  # the first step binds the gradient arena
     l0 = eng.ctx.launches
     step(False)
     torch.cuda.synchronize()
@@ -359,7 +365,8 @@ def run_ours(args):
     # ---- the yaml's own microbatch (SD-2-base-256.yaml:87 device_train_microbatch_size: 16): same step, N=1 only
     yaml_mb = None
     if world == 1 and not args.in_loop and B != 16 and not args.no_secondary:
-        yaml_mb = measure_microbatch(model, opt, 16, B, R, dev, max(2, args.steps // 4), args.warmup, not args.no_graphs)
+        yaml_mb = measure_microbatch(model, opt, 16, B, R, dev, max(2, args.steps // 4), args.warmup, not args.no_graphs,
+                                     overlap=bool(args.optimizer_overlap))
     # ---- same-GPU library comparator (eager torch bf16 autocast of the oracle), N=1 only, after our arm is done
     lib = None
     if world == 1 and not args.in_loop and not args.no_secondary:
@@ -385,6 +392,8 @@ def run_ours(args):
                                + ('in-loop VAE encoder + CLIP text encoder (precomputed_latents=false), ' if args.in_loop else 'precomputed latents, ')
                                + 'random init', 'per_gpu_microbatch': B, 'global_batch': B * world,
                    'latent': [4, R, R], 'context': [77, 1024], 'params': 865910724, 'parallelism': f'dp{world}',
+                   'optimizer': 'fused AdamW, ' + ('applied per gradient bucket during backward (FusedAdamW.arm)' if args.optimizer_overlap
+                                                   else 'one launch in optimizer.step()'),
                    'cuda_graphs': not args.no_graphs,
                    'l2': 'no explicit flush: every step streams 3.5 GB of fp32 parameters + optimizer state and tens of GB of '
                          'activations, far beyond the 126 MB L2'},
@@ -412,6 +421,9 @@ def main():
     ap.add_argument('--in-loop', action='store_true',
                     help='BASELINE config 5: precomputed_latents=false, VAE encoder + CLIP text encoder run inside the step')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--optimizer-overlap', type=int, default=0, choices=[0, 1],
+                    help='1: FusedAdamW.arm() - the update runs bucket by bucket during backward; 0 (default): one launch in opt.step(). '
+                         'Measured neutral on a power-capped B200 (DESIGN.md section 4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true',
                     help='skip the informational legs (yaml microbatch 16 line, same-GPU torch library baseline)')

@@ -116,6 +116,9 @@ class ParamArena:
         if with_grads:
             ParamArena._live.append(weakref.ref(self))
         self.shadow_version = None  # parameter-version stamp the bf16 shadow was last refreshed at
+        # optimizer update applied bucket by bucket DURING the next backward (FusedAdamW.arm): hook(lo, hi) enqueues the update of
+        # arena elements [lo, hi) on the current stream; `update_applied` tells the optimizer's step() that it has run
+        self.armed_update, self.update_applied = None, False
         self.entries = {}
         off = 0
         plist = list(unet.named_parameters())
@@ -923,6 +926,30 @@ class Engine:
 
         return cm()
 
+    def _update_points(self):
+        """For every gradient bucket: the end of the backward segment after which NO later backward op touches the bucket's
+        parameters (fp32 master, bf16 shadow) or gradients - from there on the optimizer may rewrite them while the rest of
+        backward is still running (FusedAdamW.arm).  Derived from the recorded ops' address ranges, not from layer order."""
+        if getattr(self, '_update_at', None) is None:
+            a = self.arena
+            ios = [_op_io(op)[0] for op in self.bwd]  # reads + writes of every backward op
+            pts = []
+            for lo, hi, ready in self.buckets:
+                spans = [(t.data_ptr() + lo * t.element_size(), t.data_ptr() + hi * t.element_size()) for t in (a.p32, a.p16, a.g32)]
+                last = ready
+                for i in range(len(self.bwd) - 1, ready - 1, -1):
+                    if _overlap(ios[i], spans):
+                        last = i + 1
+                        break
+                pts.append(min(e for e in self.segments if e >= last))
+            self._update_at = pts
+        return self._update_at
+
+    def _side_stream(self):
+        if getattr(self, 'comm_stream', None) is None:
+            self.comm_stream = torch.cuda.Stream(self.dev)
+        return self.comm_stream
+
     def _allreduce_bucket(self, lo, hi):
         import torch.distributed as dist
         flat = self.arena.g32[lo:hi]
@@ -945,11 +972,14 @@ class Engine:
             for op in self.fwd:
                 op()
 
-    def run_backward(self):
+    def run_backward(self, allow_update=False):
         if self.forward_only:
             raise RuntimeError('this engine was built forward-only (sampling / eval): it has no backward schedule')
         sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
-        if not sync:
+        # an armed optimizer update (FusedAdamW.arm) runs bucket by bucket on the side stream, behind the bucket's all-reduce
+        update = self.arena.armed_update if allow_update and self.dev.type == 'cuda' and (sync or getattr(self, 'dp_world', 1) == 1) \
+            else None
+        if not sync and update is None:
             if self.graph_bwd is not None:
                 for g in self.graph_bwd:
                     g.replay()
@@ -966,12 +996,23 @@ class Engine:
             else:
                 for op in self.bwd[start:end]:
                     op()
-            for lo, hi, ready in self.buckets:
-                if ready == end:
+            done = None
+            for bi, (lo, hi, ready) in enumerate(self.buckets):
+                if sync and ready == end:
                     self._allreduce_bucket(lo, hi)
+                if update is not None and self._update_points()[bi] == end:
+                    side = self._side_stream()
+                    if done is None:
+                        done = torch.cuda.Event()
+                        done.record(torch.cuda.current_stream(self.dev))
+                    side.wait_event(done)
+                    with torch.cuda.stream(side):
+                        update(lo, hi)
             start = end
-        if self.comm_stream is not None:
+        if getattr(self, 'comm_stream', None) is not None:
             torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+        if update is not None:
+            self.arena.armed_update, self.arena.update_applied = None, True
 
     def _run_two_streams(self, op_list, side_flags, main, side):
         """Issue `op_list` on two streams: ops flagged `side` go to `side`, everything else to `main` (the current
@@ -1090,7 +1131,9 @@ class _UNetFn(torch.autograd.Function):
                          for n, p in plist)
         if not accumulate:
             arena.g32.zero_()
-        eng.run_backward()
+        # (the armed optimizer update clears the gradient arena as it goes: only when the gradients stay in place and no wrapper
+        # reduces them afterwards)
+        eng.run_backward(allow_update=accumulate and not getattr(eng, 'ddp_compat', False))
         if accumulate:  # gradients were accumulated in place into the arena that param.grad already views
             if getattr(eng, 'ddp_compat', False):
                 # a DistributedDataParallel wrapper reduces `param.grad` from per-parameter autograd hooks, which only fire

@@ -40,6 +40,50 @@ class FusedAdamW(torch.optim.Optimizer):
                 return arena
         return None
 
+    def _arena_state(self, gi, arena):
+        # keyed by the parameter-group index: stable across processes, so `state_dict()` / `load_state_dict()`
+        # (Composer checkpoints, reference train.py resume) carry the flat moments
+        st = self.state.setdefault('arena_group%d' % gi, {})
+        if not st:
+            st['step'] = 0
+            st['exp_avg'] = torch.zeros_like(arena.p32)
+            st['exp_avg_sq'] = torch.zeros_like(arena.p32)
+        if st['exp_avg'].numel() != arena.p32.numel():
+            raise RuntimeError('FusedAdamW: the loaded optimizer state does not match this model\'s parameter arena')
+        for k in ('exp_avg', 'exp_avg_sq'):  # a checkpoint loaded with map_location='cpu'
+            if st[k].device != arena.p32.device or st[k].dtype != torch.float32:
+                st[k] = st[k].to(device=arena.p32.device, dtype=torch.float32).contiguous()
+        st['step'] = int(st['step'])
+        return st
+
+    @torch.no_grad()
+    def arm(self):
+        """Opt in, for ONE optimizer step: apply the update DURING the coming backward, gradient bucket by gradient bucket, as
+        soon as a bucket's gradients are final (and averaged over the data-parallel group) and nothing later in backward reads
+        its weights.  The HBM-bound update then overlaps the tensor-bound rest of backward and only the last bucket's
+        all-reduce + update stay exposed; `step()` afterwards merely counts the step.  Same arithmetic as the one-launch path.
+        Call it right before the LAST backward of the step (gradient accumulation: before the last microbatch), with the
+        learning rate of this step already set, and only when nothing between backward and `step()` looks at the gradients
+        (no clipping, no GradScaler inf check) - they are consumed and cleared bucket by bucket.
+        Returns False (and changes nothing) when the parameters are not in a bound engine arena yet (first step)."""
+        armed = False
+        for gi, group in enumerate(self.param_groups):
+            arena = self._arena_of(group)
+            if arena is None:
+                continue
+            st = self._arena_state(gi, arena)
+            lr, (b1, b2), eps, wd = group['lr'], group['betas'], group['eps'], group['weight_decay']
+            step = st['step'] + 1
+            m, v = st['exp_avg'], st['exp_avg_sq']
+
+            def update(lo, hi, arena=arena, m=m, v=v, lr=lr, b1=b1, b2=b2, eps=eps, wd=wd, step=step):
+                ops.adamw_step(ops.get_ctx(arena.p32.device), arena.p32[lo:hi], arena.g32[lo:hi], m[lo:hi], v[lo:hi],
+                               arena.p16[lo:hi], lr, b1, b2, eps, wd, step, zero_grad=True)
+
+            arena.armed_update, arena.update_applied = update, False
+            armed = True
+        return armed
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -51,19 +95,13 @@ class FusedAdamW(torch.optim.Optimizer):
             lr, (b1, b2), eps, wd = group['lr'], group['betas'], group['eps'], group['weight_decay']
             arena = self._arena_of(group)
             if arena is not None:
-                # keyed by the parameter-group index: stable across processes, so `state_dict()` / `load_state_dict()`
-                # (Composer checkpoints, reference train.py resume) carry the flat moments
-                st = self.state.setdefault('arena_group%d' % gi, {})
-                if not st:
-                    st['step'] = 0
-                    st['exp_avg'] = torch.zeros_like(arena.p32)
-                    st['exp_avg_sq'] = torch.zeros_like(arena.p32)
-                if st['exp_avg'].numel() != arena.p32.numel():
-                    raise RuntimeError('FusedAdamW: the loaded optimizer state does not match this model\'s parameter arena')
-                for k in ('exp_avg', 'exp_avg_sq'):  # a checkpoint loaded with map_location='cpu'
-                    if st[k].device != arena.p32.device or st[k].dtype != torch.float32:
-                        st[k] = st[k].to(device=arena.p32.device, dtype=torch.float32).contiguous()
-                st['step'] = int(st['step'])
+                st = self._arena_state(gi, arena)
+                arena.armed_update = None  # armed, but that backward never ran: the one-launch path below
+                if arena.update_applied:  # arm(): backward has already applied this step's update, bucket by bucket
+                    arena.update_applied = False
+                    st['step'] += 1
+                    arena.mark_shadow_fresh()
+                    continue
                 st['step'] += 1
                 ctx = ops.get_ctx(arena.p32.device)
                 ops.adamw_step(ctx, arena.p32, arena.g32, st['exp_avg'], st['exp_avg_sq'], arena.p16, lr, b1, b2, eps, wd,

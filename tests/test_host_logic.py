@@ -205,6 +205,16 @@ def test_schedule_builds_and_covers_every_parameter(dry, cfg, B, R):
     hi = sorted(b[1] for b in eng.buckets)
     assert lo[0] == 0 and hi[-1] == eng.arena.total and lo[1:] == hi[:-1]
     assert [b[2] for b in eng.buckets] == sorted(b[2] for b in eng.buckets) and eng.buckets[-1][2] == len(eng.bwd)
+    # the optimizer may take over a bucket (FusedAdamW.arm) only at a segment end, never before its gradients are final, and no
+    # backward op after that point touches the bucket's weights or gradients; in this schedule that is the bucket's own end
+    pts = eng._update_points()
+    assert all(p in eng.segments and p >= b[2] for p, b in zip(pts, eng.buckets))
+    from diffusion_b200.engine import _op_io, _overlap
+    a = eng.arena
+    for p, (lo_, hi_, _) in zip(pts, eng.buckets):
+        spans = [(t.data_ptr() + lo_ * t.element_size(), t.data_ptr() + hi_ * t.element_size()) for t in (a.p32, a.p16, a.g32)]
+        assert not any(_overlap(_op_io(op)[0], spans) for op in eng.bwd[p:])
+    assert pts == [b[2] for b in eng.buckets]
     if cfg is SD2_BASE_UNET_CONFIG:
         per_image = eng.gemm_flops / B / 1e12
         assert 0.50 < per_image < 0.56  # 0.543 TFLOP/image fwd+bwd at 32x32

@@ -154,6 +154,59 @@ def test_fused_adamw_arena_path_matches_torch_adamw():
     assert torch.nn.functional.cosine_similarity(m_a, m_c, dim=0).item() > 0.9999
 
 
+def test_adamw_applied_per_bucket_during_backward():
+    """FusedAdamW.arm(): the update of a gradient bucket runs on the side stream as soon as backward is done with the bucket.
+    Same arithmetic as the one-launch step - checked eagerly and on the captured graphs, with gradient accumulation (armed on the
+    last microbatch only) and with an armed step whose backward never came."""
+    from diffusion_b200.optim import FusedAdamW
+    from oracle.unet import TINY_UNET_CONFIG
+    _, model_a, batch = _pair(TINY_UNET_CONFIG, 2, 32)
+    _, model_b, _ = _pair(TINY_UNET_CONFIG, 2, 32)
+    opt_a = FusedAdamW(model_a.parameters(), lr=1e-3, weight_decay=0.01)
+    opt_b = FusedAdamW(model_b.parameters(), lr=1e-3, weight_decay=0.01)
+    assert opt_a.arm() is False  # no arena before the first forward: nothing armed, the first step is the ordinary one
+    steps = 0
+    for phase in ('eager', 'graphs'):
+        for step in range(3):
+            for model, opt, armed in ((model_a, opt_a, True), (model_b, opt_b, False)):
+                for micro in range(2):  # two microbatches accumulate, the update rides on the second backward
+                    torch.manual_seed(100 + 10 * steps + micro)
+                    loss = model.loss(model(batch), batch) * 0.5
+                    if armed and micro == 1:
+                        assert opt.arm()  # the first microbatch's backward has bound the gradient arena
+                    loss.backward()
+                if armed:
+                    arena = model._last_engine.arena
+                    assert arena.update_applied and arena.armed_update is None
+                    l0 = model._last_engine.ctx.launches
+                opt.step()
+                if armed:
+                    assert model._last_engine.ctx.launches == l0, 'step() launched a kernel although backward applied the update'
+                opt.zero_grad(set_to_none=True)
+            steps += 1
+        for model in (model_a, model_b):
+            model._last_engine.capture_graphs()
+    arena_a, arena_b = model_a._last_engine.arena, model_b._last_engine.arena
+    torch.cuda.synchronize()
+    assert opt_a.state['arena_group0']['step'] == opt_b.state['arena_group0']['step'] == 6
+    assert arena_a.grads_bound() and float(arena_a.g32.abs().max()) == 0.0
+    assert torch.equal(arena_a.p16, arena_a.p32.to(torch.bfloat16)), 'bf16 shadow is stale'
+    d = (arena_a.p32 - arena_b.p32).abs()
+    # the two models differ only by the reduce-add order inside backward (see the torch.optim.AdamW test above)
+    assert d.max().item() <= 2 * 6 * 1e-3 + 1e-6 and d.mean().item() < 2e-5, (d.max().item(), d.mean().item())
+    for k in ('exp_avg', 'exp_avg_sq'):
+        a, b = opt_a.state['arena_group0'][k], opt_b.state['arena_group0'][k]
+        assert F.cosine_similarity(a, b, dim=0).item() > 0.99999
+    # armed, but no backward follows: step() falls back to the one-launch update on whatever gradients there are
+    torch.manual_seed(7)
+    model_a.loss(model_a(batch), batch).backward()
+    assert opt_a.arm()
+    before = arena_a.p32.clone()
+    opt_a.step()
+    opt_a.zero_grad(set_to_none=True)
+    assert opt_a.state['arena_group0']['step'] == 7 and not torch.equal(before, arena_a.p32) and arena_a.armed_update is None
+
+
 @pytest.mark.parametrize('B,H,W,L', [(2, 16, 32, 77), (1, 32, 16, 50), (5, 8, 8, 77)])
 def test_non_square_latents_and_other_context_lengths(B, H, W, L):
     """Geometries the reference accepts but its recipes do not use: non-square latents, odd batch, shorter text context."""

@@ -112,8 +112,27 @@ def main():
     torch.cuda.synchronize()
     g_ddp = torch.cat([p.grad.float().flatten() for p in m_e.unet.parameters()])
     cos_mb = torch.nn.functional.cosine_similarity(g_ddp, g_want, dim=0).item()
+    # (d) engine route with the optimizer update applied per bucket inside backward (FusedAdamW.arm), against the one-launch step
+    def train(armed, steps=3):
+        m = make()
+        m.unet.engine(2, 16, 16, 77).enable_grad_sync()
+        opt = FusedAdamW(m.parameters(), lr=1e-3)
+        for s in range(steps):
+            torch.manual_seed(3000 + s)
+            loss = m.loss(m(batch), batch)
+            if armed:
+                assert opt.arm() == (s > 0)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        return torch.cat([p.detach().float().flatten() for p in m.unet.parameters()])
+
+    p_plain, p_armed = train(False), train(True)
+    d_armed = (p_plain - p_armed).abs()
     res = {}
-    for name, gx in (('engine', ga), ('ddp+AdamW', gb), ('ddp+FusedAdamW', gc), ('ddp+microbatches', g_ddp)):
+    for name, gx in (('engine', ga), ('ddp+AdamW', gb), ('ddp+FusedAdamW', gc), ('ddp+microbatches', g_ddp),
+                     ('weights after 3 armed steps', p_armed)):
         other = gx.clone()
         dist.broadcast(other, src=0)
         res[name] = (gx - other).abs().max().item()  # ranks agree?
@@ -123,7 +142,9 @@ def main():
         print('max |grad(rank1) - grad(rank0)| per route:', res)
         print('cosine engine vs ddp+AdamW: %.6f, engine vs ddp+FusedAdamW: %.6f' % (cos_ab, cos_ac))
         print('microbatch accumulation under DDP no_sync + ddp_compat: cosine vs explicit average %.6f' % cos_mb)
-        ok = all(v < 1e-6 for v in res.values()) and cos_ab > 0.995 and cos_ac > 0.995 and cos_mb > 0.9999
+        print('AdamW per bucket inside backward vs one launch, 3 steps: max |dp| %.2e, mean |dp| %.2e' % (d_armed.max().item(), d_armed.mean().item()))
+        ok = all(v < 1e-6 for v in res.values()) and cos_ab > 0.995 and cos_ac > 0.995 and cos_mb > 0.9999 \
+            and d_armed.max().item() <= 6.1e-3 and d_armed.mean().item() < 2e-5
         print('DDP ROUTES OK' if ok else 'DDP ROUTES MISMATCH', flush=True)
         if not ok:
             os._exit(1)
