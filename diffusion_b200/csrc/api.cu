@@ -288,9 +288,9 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     if (mse) BN = 64;
   }
 
-  // 2-CTA clusters sharing the B tile through TMA multicast: decided before the tensor maps are built, because a K-major B
-  // operand is then fetched as two half-height boxes (one per CTA of the cluster)
-  bool cluster;
+  // 2-CTA clusters (B tile shared through TMA multicast, or one cta_group::2 MMA per SM pair): decided before the tensor maps
+  // are built, because a K-major B operand is then fetched as two half-height boxes (one per CTA of the cluster)
+  int cluster;
   {
     const bool bmn = d->kind == SD2_GEMM_CONV_WGRAD ? true : d->B.mn_major != 0;
     GemmKParams q = p;
@@ -298,7 +298,9 @@ int sd2_gemm(sd2_ctx* ctx, const sd2_gemm_desc* d, sd2_stream stream_) {
     q.nt = (p.N + BN - 1) / BN;
     q.splits = splits;
     q.batches = d->kind == SD2_GEMM_PLAIN ? (d->batch > 0 ? d->batch : 1) : (d->kind == SD2_GEMM_CONV_WGRAD ? d->conv.ntaps : 1);
-    cluster = gemm_use_cluster(q, BN, bmn, ctx->num_sms);
+    q.total_kb = d->kind == SD2_GEMM_CONV ? d->conv.ntaps * ((d->conv.C + 63) / 64) : (int)((d->K + 63) / 64);
+    const bool amn = d->kind == SD2_GEMM_CONV_WGRAD ? true : (d->kind == SD2_GEMM_PLAIN && d->A.mn_major != 0);
+    cluster = gemm_use_cluster(q, BN, amn, bmn, ctx->num_sms);
   }
   const int b_box_rows = cluster ? BN / 2 : BN;
 

@@ -48,6 +48,12 @@ int gemm_stages(int BN) {
   int s = (SMEM_LIMIT - 1024 - 256 - STG_TOTAL) / stage_bytes;
   return s < 2 ? 2 : (s > 8 ? 8 : s);
 }
+// cta_group::2 pair mode: a stage is the CTA's A tile and HALF of the B tile
+int gemm_stages_pair(int BN) {
+  const int stage_bytes = A_BYTES + BN * BK;
+  int s = (SMEM_LIMIT - 1024 - 256 - STG_TOTAL) / stage_bytes;
+  return s < 2 ? 2 : (s > 8 ? 8 : s);
+}
 int gemm_out_chunk(int BN) { return (BN % 128 == 0) ? 64 : 32; }
 
 struct WorkItem {
@@ -179,7 +185,7 @@ __device__ __forceinline__ float mse_target_at(const void* tgt, int dtype, long 
 template <int BN>
 __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c, const EpiPre& cur, EpiPre& nxt,
                                           uint32_t t_addr, uint8_t* stg, int lane, const CUtensorMap* tmO,
-                                          uint64_t* tmem_empty, const GemmKParams& p) {
+                                          uint64_t* tmem_empty, bool empty_on_leader, const GemmKParams& p) {
   constexpr int OUT_CH = (BN % 128 == 0) ? 64 : 32;
   const bool f32_out = t.out_mode != OUT_BF16;
   uint32_t r[32];
@@ -188,7 +194,10 @@ __device__ __forceinline__ void epi_chunk(const EpiTile& t, EpiState& st, int c,
   if (c == st.c1 - 1) {  // this warp's columns are fully read: its share of handing the TMEM buffer back to the MMA warp
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty);
+    if (lane == 0) {
+      if (empty_on_leader) mbar_arrive_cluster(tmem_empty, 0);  // cta_group::2: the even CTA's MMA warp serves both accumulators
+      else mbar_arrive(tmem_empty);
+    }
   } else {
     epi_prefetch(t, c + 1, nxt);
   }
@@ -291,9 +300,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   using Cfg = TileCfg<BN>;
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide chunks");
   static_assert(CL == 1 || (B_MN ? BN % 128 == 0 : BN % 16 == 0), "2-CTA clusters split the B tile in two halves");
+  // CL = 2: each CTA runs its own 128 x BN MMAs on a B tile the two CTAs fetch half each and multicast.
+  // CL = 3 (PAIR): cta_group::2 - the even CTA issues ONE 256 x BN MMA per K step for the pair; every CTA keeps its 128 rows of A,
+  // its HALF of B and its 128 accumulator rows, so a stage is A + B/2 (more stages, half the shared-memory reads of B per SM).
+  constexpr bool CLU = CL >= 2, PAIR = CL == 3;
+  constexpr int STAGE_B = PAIR ? A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stg_base = smem + (size_t)stages * Cfg::STAGE_BYTES;
+  uint8_t* stg_base = smem + (size_t)stages * STAGE_B;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_TOTAL);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;  // [2]
@@ -303,11 +317,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work units: one M tile (CL = 1) or a pair of M tiles, one per CTA of the cluster (CL = 2; an odd tile count leaves the
   // last pair's second CTA with an out-of-range tile: its loads are zero-filled, its stores clipped)
-  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
-  const int mtd = CL == 2 ? (p.mt + 1) / 2 : p.mt;
+  const int crank = CLU ? (int)cluster_ctarank() : 0;
+  const int mtd = CLU ? (p.mt + 1) / 2 : p.mt;
   const int n_items = mtd * p.nt * p.splits * p.batches;
-  const int unit0 = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int unit0 = CLU ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CLU ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -318,20 +332,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], CL);  // one MMA-warp commit per CTA of the cluster
+        mbar_init(&empty_bar[s], CL == 2 ? 2 : 1);  // one MMA-warp commit per issuing CTA (PAIR: the even CTA's, multicast)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full_bar[a], 1);
-        mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty_bar[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (PAIR: of both CTAs)
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_cg2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
+  if (CLU) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -346,12 +365,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint32_t ph = 0;
     const int bpi = p.cnb == 1 ? (p.cH / p.cth) * p.cws : 1;  // pixel blocks (M tiles or wgrad k-blocks) per image
     constexpr int BH = BN / 2;                          // rows of B this CTA fetches for the cluster (K-major B)
-    constexpr int NCH = BN / 64, NCH_CL = NCH / CL;     // 64-wide chunks of an MN-major B tile: all / per CTA
+    constexpr int NCH = BN / 64, NCH_CL = NCH / (CLU ? 2 : 1);     // 64-wide chunks of an MN-major B tile: all / per CTA
     const int j0 = crank * NCH_CL;
     bool first_tile = true;
     for (int item = unit0; item < n_items; item += unit_step) {
       WorkItem w = decode_item(p, item, mtd);
-      if (CL == 2) w.m_tile = 2 * w.m_tile + crank;
+      if (CLU) w.m_tile = 2 * w.m_tile + crank;
       const int n_off = w.n_tile * BN, m_off = w.m_tile * BM;
       const int ab0 = p.a_batched ? w.batch % p.a_nb0 : 0, ab1 = p.a_batched ? w.batch / p.a_nb0 : 0;
       const int bb0 = p.b_batched ? w.batch % p.b_nb0 : 0, bb1 = p.b_batched ? w.batch / p.b_nb0 : 0;
@@ -390,10 +409,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int i = 0; i < w.nkb; ++i) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
         if (elect_one()) {
-          uint8_t* a_dst = smem + (size_t)s * Cfg::STAGE_BYTES;
+          uint8_t* a_dst = smem + (size_t)s * STAGE_B;
           uint8_t* b_dst = a_dst + A_BYTES;
           uint64_t* fb = &full_bar[s];
-          const bool load_b = CL == 2 || !p.b_resident || first_tile;  // B-resident: the weight tile is already in this stage
+          const bool load_b = CLU || !p.b_resident || first_tile;  // B-resident: the weight tile is already in this stage
+          if (PAIR) {
+            // both CTAs' bytes of this stage are counted on the even CTA's barrier, which its MMA warp waits on
+            if (crank == 0) mbar_arrive_expect_tx(fb, 2 * STAGE_B);
+            if (p.kind == KIND_CONV) tma_load_4d_cg2(a_dst, &tmA, fb, cb * 64, cw0 + dw, ch0 + dh, cn0 + dn);
+            else if (!A_MN) tma_load_4d_cg2(a_dst, &tmA, fb, kcol, m_off, ab0, ab1);
+            else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) tma_load_4d_cg2(a_dst + j * CHUNK_BYTES, &tmA, fb, m_off + 64 * j, kcol, ab0, ab1);
+            }
+            // this CTA's half of the B tile: rows [crank * BN/2, +BN/2) of a K-major tile, or its NCH/2 64-wide chunks
+            if (!B_MN) {
+              if (p.kind == KIND_CONV) tma_load_4d_cg2(b_dst, &tmB, fb, cb * 64, n_off + crank * BH, tw, 0);
+              else tma_load_4d_cg2(b_dst, &tmB, fb, kcol, n_off + crank * BH, bb0, bb1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < NCH_CL; ++j) {
+                if (p.kind == KIND_CONV) tma_load_4d_cg2(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * (j0 + j), cb * 64, tw, 0);
+                else if (p.kind == KIND_PLAIN) tma_load_4d_cg2(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * (j0 + j), kcol, bb0, bb1);
+                else tma_load_4d_cg2(b_dst + j * CHUNK_BYTES, &tmB, fb, n_off + 64 * (j0 + j), dw, wh + dh, wn + dn);
+              }
+            }
+          } else {
           mbar_arrive_expect_tx(fb, load_b ? Cfg::STAGE_BYTES : A_BYTES);
           if (p.kind == KIND_CONV) {
             tma_load_4d(a_dst, &tmA, fb, cb * 64, cw0 + dw, ch0 + dh, cn0 + dn);
@@ -445,6 +486,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               }
             }
           }
+          }  // !PAIR
         }
         __syncwarp();
         // advance the k-block coordinates (warp-uniform)
@@ -483,18 +525,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // Warp-uniform loop; one elected lane (always the same one) issues the four K=16 MMAs of a stage and the commit.
     // The 64-bit smem descriptors are built once; per stage / per K step only their 14-bit address field moves
     // ((byte offset) >> 4 added to the low word), so a k-block costs a handful of instructions.
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const uint32_t smem_a0 = smem_u32(smem);
     const uint64_t adesc0 = A_MN ? umma_desc_sw128(smem_a0, CHUNK_BYTES, 1024) : umma_desc_sw128(smem_a0, 16, 1024);
     const uint64_t bdesc0 = B_MN ? umma_desc_sw128(smem_a0 + A_BYTES, CHUNK_BYTES, 1024)
                                  : umma_desc_sw128(smem_a0 + A_BYTES, 16, 1024);
     constexpr uint64_t A_KSTEP = (A_MN ? 2048 : 32) >> 4, B_KSTEP = (B_MN ? 2048 : 32) >> 4;
-    constexpr uint64_t STAGE_STEP = Cfg::STAGE_BYTES >> 4;
+    constexpr uint64_t STAGE_STEP = STAGE_B >> 4;
     int s = 0;
     uint32_t ph = 0;
     uint64_t ad = adesc0, bd = bdesc0;
     int it = 0;
-    for (int item = unit0; item < n_items; item += unit_step, ++it) {
+    const int mma_items = (PAIR && crank != 0) ? 0 : n_items;  // cta_group::2: only the even CTA issues
+    for (int item = unit0; item < mma_items; item += unit_step, ++it) {
       const WorkItem w = decode_item(p, item, mtd);
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -505,6 +548,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
+          if (PAIR) {
+            tc_mma_bf16_cg2(d_tmem, ad, bd, idesc, i != 0 ? 1u : 0u);
+            tc_mma_bf16_cg2(d_tmem, ad + A_KSTEP, bd + B_KSTEP, idesc, 1u);
+            tc_mma_bf16_cg2(d_tmem, ad + 2 * A_KSTEP, bd + 2 * B_KSTEP, idesc, 1u);
+            tc_mma_bf16_cg2(d_tmem, ad + 3 * A_KSTEP, bd + 3 * B_KSTEP, idesc, 1u);
+            tc_commit_cg2_mc(&empty_bar[s], 3);                                // both CTAs' producers may refill the stage
+            if (i == w.nkb - 1) tc_commit_cg2_mc(&tmem_full_bar[acc], 3);      // both CTAs' epilogues may read their rows
+          } else {
           tc_mma_bf16(d_tmem, ad, bd, idesc, i != 0 ? 1u : 0u);
           tc_mma_bf16(d_tmem, ad + A_KSTEP, bd + B_KSTEP, idesc, 1u);
           tc_mma_bf16(d_tmem, ad + 2 * A_KSTEP, bd + 2 * B_KSTEP, idesc, 1u);
@@ -512,6 +563,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (CL == 2) tc_commit_mc(&empty_bar[s], 3);  // the stage is shared: both CTAs' producers wait for both MMA warps
           else tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have consumed it
           if (i == w.nkb - 1) tc_commit(&tmem_full_bar[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         ad += STAGE_STEP;
@@ -541,7 +593,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool raw = p.out_mode == OUT_F32_PARTIAL;
     for (int item = unit0; item < n_items; item += unit_step, ++it) {
       WorkItem w = decode_item(p, item, mtd);
-      if (CL == 2) w.m_tile = 2 * w.m_tile + crank;
+      if (CLU) w.m_tile = 2 * w.m_tile + crank;
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       EpiTile t;
@@ -584,17 +636,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
 #pragma unroll 1
       for (int c = st.c0; c < st.c1; c += 2) {
-        epi_chunk<BN>(t, st, c, pa, pb, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc], p);
-        if (c + 1 < st.c1) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc], p);
+        epi_chunk<BN>(t, st, c, pa, pb, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc], PAIR, p);
+        if (c + 1 < st.c1) epi_chunk<BN>(t, st, c + 1, pb, pa, t_addr, stg, lane, &tmO, &tmem_empty_bar[acc], PAIR, p);
       }
     }
     if (lane == 0) bulk_wait_read<0>();  // staging smem no longer read by the copy engine; the writes complete with the grid
     __syncwarp();
   }
   tc_fence_before();
-  if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (CLU) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   else __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // out[m][n] = bf16/f32( alpha * sum_s ws[s][m][n] + bias[n] + rowbias[m/rpg][n] + residual[m][n] )
@@ -646,7 +701,8 @@ template <int BN, bool A_MN, bool B_MN, int CL>
 static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
                               int grid, int stages, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
-  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + STG_TOTAL + (2 * stages + 4) * 8 + 16 + 1024;
+  const size_t stage_bytes = CL == 3 ? A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
+  const size_t smem = (size_t)stages * stage_bytes + STG_TOTAL + (2 * stages + 4) * 8 + 16 + 1024;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, CL>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -677,25 +733,46 @@ static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 // (tools/gemm_shapes.py, SD2_GEMM_CLUSTER=0 vs 2, profiles/r02_gemm_cluster_ab.md): the implicit-GEMM convolutions (forward
 // and dgrad) gain up to 17 %, the weight gradients lose 10-80 % (their M dimension is Cout: 3 or 5 tiles pair badly, and
 // both operands are streamed), the linears are a wash.  Default policy: convolution forward / dgrad only, even M-tile
-// count or many tiles.  SD2_GEMM_CLUSTER=0 disables clusters, =2 enables them wherever the kernel supports it.
-bool gemm_use_cluster(const GemmKParams& p, int BN, bool b_mn, int num_sms) {
+// count or many tiles.  SD2_GEMM_CLUSTER=0 disables clusters, =2 enables them wherever the kernel supports it, =3 runs the
+// cta_group::2 pair mode (one 256-row MMA per SM pair) wherever it is instantiated.  Returns 0 / 2 / 3 (the kernel's CL).
+int gemm_use_cluster(const GemmKParams& p, int BN, bool a_mn, bool b_mn, int num_sms) {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("SD2_GEMM_CLUSTER");
     mode = e ? atoi(e) : 1;
   }
-  if (mode == 0) return false;
-  if (b_mn && BN < 128) return false;  // an MN-major B tile needs two 64-wide chunks to split
-  if (p.mt < 2) return false;
+  if (mode == 0) return 0;
+  if (b_mn && BN < 128) return 0;  // an MN-major B tile needs two 64-wide chunks to split
+  if (p.mt < 2) return 0;
   const long long pair_items = (long long)((p.mt + 1) / 2) * p.nt * p.splits * p.batches;
-  if (pair_items < num_sms / 2) return false;
-  if (mode == 2) return true;
-  return p.kind == KIND_CONV && (p.mt % 2 == 0 || p.mt >= 32);
+  if (pair_items < num_sms / 2) return 0;
+  const bool pair_ok = BN == 256 || (BN == 160 && !b_mn);  // the instantiated cta_group::2 kernels
+  if (mode == 2) return 2;
+  if (mode == 3) return pair_ok ? 3 : 0;  // cta_group::2 wherever it is instantiated (A/B runs)
+  // cta_group::2 (profiles/r02_gemm_pair_ab.md): K-major linears with a long contraction (K >= 1024) and M >= 16384 gain 4-10 %;
+  // MN-major operands (every weight gradient, the dgrads) and the K = 320 layers lose, the convolutions are +-3 % around the
+  // multicast variant
+  static const int pair_rule = getenv("SD2_GEMM_PAIR") ? atoi(getenv("SD2_GEMM_PAIR")) : 1;  // 0: A/B switch for this rule
+  if (pair_rule && pair_ok && p.kind == KIND_PLAIN && !a_mn && !b_mn && p.total_kb >= 16 && p.mt >= 128 && p.splits == 1 && p.batches == 1) return 3;
+  return (p.kind == KIND_CONV && (p.mt % 2 == 0 || p.mt >= 32)) ? 2 : 0;
 }
 
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
-                           int BN, bool a_mn, bool b_mn, bool cluster, int num_sms, cudaStream_t stream) {
+                           int BN, bool a_mn, bool b_mn, int cluster, int num_sms, cudaStream_t stream) {
   const int st = gemm_stages(BN);
+  if (cluster == 3) {
+    const long long items = (long long)((p.mt + 1) / 2) * p.nt * p.splits * p.batches;
+    const int ncl = (int)(items < num_sms / 2 ? items : num_sms / 2);
+    const int grid = 2 * ncl, stp = gemm_stages_pair(BN);
+#define SD2_GEMM_CASE(bn, amn, bmn) \
+  if (BN == bn && a_mn == amn && b_mn == bmn) return launch_one<bn, amn, bmn, 3>(tmA, tmB, tmO, p, grid, stp, stream);
+    SD2_GEMM_CASE(256, false, false) SD2_GEMM_CASE(160, false, false)
+    SD2_GEMM_CASE(256, false, true)
+    SD2_GEMM_CASE(256, true, false) SD2_GEMM_CASE(160, true, false)
+    SD2_GEMM_CASE(256, true, true)
+#undef SD2_GEMM_CASE
+    return cudaErrorInvalidValue;
+  }
   if (cluster) {
     const long long items = (long long)((p.mt + 1) / 2) * p.nt * p.splits * p.batches;
     const int ncl = (int)(items < num_sms / 2 ? items : num_sms / 2);

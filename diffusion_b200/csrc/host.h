@@ -47,9 +47,9 @@ bool plain_tmap(CUtensorMap* tm, const sd2_operand& o, int box_rows, std::string
 bool out_tmap(CUtensorMap* tm, void* ptr, bool f32, int chunk_cols, int N, int M, long long ldo, long long nb0,
               long long nb1, long long bs0, long long bs1, std::string* err);
 // cluster: run as 2-CTA clusters that share the B tile through TMA multicast (tmB of a K-major B then has BN/2-row boxes)
-bool gemm_use_cluster(const GemmKParams& p, int BN, bool b_mn, int num_sms);
+int gemm_use_cluster(const GemmKParams& p, int BN, bool a_mn, bool b_mn, int num_sms);  // 0 / 2 (multicast B) / 3 (cta_group::2)
 cudaError_t launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKParams& p,
-                           int BN, bool a_mn, bool b_mn, bool cluster, int num_sms, cudaStream_t stream);
+                           int BN, bool a_mn, bool b_mn, int cluster, int num_sms, cudaStream_t stream);
 cudaError_t launch_splitk_finalize(const float* ws, int splits, long long M, int N, float alpha, const float* bias,
                                    const float* rowbias, int rows_per_group, long long ld_rowbias, const bf16* residual,
                                    long long ldr, void* out, long long ldo, int out_f32, cudaStream_t stream);
