@@ -9,10 +9,10 @@ import re
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OPS = ['UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAREDG', 'UBLKCP', 'UTCBAR', 'SYNCS', 'UCGABAR_ARV', 'MUFU', 'REDG',
+OPS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAREDG', 'UBLKCP', 'UTCBAR', 'SYNCS', 'UCGABAR_ARV', 'MUFU', 'REDG',
        'LDS', 'STS', 'LD', 'ST', 'LDL', 'STL']
 print('`cuobjdump -sass build/*.o` (nvcc 12.9, `-gencode arch=compute_100a,code=sm_100a`), instruction counts per kernel '
-      '(static SASS, not executed counts).  UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG / UTMAREDG = '
+      '(static SASS, not executed counts).  UTCHMMA = tcgen05.mma (UTCHMMA.2CTA = the cta_group::2 form, also counted under UTCHMMA), LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG / UTMAREDG = '
       'TMA tensor load / store / reduce (`.MULTICAST` counted with UTMALDG), UBLKCP = cp.async.bulk, UTCBAR = tcgen05.commit, '
       'SYNCS = mbarrier ops, UCGABAR = cluster barrier; LD / ST = generic-address loads / stores, LDL / STL = local memory.\n')
 print('| object | kernel | total | ' + ' | '.join(OPS) + ' |')
@@ -29,6 +29,8 @@ for obj in sorted(glob.glob(os.path.join(ROOT, 'build', '*.o'))):
         m = re.search(r'^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)', line)
         if m and cur:
             cnt[cur][m.group(1).split('.')[0]] += 1
+            if m.group(1).startswith('UTCHMMA.2CTA'):
+                cnt[cur]['UTCHMMA.2CTA'] += 1
             cnt[cur]['_total'] += 1
     for k, c in cnt.items():
         name = subprocess.run(['c++filt', k], capture_output=True, text=True).stdout.strip()
