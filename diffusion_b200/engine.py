@@ -977,8 +977,7 @@ class Engine:
             raise RuntimeError('this engine was built forward-only (sampling / eval): it has no backward schedule')
         sync = getattr(self, 'sync_grads', False) and getattr(self, 'dp_world', 1) > 1
         # an armed optimizer update (FusedAdamW.arm) runs bucket by bucket on the side stream, behind the bucket's all-reduce
-        update = self.arena.armed_update if allow_update and self.dev.type == 'cuda' and (sync or getattr(self, 'dp_world', 1) == 1) \
-            else None
+        update = self.arena.armed_update if allow_update and (sync or getattr(self, 'dp_world', 1) == 1) else None
         if not sync and update is None:
             if self.graph_bwd is not None:
                 for g in self.graph_bwd:
@@ -1001,6 +1000,9 @@ class Engine:
                 if sync and ready == end:
                     self._allreduce_bucket(lo, hi)
                 if update is not None and self._update_points()[bi] == end:
+                    if self.dev.type != 'cuda':  # host-logic tests (dry run): no streams, same order
+                        update(lo, hi)
+                        continue
                     side = self._side_stream()
                     if done is None:
                         done = torch.cuda.Event()

@@ -220,6 +220,48 @@ def test_schedule_builds_and_covers_every_parameter(dry, cfg, B, R):
         assert 0.50 < per_image < 0.56  # 0.543 TFLOP/image fwd+bwd at 32x32
 
 
+def test_armed_optimizer_update_runs_bucket_by_bucket_inside_backward(dry):
+    """FusedAdamW.arm(): one sd2_adamw_step per gradient bucket, issued right after the last backward op that touches the bucket,
+    in completion order; step() then only counts.  Unarmed, step() is the single launch over the whole arena."""
+    from diffusion_b200.optim import FusedAdamW
+    from diffusion_b200.unet import UNet2DConditionModel
+    u = UNet2DConditionModel(**TINY_UNET_CONFIG)
+    eng = u.engine(2, 32, 32, 77)
+    arena, lib = eng.arena, eng.ctx.lib
+    opt = FusedAdamW(u.parameters(), lr=1e-3)
+    assert opt.arm() is False  # gradients not bound to the arena yet
+    for n, p in arena.params.items():
+        p.grad = arena.grad_view(n)
+    pts = eng._update_points()
+    log = []
+    eng.bwd = [(lambda i=i, op=op: (log.append(i), op())) for i, op in enumerate(eng.bwd)]
+    assert opt.arm() is True
+    hook = arena.armed_update
+    arena.armed_update = lambda lo, hi: (log.append(('update', lo, hi)), hook(lo, hi))
+    eng.run_forward()
+    before = lib.calls.get('sd2_adamw_step', 0)
+    eng.run_backward(allow_update=True)
+    assert lib.calls['sd2_adamw_step'] - before == len(eng.buckets)
+    ups = [(i, e) for i, e in enumerate(log) if isinstance(e, tuple)]
+    assert [e[1:] for _, e in ups] == [(lo, hi) for lo, hi, _ in eng.buckets]
+    for (pos, _), pt in zip(ups, pts):
+        prev = [e for e in log[:pos] if not isinstance(e, tuple)]
+        assert prev[-1] == pt - 1 and len(prev) == pt  # every backward op up to the bucket's update point ran before it
+    assert arena.update_applied and arena.armed_update is None
+    opt.step()
+    assert lib.calls['sd2_adamw_step'] - before == len(eng.buckets) and opt.state['arena_group0']['step'] == 1
+    assert not arena.update_applied
+    # unarmed: the ordinary one-launch step; an armed step whose backward never ran falls back to it as well
+    log.clear()
+    eng.run_backward(allow_update=True)
+    assert not any(isinstance(e, tuple) for e in log)
+    opt.step()
+    assert lib.calls['sd2_adamw_step'] - before == len(eng.buckets) + 1 and opt.state['arena_group0']['step'] == 2
+    assert opt.arm() is True
+    opt.step()
+    assert lib.calls['sd2_adamw_step'] - before == len(eng.buckets) + 2 and arena.armed_update is None
+
+
 def test_low_precision_norm_surgery_finds_nothing_to_replace():
     """reference train.py:91-108 runs composer's module surgery over `model.unet`, replacing every nn.GroupNorm / nn.LayerNorm
     instance by a new module with new parameters; the product's norm holders must not be such instances (their parameters
