@@ -145,6 +145,8 @@ SIGNATURES = {
     'sd2_axpby': (_i, [_vp, _vp, _f, _vp, _f, _vp, _ll, _vp]),
     'sd2_copy2d': (_i, [_vp, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp]),
     'sd2_upsample2x_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'sd2_upconv_weff_build': (_i, [_vp, _vp, _vp, _ll, _vp]),
+    'sd2_upconv_wgrad_scatter': (_i, [_vp, _vp, _vp, _ll, _vp]),
     'sd2_upsample2x_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'sd2_phase_split': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'sd2_phase_merge': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -40,6 +40,7 @@ _OP_WRITES = {
     'axpby': ((4,), ()), 'copy2d': ((1,), ()), 'concat_stats': ((2, 3), ()), 'upsample2x_fwd': ((1,), ()), 'upsample2x_bwd': ((1,), ()),
     'phase_split': ((1,), ()), 'phase_merge': ((1,), ()), 'colsum': ((1,), ()), 'cast_f32_to_bf16': ((1,), ()),
     'pad_cast_rows': ((2,), ()), 'unpad_accum_rows': ((2,), ()), 'fill_f32': ((0,), ()),
+    'upconv_weff_build': ((1,), ()), 'upconv_wgrad_scatter': ((1,), ()),
 }
 
 
@@ -217,6 +218,7 @@ class Engine:
         self._norm_emitted = set()  # bias parameters whose gradient a GroupNorm backward produced
         import os
         self.fuse_gn_stats = os.environ.get('SD2_NO_GN_FUSION') != '1'  # A/B switch of the epilogue GroupNorm statistics
+        self.fold_upsample = os.environ.get('SD2_NO_UPCONV_FOLD') != '1'  # A/B switch: Upsample2D as four 4-tap phase convolutions
         self.gn_part = None  # scratch of those statistics: written by a producer's epilogue, read by the norm right behind it
         reuse = shared is not None and getattr(shared, 'ws', None) is not None
         self.ws = shared.ws if reuse else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -319,7 +321,7 @@ class Engine:
         self.fwd.append(op)
         self.fwd_is_gemm.append(fn in _GEMM_FUNCS)
         self.fwd_side.append(bool(side))
-        self._count_flops(fn, a)
+        self._count_flops(fn, a, k)
         return op
 
     def b(self, fn, *a, side=None, **k):
@@ -332,7 +334,7 @@ class Engine:
         self.bwd.append(op)
         self.bwd_is_gemm.append(fn in _GEMM_FUNCS)
         self.bwd_side.append(bool(side))
-        self._count_flops(fn, a)
+        self._count_flops(fn, a, k)
 
     @staticmethod
     def _attach_plan(fn, a, k):
@@ -346,16 +348,16 @@ class Engine:
         g = self.arena.g32
         return g.data_ptr() <= t.data_ptr() < g.data_ptr() + g.numel() * 4
 
-    def _count_flops(self, fn, a):
+    def _count_flops(self, fn, a, k=None):
+        ntaps = len(k['taps']) if k and k.get('taps') else 9
         if fn in (ops.linear_fwd, ops.linear_dgrad):
             self.gemm_flops += 2 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0 if fn is ops.linear_fwd else 1]
         elif fn is ops.linear_wgrad:
             self.gemm_flops += 2 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1]
         elif fn in (ops.conv3x3_fwd, ops.conv3x3_dgrad):  # (x, B, H, W, w9, ...)
-            taps = 9
-            self.gemm_flops += 2 * a[1] * a[2] * a[3] * a[4].shape[1] * a[4].shape[2] * taps
+            self.gemm_flops += 2 * a[1] * a[2] * a[3] * a[4].shape[1] * a[4].shape[2] * ntaps
         elif fn is ops.conv3x3_wgrad:  # (dy, x, B, H, W, dw9)
-            self.gemm_flops += 2 * a[2] * a[3] * a[4] * a[5].shape[1] * min(a[5].shape[2], a[1].shape[1]) * 9
+            self.gemm_flops += 2 * a[2] * a[3] * a[4] * a[5].shape[1] * min(a[5].shape[2], a[1].shape[1]) * ntaps
         elif fn is ops.bmm:  # (..., M, N, K, batch, nb0) at positions 9..12
             self.gemm_flops += 2 * a[9] * a[10] * a[11] * a[12]
 
@@ -599,6 +601,45 @@ class Engine:
         return out
 
     def upsample(self, x, Hc, Wc, prefix):
+        """Upsample2D (nearest x2, then 3x3 conv) without the 4x tensor: the four output phases are 4-tap convolutions of the
+        low-resolution input with summed weights (ops.upconv_weff_build) - 16 instead of 36 tap-products per input pixel, in
+        forward, dgrad and wgrad alike; the phase planes are interleaved by the stride-2 merge kernel."""
+        if not self.fold_upsample:
+            return self._upsample_materialised(x, Hc, Wc, prefix)
+        B, C, M = self.B, x.C, x.M
+        w32, bias = self.p32(prefix + '.weight'), self.p32(prefix + '.bias')  # fp32 master taps [9, Cout, Cin]
+        Cout = w32.shape[1]
+        weff = self.buf(16, Cout, C)
+        planes = self.buf(4 * M, Cout)
+        out = self.node(4 * M, Cout)
+        self._use(x)
+        self.f(ops.upconv_weff_build, w32, weff)
+        for ph in range(4):
+            self.f(ops.conv3x3_fwd, x.data, B, Hc, Wc, weff[4 * ph:4 * ph + 4], planes[ph * M:(ph + 1) * M], bias=bias,
+                   taps=ops.taps_upconv(ph), workspace=self.ws)
+        self.f(ops.phase_merge, planes, out.data, B, 2 * Hc, 2 * Wc)
+
+        def bwd():
+            g = out.grad
+            assert out.gw
+            gplanes = self.buf(4 * M, Cout)
+            dweff = self.buf(16, Cout, C, dtype=torch.float32)
+            self.b(ops.phase_split, g, gplanes, B, 2 * Hc, 2 * Wc)
+            gx, acc = self._gout(x)
+            for ph in range(4):
+                self.b(ops.conv3x3_dgrad, gplanes[ph * M:(ph + 1) * M], B, Hc, Wc, weff[4 * ph:4 * ph + 4], gx,
+                       residual=gx if (acc or ph > 0) else None, taps=ops.taps_upconv_dgrad(ph), workspace=self.ws)
+            self.b(ops.fill_f32, dweff.view(-1), 0.0)
+            for ph in range(4):
+                self.b(ops.conv3x3_wgrad, gplanes[ph * M:(ph + 1) * M], x.data, B, Hc, Wc, dweff[4 * ph:4 * ph + 4],
+                       taps=ops.taps_upconv(ph))
+            self.b(ops.upconv_wgrad_scatter, dweff, self.g32(prefix + '.weight'))
+            self.b(ops.colsum, g, self.g32(prefix + '.bias'), 1, 4 * M, True)
+
+        self._bwd_builders.append(bwd)
+        return out
+
+    def _upsample_materialised(self, x, Hc, Wc, prefix):
         up = self.node(4 * x.M, x.C)
         self._use(x)
         self.f(ops.upsample2x_fwd, x.data, up.data, self.B, Hc, Wc)

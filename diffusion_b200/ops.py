@@ -426,6 +426,33 @@ def upsample2x_bwd(ctx, dy, dx, B, H, W):
     ctx.check(ctx.lib.sd2_upsample2x_bwd(ctx.h, _p(dy), _p(dx), B, H, W, dy.shape[1], _s()))
 
 
+def _upconv_groups(parity):
+    """Row (or column) groups of the 3 kernel rows for output parity `parity`: [(shift, [kernel indices])]."""
+    return [(-1, [0]), (0, [1, 2])] if parity == 0 else [(0, [0, 1]), (1, [2])]
+
+
+def taps_upconv(phase):
+    """Taps of output phase (py, px) = (phase // 2, phase % 2) of conv3x3(nearest_up2(x)) over the LOW-resolution x:
+    [(dh, dw, 0, tap)] with tap = a * 2 + b indexing weff[phase] (sd2_upconv_weff_build)."""
+    py, px = phase >> 1, phase & 1
+    return [(dh, dw, 0, a * 2 + b) for a, (dh, _) in enumerate(_upconv_groups(py)) for b, (dw, _) in enumerate(_upconv_groups(px))]
+
+
+def taps_upconv_dgrad(phase):
+    """dx[p] += sum_t dy_phase[p - d_t] weff[phase][t]^T."""
+    return [(-dh, -dw, 0, t) for dh, dw, _, t in taps_upconv(phase)]
+
+
+def upconv_weff_build(ctx, w9, weff):
+    """w9: fp32 [9, Cout, Cin] (storage layout of the master weights) -> weff: bf16 [16, Cout, Cin]."""
+    ctx.check(ctx.lib.sd2_upconv_weff_build(ctx.h, _p(w9), _p(weff), w9.shape[1] * w9.shape[2], _s()))
+
+
+def upconv_wgrad_scatter(ctx, dweff, dw9):
+    """dw9 (fp32 [9, Cout, Cin]) += adjoint of upconv_weff_build applied to dweff (fp32 [16, Cout, Cin])."""
+    ctx.check(ctx.lib.sd2_upconv_wgrad_scatter(ctx.h, _p(dweff), _p(dw9), dw9.shape[1] * dw9.shape[2], _s()))
+
+
 def phase_split(ctx, x, planes, B, H, W):
     ctx.check(ctx.lib.sd2_phase_split(ctx.h, _p(x), _p(planes), B, H, W, x.shape[1], _s()))
 

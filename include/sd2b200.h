@@ -198,6 +198,12 @@ int sd2_copy2d(sd2_ctx* ctx, const void* src, long long lds, void* dst, long lon
                int accumulate, sd2_stream stream);
 int sd2_upsample2x_fwd(sd2_ctx* ctx, const void* x, void* y, int B, int H, int W, int C, sd2_stream stream);
 int sd2_upsample2x_bwd(sd2_ctx* ctx, const void* dy, void* dx, int B, int H, int W, int C, sd2_stream stream);
+/* Upsample2D = nearest x2 + 3x3 conv (diffusers resnet.py::Upsample2D, reached from models.py:74-78) without the 4x tensor:
+ * every output phase (py, px) is a 4-tap convolution of the low-resolution input with summed weights.
+ * weff16: bf16 [16 = phase*4 + tap][Cout][Cin] built from the fp32 taps w9 [9][Cout][Cin]; n = Cout*Cin.
+ * scatter: dw9[t] += sum of the dweff16 (fp32) entries whose group contains tap t - the exact adjoint of the build. */
+int sd2_upconv_weff_build(sd2_ctx* ctx, const float* w9, void* weff16, long long n, sd2_stream stream);
+int sd2_upconv_wgrad_scatter(sd2_ctx* ctx, const float* dweff16, float* dw9, long long n, sd2_stream stream);
 /* stride-2 phase split: x [B][H][W][C] -> planes [4][B][H/2][W/2][C], plane = (h%2)*2 + (w%2); and inverse */
 int sd2_phase_split(sd2_ctx* ctx, const void* x, void* planes, int B, int H, int W, int C, sd2_stream stream);
 int sd2_phase_merge(sd2_ctx* ctx, const void* planes, void* x, int B, int H, int W, int C, sd2_stream stream);

@@ -262,6 +262,57 @@ def test_conv3x3_stride2(ctx, B, H, W, Cc):
     close(dx, x.grad, name='s2 dgrad')
 
 
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 8, 8, 64, 64), (1, 16, 16, 128, 64), (3, 4, 4, 64, 128), (16, 16, 16, 640, 640)])
+def test_upsample_conv_as_four_phase_convs(ctx, B, H, W, Cin, Cout):
+    """Upsample2D: conv3x3(nearest x2 (x)) computed as four 4-tap convolutions of the low-resolution x with summed weights
+    (sd2_upconv_weff_build), forward, dgrad and wgrad (+ sd2_upconv_wgrad_scatter), against torch on the upsampled tensor."""
+    from diffusion_b200 import ops
+    M = B * H * W
+    x = bf(M, Cin, seed=1).float().requires_grad_(True)
+    w9 = (torch.randn(9, Cout, Cin, device='cuda', generator=torch.Generator(device='cuda').manual_seed(2)) * (9 * Cin)**-0.5).requires_grad_(True)
+    bias = torch.randn(Cout, device='cuda')
+    dy = bf(4 * M, Cout, seed=5)
+    up = F.interpolate(x.view(B, H, W, Cin).permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
+    wt = w9.view(3, 3, Cout, Cin).permute(2, 3, 0, 1)
+    y = (F.conv2d(up, wt, padding=1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(4 * M, Cout)
+    y.backward(dy.float())
+    # build + its adjoint are exact linear maps of each other
+    weff = torch.empty(16, Cout, Cin, dtype=torch.bfloat16, device='cuda')
+    ops.upconv_weff_build(ctx, w9.detach(), weff)
+    sel = torch.zeros(16, 9, device='cuda')
+    for ph in range(4):
+        for a, (_, kys) in enumerate(ops._upconv_groups(ph >> 1)):
+            for b, (_, kxs) in enumerate(ops._upconv_groups(ph & 1)):
+                for ky in kys:
+                    for kx in kxs:
+                        sel[ph * 4 + a * 2 + b, ky * 3 + kx] = 1.0
+    want = torch.einsum('pt,tnk->pnk', sel, w9.detach())
+    assert torch.equal(weff, want.to(torch.bfloat16)) or (weff.float() - want).abs().max() <= 2**-8 * want.abs().max()
+    xb = x.detach().to(torch.bfloat16)
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device='cuda')
+    planes = torch.empty(4 * M, Cout, dtype=torch.bfloat16, device='cuda')
+    for ph in range(4):
+        ops.conv3x3_fwd(ctx, xb, B, H, W, weff[4 * ph:4 * ph + 4], planes[ph * M:(ph + 1) * M], bias=bias, taps=ops.taps_upconv(ph),
+                        workspace=ws)
+    out = torch.empty(4 * M, Cout, dtype=torch.bfloat16, device='cuda')
+    ops.phase_merge(ctx, planes, out, B, 2 * H, 2 * W)
+    close(out, y.detach(), name='upconv fwd')
+    gplanes = torch.empty(4 * M, Cout, dtype=torch.bfloat16, device='cuda')
+    ops.phase_split(ctx, dy, gplanes, B, 2 * H, 2 * W)
+    dx = torch.empty(M, Cin, dtype=torch.bfloat16, device='cuda')
+    for ph in range(4):
+        ops.conv3x3_dgrad(ctx, gplanes[ph * M:(ph + 1) * M], B, H, W, weff[4 * ph:4 * ph + 4], dx, residual=dx if ph else None,
+                          taps=ops.taps_upconv_dgrad(ph), workspace=ws)
+    close(dx, x.grad, name='upconv dgrad')
+    dweff = torch.zeros(16, Cout, Cin, dtype=torch.float32, device='cuda')
+    for ph in range(4):
+        ops.conv3x3_wgrad(ctx, gplanes[ph * M:(ph + 1) * M], xb, B, H, W, dweff[4 * ph:4 * ph + 4], taps=ops.taps_upconv(ph))
+    dw = torch.ones(9, Cout, Cin, dtype=torch.float32, device='cuda')  # accumulates
+    ops.upconv_wgrad_scatter(ctx, dweff, dw)
+    close(dw - 1.0, w9.grad, rtol=2e-3, atol=2e-3 * w9.grad.abs().max().item(), name='upconv wgrad')
+    assert torch.allclose(dw - 1.0, torch.einsum('pt,pnk->tnk', sel, dweff), rtol=1e-5, atol=1e-5 * dweff.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ batched (attention)
 @pytest.mark.parametrize('B,heads,Nq,Nk', [(2, 5, 1024, 1024), (2, 10, 256, 77), (1, 4, 64, 64), (2, 2, 16, 77)])
 def test_attention_pieces(ctx, B, heads, Nq, Nk):

@@ -5,7 +5,7 @@ and latent size, time the kernel under each (tile width BN, K-split) it supports
 buffers - and keep the fastest.  Output: a JSON table {shape key: [BN, splits, best us, planner us]} that is merged
 into diffusion_b200/gemm_plans.json (the engine reads it at build time; unknown shapes use the library's cycle model).
 
-Usage (on a B200): SD2_NO_PLANS=1 python tools/autotune_gemm.py B latent out.json [B latent ...]
+Usage (on a B200): SD2_NO_PLANS=1 [SD2_TUNE_ONLY=substr,substr] python tools/autotune_gemm.py B latent out.json [B latent ...]
 """
 import json
 import os
@@ -59,6 +59,9 @@ def tune(B, R, table):
             continue
         key = ops.gemm_key(name, op.args[1:], op.keywords)
         if key is None:
+            continue
+        only = os.environ.get('SD2_TUNE_ONLY')  # comma-separated substrings: tune only the shape keys containing one of them
+        if only and not any(x in key for x in only.split(',')):
             continue
         seen.setdefault(key, [op, 0])[1] += 1
     tot_def = tot_best = 0.0
