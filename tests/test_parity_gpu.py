@@ -42,6 +42,15 @@ def test_tiny_train_step_parity(B, R):
     _check(parity.step_triplet(TINY_UNET_CONFIG, B, R))
 
 
+def test_tiny_train_step_parity_materialised_upsample(monkeypatch):
+    """Small launches keep the nearest-neighbour upsample as a 4x tensor + 9-tap conv (Engine.fold_upsample_min_rows)."""
+    from oracle.unet import TINY_UNET_CONFIG
+    monkeypatch.setenv('SD2_UPCONV_FOLD_MIN_ROWS', '1000000000')
+    res = parity.step_triplet(TINY_UNET_CONFIG, 2, 32)
+    _check(res)
+    assert res['model']._last_engine.ctx.lib is not None and res['model']._last_engine.fold_upsample_min_rows == 1000000000
+
+
 def test_forward_is_bit_deterministic_and_gradients_repeat():
     """Two runs of the same step: identical prediction bits; gradients agree to cosine > 0.999999 per tensor.  Every bf16
     activation gradient is bit-reproducible (the attention backward adds the key tiles' dQ contributions in a fixed order);

@@ -162,16 +162,21 @@ def test_adamw_applied_per_bucket_during_backward():
     from oracle.unet import TINY_UNET_CONFIG
     _, model_a, batch = _pair(TINY_UNET_CONFIG, 2, 32)
     _, model_b, _ = _pair(TINY_UNET_CONFIG, 2, 32)
-    opt_a = FusedAdamW(model_a.parameters(), lr=1e-3, weight_decay=0.01)
-    opt_b = FusedAdamW(model_b.parameters(), lr=1e-3, weight_decay=0.01)
+    # eps far above the gradient scale keeps Adam's update linear in the gradient, so the 1e-7-level arrival-order differences of
+    # the fp32 gradient sums between two runs stay that small in the weights and the comparison can be tight
+    opt_a = FusedAdamW(model_a.parameters(), lr=1e-3, weight_decay=0.01, eps=1e-2)
+    opt_b = FusedAdamW(model_b.parameters(), lr=1e-3, weight_decay=0.01, eps=1e-2)
     assert opt_a.arm() is False  # no arena before the first forward: nothing armed, the first step is the ordinary one
     steps = 0
+    before_training = None
     for phase in ('eager', 'graphs'):
         for step in range(3):
             for model, opt, armed in ((model_a, opt_a, True), (model_b, opt_b, False)):
                 for micro in range(2):  # two microbatches accumulate, the update rides on the second backward
                     torch.manual_seed(100 + 10 * steps + micro)
                     loss = model.loss(model(batch), batch) * 0.5
+                    if before_training is None:
+                        before_training = model._last_engine.arena.p32.clone()
                     if armed and micro == 1:
                         assert opt.arm()  # the first microbatch's backward has bound the gradient arena
                     loss.backward()
@@ -192,8 +197,11 @@ def test_adamw_applied_per_bucket_during_backward():
     assert arena_a.grads_bound() and float(arena_a.g32.abs().max()) == 0.0
     assert torch.equal(arena_a.p16, arena_a.p32.to(torch.bfloat16)), 'bf16 shadow is stale'
     d = (arena_a.p32 - arena_b.p32).abs()
-    # the two models differ only by the reduce-add order inside backward (see the torch.optim.AdamW test above)
-    assert d.max().item() <= 2 * 6 * 1e-3 + 1e-6 and d.mean().item() < 2e-5, (d.max().item(), d.mean().item())
+    # the two models differ only by the reduce-add order inside backward
+    # (observed over repeated runs: max <= 1.3e-5, mean <= 1.9e-7; a bucket that missed one update would move its eighth of the
+    # weights by 1e-5 .. 1e-4 each)
+    assert d.max().item() <= 5e-5 and d.mean().item() < 1e-6, (d.max().item(), d.mean().item())
+    assert (arena_a.p32 - before_training).abs().max().item() > 1e-5  # and they did train
     for k in ('exp_avg', 'exp_avg_sq'):
         a, b = opt_a.state['arena_group0'][k], opt_b.state['arena_group0'][k]
         assert F.cosine_similarity(a, b, dim=0).item() > 0.99999
