@@ -501,6 +501,52 @@ using namespace sd2;
 #define SD2_BF(p) reinterpret_cast<const bf16*>(p)
 #define SD2_BFW(p) reinterpret_cast<bf16*>(p)
 
+// ---- nearest-neighbour x2 upsample folded into the 3x3 convolution that follows it (Upsample2D)
+// conv3x3(up2(x))[2h+py, 2w+px] only sees 2 x 2 distinct low-resolution pixels: the 3 kernel rows collapse to two row groups
+// (py = 0: {0} at dh = -1, {1, 2} at dh = 0; py = 1: {0, 1} at dh = 0, {2} at dh = +1), likewise the columns.  Each of the four
+// output phases is therefore a 4-tap convolution of x with summed weights: 16 instead of 36 tap-products per low-res pixel.
+// weff[phase = py*2+px][tap = a*2+b][Cout][Cin] (bf16) = sum of the fp32 master taps of row group a x column group b.
+namespace sd2 {
+__device__ __forceinline__ int upconv_group(int parity, int k) { return parity == 0 ? (k >= 1) : (k >= 2); }
+__global__ void __launch_bounds__(256) upconv_weff_build_kernel(const float* __restrict__ w9, bf16* __restrict__ weff, long long n) {
+  pdl_grid_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t] = w9[t * n + i];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc[upconv_group(py, ky) * 2 + upconv_group(px, kx)] += w[ky * 3 + kx];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) weff[(ph * 4 + t) * n + i] = __float2bfloat16_rn(acc[t]);
+    }
+  }
+}
+// dw9[ky*3+kx] += sum over the four phases of dweff[phase][group tap that contains (ky, kx)]   (fp32, accumulating)
+__global__ void __launch_bounds__(256) upconv_wgrad_scatter_kernel(const float* __restrict__ dweff, float* __restrict__ dw9, long long n) {
+  pdl_grid_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) d[t] = dweff[t * n + i];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float g = 0.f;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) g += d[ph * 4 + upconv_group(ph >> 1, ky) * 2 + upconv_group(ph & 1, kx)];
+        dw9[(ky * 3 + kx) * n + i] += g;
+      }
+  }
+}
+}  // namespace sd2
+
 extern "C" {
 
 int sd2_softmax_fwd(sd2_ctx* ctx, const float* S, long long lds, void* P, long long ldp, long long rows, int cols,
@@ -592,51 +638,6 @@ int sd2_upsample2x_bwd(sd2_ctx* ctx, const void* dy, void* dx, int B, int H, int
                                                                                                        B, H, W, C);
   return check_launch(ctx, "upsample2x_bwd");
 }
-// ---- nearest-neighbour x2 upsample folded into the 3x3 convolution that follows it (Upsample2D)
-// conv3x3(up2(x))[2h+py, 2w+px] only sees 2 x 2 distinct low-resolution pixels: the 3 kernel rows collapse to two row groups
-// (py = 0: {0} at dh = -1, {1, 2} at dh = 0; py = 1: {0, 1} at dh = 0, {2} at dh = +1), likewise the columns.  Each of the four
-// output phases is therefore a 4-tap convolution of x with summed weights: 16 instead of 36 tap-products per low-res pixel.
-// weff[phase = py*2+px][tap = a*2+b][Cout][Cin] (bf16) = sum of the fp32 master taps of row group a x column group b.
-namespace sd2 {
-__device__ __forceinline__ int upconv_group(int parity, int k) { return parity == 0 ? (k >= 1) : (k >= 2); }
-__global__ void __launch_bounds__(256) upconv_weff_build_kernel(const float* __restrict__ w9, bf16* __restrict__ weff, long long n) {
-  pdl_grid_sync();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float w[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) w[t] = w9[t * n + i];
-#pragma unroll
-    for (int ph = 0; ph < 4; ++ph) {
-      const int py = ph >> 1, px = ph & 1;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc[upconv_group(py, ky) * 2 + upconv_group(px, kx)] += w[ky * 3 + kx];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) weff[(ph * 4 + t) * n + i] = __float2bfloat16_rn(acc[t]);
-    }
-  }
-}
-// dw9[ky*3+kx] += sum over the four phases of dweff[phase][group tap that contains (ky, kx)]   (fp32, accumulating)
-__global__ void __launch_bounds__(256) upconv_wgrad_scatter_kernel(const float* __restrict__ dweff, float* __restrict__ dw9, long long n) {
-  pdl_grid_sync();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float d[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) d[t] = dweff[t * n + i];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        float g = 0.f;
-#pragma unroll
-        for (int ph = 0; ph < 4; ++ph) g += d[ph * 4 + upconv_group(ph >> 1, ky) * 2 + upconv_group(ph & 1, kx)];
-        dw9[(ky * 3 + kx) * n + i] += g;
-      }
-  }
-}
-}  // namespace sd2
 int sd2_upconv_weff_build(sd2_ctx* ctx, const float* w9, void* weff16, long long n, sd2_stream stream_) {
   if (!ctx) return 1;
   if (n <= 0) return fail(ctx, "upconv_weff_build: n <= 0");
