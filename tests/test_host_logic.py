@@ -262,6 +262,47 @@ def test_armed_optimizer_update_runs_bucket_by_bucket_inside_backward(dry):
     assert lib.calls['sd2_adamw_step'] - before == len(eng.buckets) + 2 and arena.armed_update is None
 
 
+def test_upsample_fold_tap_tables_reproduce_conv_of_the_upsampled_tensor():
+    """The host-side tap tables of the folded Upsample2D (ops.taps_upconv / taps_upconv_dgrad / _upconv_groups) restated on the
+    CPU: four 4-tap phase convolutions of the low-resolution input with group-summed weights equal conv3x3(nearest x2 (x)), and
+    the dgrad taps are their adjoint.  (The kernels are checked against torch on the GPU in tests/test_kernels_gpu.py.)"""
+    import torch.nn.functional as F
+    from diffusion_b200 import ops
+    torch.manual_seed(3)
+    B, C, Co, H, W = 2, 5, 4, 6, 7
+    x = torch.randn(B, C, H, W, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Co, C, 3, 3, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, padding=1)
+
+    def shifted(t, dh, dw):  # y[h, w] = t[h + dh, w + dw], zero outside
+        p = F.pad(t, (1, 1, 1, 1))
+        return p[:, :, 1 + dh:1 + dh + t.shape[2], 1 + dw:1 + dw + t.shape[3]]
+
+    def weff(ph, tap):
+        a, b = tap >> 1, tap & 1
+        kys, kxs = ops._upconv_groups(ph >> 1)[a][1], ops._upconv_groups(ph & 1)[b][1]
+        return sum(w[:, :, ky, kx] for ky in kys for kx in kxs)
+
+    out = torch.zeros_like(ref)
+    for ph in range(4):
+        taps = ops.taps_upconv(ph)
+        assert len(taps) == 4 and sorted(t[3] for t in taps) == [0, 1, 2, 3] and all(t[2] == 0 for t in taps)
+        plane = sum(torch.einsum('bchw,oc->bohw', shifted(x, dh, dw), weff(ph, t)) for dh, dw, _, t in taps)
+        out[:, :, (ph >> 1)::2, (ph & 1)::2] = plane
+    assert torch.allclose(out, ref, atol=1e-12)
+    # dgrad: dx = sum over phases and taps of the phase gradient shifted by (-dh, -dw) times weff^T
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    dx = torch.zeros_like(x)
+    for ph in range(4):
+        gp = g[:, :, (ph >> 1)::2, (ph & 1)::2]
+        fwd = {t: (dh, dw) for dh, dw, _, t in ops.taps_upconv(ph)}
+        for dh, dw, _, t in ops.taps_upconv_dgrad(ph):
+            assert (dh, dw) == (-fwd[t][0], -fwd[t][1])
+            dx = dx + torch.einsum('bohw,oc->bchw', shifted(gp, dh, dw), weff(ph, t))
+    assert torch.allclose(dx, x.grad, atol=1e-12)
+
+
 def test_low_precision_norm_surgery_finds_nothing_to_replace():
     """reference train.py:91-108 runs composer's module surgery over `model.unet`, replacing every nn.GroupNorm / nn.LayerNorm
     instance by a new module with new parameters; the product's norm holders must not be such instances (their parameters
