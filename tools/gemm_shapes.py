@@ -27,6 +27,8 @@ def diff(a, b):
 
 def main():
     if sys.argv[1] == '--diff':
+        import signal
+        signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `... --diff a b | head` ends quietly
         return diff(sys.argv[2], sys.argv[3])
     from diffusion_b200 import ops
     from diffusion_b200.model import stable_diffusion_2
